@@ -1,0 +1,184 @@
+/*
+ * slr_b200.h — C ABI of libslr_b200.so, the B200 (sm_100a) structured-light
+ * decode + stereo-match + triangulate engine.
+ *
+ * This is the drop-in boundary for the reference's reconstruction hot path
+ * (DrawZeroPoint/Structure-Light-Reconstructor @ 4a79a80).  The reference has no FFI layer:
+ * its boundary is the C++ class surface `Reconstruct` / `MFReconstruct` (Duke/reconstruct.h:14-42,
+ * Duke/mfreconstruct.h:12-20) that MainWindow::startreconstruct calls (Duke/mainwindow.cpp:562-652).
+ * The Qt-free facade classes in structure-light-reconstructor_b200/facade/ keep those names and
+ * call the entry points below; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *  - plain C: opaque handle, pointers and sizes only; no torch / OpenCV / Qt types.
+ *  - every entry point returns slr_status; slr_last_error() gives the text for the calling thread.
+ *  - one engine per GPU.  Calls are stream-ordered on the engine's stream (slr_set_stream) and
+ *    asynchronous unless stated; an engine is thread-compatible, not thread-safe.
+ *  - "d_" pointers are device memory on the engine's GPU, "h_" pointers are host memory.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Data layout (HBM):
+ *   image stacks   uint8  [batch][cam=2][N][H][W]   (cam 0 = left, 1 = right; rectified for the
+ *                                                   MF / Gray-EPI paths, raw for Gray-only)
+ *     MF   stack:  N = 2 + F*S; [0]=white, [1]=black, [2 + S*f + s] = frequency f, shift s
+ *                  (Duke/multifrequency.cpp:16-17,30; Duke/mfreconstruct.cpp:239-242)
+ *     Gray stack:  N = 2 + 2*nbits_col (+ 2*nbits_row); [0]=white, [1]=black,
+ *                  column bit c (MSB first) at [2+2c] (pattern) and [3+2c] (inverse), row bits after
+ *                  (Duke/graycodes.cpp:63-110; Duke/reconstruct.cpp:387-400, 349-360)
+ *   phase          float  [batch][2][H][W]   NaN where the pixel carries no phase
+ *   code           int32  [batch][2][H][W]   -1 where masked
+ *   mask / valid   uint8  same shape, 0/1
+ *   xyz            float  [batch][H][W][3]   NaN where no point (indexed by the LEFT pixel)
+ *   match_k        int32  [batch][H][W]      matched right column, -1 if none
+ */
+#ifndef SLR_B200_H
+#define SLR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SLR_API __attribute__((visibility("default")))
+#else
+#define SLR_API
+#endif
+
+typedef struct slr_engine slr_engine;
+
+typedef enum {
+    SLR_OK = 0,
+    SLR_ERR_INVALID = 1,     /* bad argument / unsupported shape */
+    SLR_ERR_CUDA = 2,        /* CUDA runtime error (or no device: there is no CPU fallback) */
+    SLR_ERR_STATE = 3,       /* call order (e.g. calibration not set) */
+    SLR_ERR_NOMEM = 4
+} slr_status;
+
+/* Decode arithmetic.  STRICT reproduces Duke/mfreconstruct.cpp:231-269 bit for bit (integer-division
+ * atan, PI = 3.1416f) and requires F=3, S=4.  CORRECTED is the physically
+ * meaningful atan2 + heterodyne cascade (no reference counterpart). */
+typedef enum { SLR_MODE_STRICT = 0, SLR_MODE_CORRECTED = 1 } slr_mode;
+
+/* The fields of the reference's VirtualCamera that the path reads (Duke/virtualcamera.h:27-37;
+ * all CV_32F there). */
+typedef struct {
+    float fc[2];   /* VirtualCamera::fc   */
+    float cc[2];   /* VirtualCamera::cc   */
+    float dist[5]; /* VirtualCamera::distortion (k1 k2 p1 p2 k3; k3 unused, Duke/utilities.cpp:66) */
+    float R[9];    /* VirtualCamera::rotationMatrix, row-major */
+    float t[3];    /* VirtualCamera::translationVector */
+} slr_camera;
+
+/* ---- engine --------------------------------------------------------------------------------- */
+
+/* One engine per GPU.  width/height = camera image size (Reconstruct::getParameters camw/camh,
+ * Duke/reconstruct.cpp:615-621); max_batch = scans per call the host-buffer entry points stage. */
+SLR_API slr_status slr_create(slr_engine **out, int device, int width, int height, int max_batch);
+SLR_API slr_status slr_destroy(slr_engine *e);
+/* Run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the engine's own stream. */
+SLR_API slr_status slr_set_stream(slr_engine *e, void *cuda_stream);
+SLR_API slr_status slr_synchronize(slr_engine *e);
+/* Replaces stereoRect::Q (Duke/stereorect.h:21), MFReconstruct/Reconstruct::cameras[2]
+ * (Duke/reconstruct.h:24) and the optional scan/transfer_mat<sn>.txt 3x4 matrix
+ * (Duke/mfreconstruct.cpp:276-282; NULL when scanSN == 0).  Also precomputes the per-pixel
+ * Utilities::undistortPoints maps (Duke/utilities.cpp:58-94) used by the MF emitter. */
+SLR_API slr_status slr_set_calib(slr_engine *e, const slr_camera cams[2], const double Q[16],
+                                 const float *rigid3x4);
+SLR_API const char *slr_last_error(void);
+SLR_API const char *slr_version(void);
+
+/* ---- pattern synthesis (host; rows a1, a2 of SURVEY.md §8) ------------------------------------- */
+/* GrayCodes::calNumOfImgs, Duke/graycodes.cpp:22-30 */
+SLR_API int slr_gray_num_bits(int n);
+SLR_API int slr_gray_num_imgs(int scan_w, int scan_h, int use_epi);
+/* GrayCodes::generateGrays, Duke/graycodes.cpp:55-114.  h_out = [nimgs][H][W] */
+SLR_API slr_status slr_generate_gray_patterns(uint8_t *h_out, int W, int H, int use_epi);
+/* MultiFrequency::generateMutiFreq, Duke/multifrequency.cpp:14-33.  h_out = [14][projH][projW] */
+SLR_API slr_status slr_generate_mf_patterns(uint8_t *h_out, int projW, int projH);
+
+/* ---- K1: multi-frequency phase decode -------------------------------------------------------- */
+/* MFReconstruct::computeShadows + decodePatterns + getPhase, Duke/mfreconstruct.cpp:190-269. */
+SLR_API slr_status slr_mf_decode(slr_engine *e, const uint8_t *d_stack, int batch, int F, int S,
+                                 int black_thr, int mode, float *d_phase, uint8_t *d_mask);
+
+/* ---- K2: Gray-code decode --------------------------------------------------------------------- */
+/* Reconstruct::computeShadows + decodePatterns_GE/getProjPixel_GE (nbits_row == 0) or
+ * decodePaterns/getProjPixel (nbits_row > 0) + GrayCodes::grayToDec,
+ * Duke/reconstruct.cpp:210-227, 79-97, 381-407, 56-74, 325-370; Duke/graycodes.cpp:116-128.
+ * d_row may be NULL when nbits_row == 0. */
+SLR_API slr_status slr_gray_decode(slr_engine *e, const uint8_t *d_stack, int batch,
+                                   int nbits_col, int nbits_row, int black_thr, int white_thr,
+                                   int scan_w, int scan_h,
+                                   int32_t *d_col, int32_t *d_row, uint8_t *d_mask);
+
+/* ---- K3a: phase match + Q-matrix triangulation ------------------------------------------------ */
+/* MFReconstruct::triangulation, Duke/mfreconstruct.cpp:272-334 (+ Utilities::undistortPoints).
+ * d_match_k and d_n_points may be NULL.  *d_n_points (device, one uint64) is ADDED to. */
+SLR_API slr_status slr_match_triangulate_phase(slr_engine *e, const float *d_phase, const uint8_t *d_mask,
+                                               int batch, float *d_xyz, uint8_t *d_valid,
+                                               int32_t *d_match_k, unsigned long long *d_n_points);
+
+/* ---- K3b: Gray-EPI code match + Q-matrix triangulation ---------------------------------------- */
+/* Reconstruct::triangulation_ge, Duke/reconstruct.cpp:555-611.  d_white = the [batch][2][H][W]
+ * white images when haveColor is on (else NULL, and d_color NULL). */
+SLR_API slr_status slr_match_triangulate_code(slr_engine *e, const int32_t *d_col, const uint8_t *d_mask,
+                                              int batch, const uint8_t *d_white,
+                                              float *d_xyz, uint8_t *d_valid, int32_t *d_match_k,
+                                              uint8_t *d_color, unsigned long long *d_n_points);
+
+/* ---- K3c: Gray-only projector-cell bucket triangulation ---------------------------------------- */
+/* Reconstruct::decodePaterns bucketing + Reconstruct::triangulation + cam2WorldSpace +
+ * Utilities::line_lineIntersection + PointCloudImage::addPoint,
+ * Duke/reconstruct.cpp:56-74, 417-481, 310-322; Duke/utilities.cpp:399-425; Duke/pointcloudimage.cpp:86-97.
+ * d_sum = float [batch][scan_w*scan_h][3] indexed by the reference's ac(x,y) = x*scan_h + y,
+ * d_cnt = uint8 [batch][scan_w*scan_h] (the reference's wrapping u8 point count). */
+SLR_API slr_status slr_bucket_triangulate(slr_engine *e, const int32_t *d_col, const int32_t *d_row,
+                                          const uint8_t *d_mask, int batch, int scan_w, int scan_h,
+                                          float *d_sum, uint8_t *d_cnt, unsigned long long *d_n_cells);
+
+/* ---- fused pipelines --------------------------------------------------------------------------- */
+/* MFReconstruct::runReconstruction minus image IO, Duke/mfreconstruct.cpp:160-187: one kernel reads
+ * each stack byte once and writes each output byte once (no phase round trip through HBM). */
+SLR_API slr_status slr_run_mf(slr_engine *e, const uint8_t *d_stack, int batch, int F, int S,
+                              int black_thr, int mode, float *d_xyz, uint8_t *d_valid,
+                              int32_t *d_match_k, unsigned long long *d_n_points);
+/* Reconstruct::runReconstruction_GE minus image IO, Duke/reconstruct.cpp:271-307. */
+SLR_API slr_status slr_run_ge(slr_engine *e, const uint8_t *d_stack, int batch, int nbits_col,
+                              int black_thr, int white_thr, int scan_w, int have_color,
+                              float *d_xyz, uint8_t *d_valid, int32_t *d_match_k, uint8_t *d_color,
+                              unsigned long long *d_n_points);
+
+/* ---- host-buffer entry points (what the facade classes call) ------------------------------------ */
+/* Same as slr_run_mf with HOST buffers: stages host->device copies, the kernels and the
+ * device->host copy of the cloud on the engine's streams, scan by scan, and returns when h_xyz /
+ * h_valid are complete.  batch may exceed max_batch (processed in chunks).  h_match_k may be NULL.
+ * Pinned host memory (slr_host_alloc) makes the copies asynchronous. */
+SLR_API slr_status slr_run_mf_host(slr_engine *e, const uint8_t *h_stack, int batch, int F, int S,
+                                   int black_thr, int mode, float *h_xyz, uint8_t *h_valid,
+                                   int32_t *h_match_k, unsigned long long *h_n_points);
+SLR_API slr_status slr_run_ge_host(slr_engine *e, const uint8_t *h_stack, int batch, int nbits_col,
+                                   int black_thr, int white_thr, int scan_w, int have_color,
+                                   float *h_xyz, uint8_t *h_valid, int32_t *h_match_k, uint8_t *h_color,
+                                   unsigned long long *h_n_points);
+SLR_API slr_status slr_host_alloc(void **out, size_t bytes); /* pinned */
+SLR_API slr_status slr_host_free(void *p);
+
+/* ---- synthetic scans (bench / smoke inputs) -------------------------------------- */
+/* Renders `batch` rectified stereo MF stacks of a plane+bump scene straight into device memory:
+ * d_stack = [batch][2][14][H][W].  integer_disparity != 0 makes left/right samples coincide exactly. */
+SLR_API slr_status slr_synth_mf(slr_engine *e, uint8_t *d_stack, int batch, int proj_w,
+                                unsigned seed, int integer_disparity, float noise_dn);
+/* d_stack = [batch][2][2+2*nbits_col][H][W] Gray-EPI stacks of the same scene family. */
+SLR_API slr_status slr_synth_gray(slr_engine *e, uint8_t *d_stack, int batch, int scan_w,
+                                  unsigned seed, int integer_disparity, float noise_dn);
+
+/* Number of kernels this library has launched on this engine since creation (bench accounting). */
+SLR_API unsigned long long slr_kernel_launches(const slr_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLR_B200_H */

@@ -1,0 +1,12 @@
+"""Import shim: `import slr_b200` loads the package directory `structure-light-reconstructor_b200/`
+(whose name carries a hyphen and so cannot be imported directly)."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "structure-light-reconstructor_b200")
+_spec = importlib.util.spec_from_file_location("slr_b200", os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["slr_b200"] = _mod
+_spec.loader.exec_module(_mod)

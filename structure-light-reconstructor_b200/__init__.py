@@ -1,0 +1,331 @@
+"""slr_b200 — Python host-side plumbing over the C ABI of libslr_b200.so (include/slr_b200.h).
+
+The product is the CUDA library; this module only (a) loads it with ctypes, (b) wraps the entry
+points so tests and bench.py can hand it torch device tensors / numpy host arrays, and (c) offers
+small helpers (synthetic calibration, numpy scene synthesis).  There is no CPU fallback: if the
+shared library is missing, importing `capi()` raises.
+
+Import as `import slr_b200` (the repo-root shim) — the directory name carries a hyphen.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libslr_b200.so")
+
+MODE_STRICT = 0
+MODE_CORRECTED = 1
+
+
+class SlrError(RuntimeError):
+    pass
+
+
+class CCamera(C.Structure):
+    """slr_camera (include/slr_b200.h) == the VirtualCamera fields the path reads."""
+    _fields_ = [("fc", C.c_float * 2), ("cc", C.c_float * 2), ("dist", C.c_float * 5),
+                ("R", C.c_float * 9), ("t", C.c_float * 3)]
+
+
+@dataclass
+class Camera:
+    fc: tuple = (2400.0, 2400.0)
+    cc: tuple = (640.0, 512.0)
+    dist: tuple = (0.0, 0.0, 0.0, 0.0, 0.0)
+    R: tuple = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0)
+    t: tuple = (0.0, 0.0, 0.0)
+
+    def to_c(self) -> CCamera:
+        c = CCamera()
+        c.fc[:] = [np.float32(v) for v in self.fc]
+        c.cc[:] = [np.float32(v) for v in self.cc]
+        c.dist[:] = [np.float32(v) for v in self.dist]
+        c.R[:] = [np.float32(v) for v in self.R]
+        c.t[:] = [np.float32(v) for v in self.t]
+        return c
+
+
+_lib = None
+
+# every symbol include/slr_b200.h declares (tests check the library exports each of them)
+EXPORTS = [
+    "slr_create", "slr_destroy", "slr_set_stream", "slr_synchronize", "slr_set_calib", "slr_last_error",
+    "slr_version", "slr_gray_num_bits", "slr_gray_num_imgs", "slr_generate_gray_patterns",
+    "slr_generate_mf_patterns", "slr_mf_decode", "slr_gray_decode", "slr_match_triangulate_phase",
+    "slr_match_triangulate_code", "slr_bucket_triangulate", "slr_run_mf", "slr_run_ge", "slr_run_mf_host",
+    "slr_run_ge_host", "slr_host_alloc", "slr_host_free", "slr_synth_mf", "slr_synth_gray",
+    "slr_kernel_launches",
+]
+
+
+def capi():
+    """Load libslr_b200.so and declare the prototypes.  Raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SlrError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, u32, u64p = C.c_void_p, C.c_int, C.c_uint, C.c_void_p
+    lib.slr_last_error.restype = C.c_char_p
+    lib.slr_version.restype = C.c_char_p
+    lib.slr_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32]
+    lib.slr_destroy.argtypes = [vp]
+    lib.slr_set_stream.argtypes = [vp, vp]
+    lib.slr_synchronize.argtypes = [vp]
+    lib.slr_set_calib.argtypes = [vp, C.POINTER(CCamera), C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    lib.slr_gray_num_bits.argtypes = [i32]
+    lib.slr_gray_num_imgs.argtypes = [i32, i32, i32]
+    lib.slr_generate_gray_patterns.argtypes = [vp, i32, i32, i32]
+    lib.slr_generate_mf_patterns.argtypes = [vp, i32, i32]
+    lib.slr_mf_decode.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
+    lib.slr_gray_decode.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.slr_match_triangulate_phase.argtypes = [vp, vp, vp, i32, vp, vp, vp, u64p]
+    lib.slr_match_triangulate_code.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, u64p]
+    lib.slr_bucket_triangulate.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, u64p]
+    lib.slr_run_mf.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, u64p]
+    lib.slr_run_ge.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, u64p]
+    lib.slr_run_mf_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, C.POINTER(C.c_ulonglong)]
+    lib.slr_run_ge_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp,
+                                    C.POINTER(C.c_ulonglong)]
+    lib.slr_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    lib.slr_host_free.argtypes = [vp]
+    lib.slr_synth_mf.argtypes = [vp, vp, i32, i32, u32, i32, C.c_float]
+    lib.slr_synth_gray.argtypes = [vp, vp, i32, i32, u32, i32, C.c_float]
+    lib.slr_kernel_launches.argtypes = [vp]
+    lib.slr_kernel_launches.restype = C.c_ulonglong
+    _lib = lib
+    return lib
+
+
+def _check(status: int, what: str):
+    if status != 0:
+        msg = capi().slr_last_error().decode("utf-8", "replace")
+        raise SlrError(f"{what} failed (status {status}): {msg}")
+
+
+def gray_num_bits(n: int) -> int:
+    return capi().slr_gray_num_bits(n)
+
+
+def generate_gray_patterns(W: int, H: int, use_epi: bool) -> np.ndarray:
+    """GrayCodes::generateGrays (Duke/graycodes.cpp:55-114) -> uint8 [nimgs, H, W]."""
+    lib = capi()
+    n = lib.slr_gray_num_imgs(W, H, int(use_epi))
+    out = np.empty((n, H, W), np.uint8)
+    _check(lib.slr_generate_gray_patterns(out.ctypes.data, W, H, int(use_epi)), "slr_generate_gray_patterns")
+    return out
+
+
+def generate_mf_patterns(projW: int, projH: int) -> np.ndarray:
+    """MultiFrequency::generateMutiFreq (Duke/multifrequency.cpp:14-33) -> uint8 [14, projH, projW]."""
+    out = np.empty((14, projH, projW), np.uint8)
+    _check(capi().slr_generate_mf_patterns(out.ctypes.data, projW, projH), "slr_generate_mf_patterns")
+    return out
+
+
+def synthetic_rig(W: int, H: int, f: float = 2400.0, tx: float = -200.0, distort: bool = True):
+    """A synthetic rectified rig: two cameras, Q as cv::stereoRectify lays it out.
+
+    Q = [[1,0,0,-cx],[0,1,0,-cy],[0,0,0,f],[0,0,-1/Tx,(cx-cx')/Tx]].
+    """
+    cx, cy = W / 2.0, H / 2.0
+    distL = (-0.12, 0.08, 0.0007, -0.0004, 0.0) if distort else (0.0,) * 5
+    distR = (-0.10, 0.05, -0.0005, 0.0006, 0.0) if distort else (0.0,) * 5
+    camL = Camera(fc=(f, f * 1.001), cc=(cx + 3.25, cy - 2.5), dist=distL)
+    camR = Camera(fc=(f * 0.999, f), cc=(cx - 1.75, cy + 1.25), dist=distR,
+                  R=(0.9998, 0.0, 0.02, 0.0, 1.0, 0.0, -0.02, 0.0, 0.9998), t=(tx, 0.0, 0.0))
+    Q = np.array([[1, 0, 0, -cx], [0, 1, 0, -cy], [0, 0, 0, f], [0, 0, -1.0 / tx, 0.0]], np.float64)
+    return [camL, camR], Q
+
+
+class Engine:
+    """One engine per GPU; thin torch-tensor wrapper over the C ABI.  Work is issued on torch's current
+    CUDA stream so torch.cuda.Event timing brackets the library's kernels."""
+
+    def __init__(self, width: int, height: int, max_batch: int = 1, device: int = 0):
+        import torch
+        self._torch = torch
+        self.lib = capi()
+        self.W, self.H, self.max_batch, self.device = width, height, max_batch, device
+        h = C.c_void_p()
+        _check(self.lib.slr_create(C.byref(h), device, width, height, max_batch), "slr_create")
+        self.h = h
+        self.dev = torch.device("cuda", device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.slr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _bind_stream(self):
+        s = self._torch.cuda.current_stream(self.dev).cuda_stream
+        _check(self.lib.slr_set_stream(self.h, C.c_void_p(s)), "slr_set_stream")
+
+    def _empty(self, shape, dtype):
+        return self._torch.empty(shape, dtype=dtype, device=self.dev)
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+    def launches(self) -> int:
+        return int(self.lib.slr_kernel_launches(self.h))
+
+    def synchronize(self):
+        _check(self.lib.slr_synchronize(self.h), "slr_synchronize")
+
+    def set_calib(self, cams, Q, rigid=None):
+        arr = (CCamera * 2)(cams[0].to_c(), cams[1].to_c())
+        q = np.ascontiguousarray(np.asarray(Q, np.float64).reshape(16))
+        r = None
+        if rigid is not None:
+            r = np.ascontiguousarray(np.asarray(rigid, np.float32).reshape(12))
+        self._bind_stream()
+        _check(self.lib.slr_set_calib(self.h, arr, q.ctypes.data_as(C.POINTER(C.c_double)),
+                                      r.ctypes.data_as(C.POINTER(C.c_float)) if r is not None else None),
+               "slr_set_calib")
+        self.synchronize()
+
+    # -- kernels ----------------------------------------------------------------------------
+    def mf_decode(self, stack, F=3, S=4, black_thr=40, mode=MODE_STRICT):
+        t = self._torch
+        B = stack.shape[0]
+        assert stack.dtype == t.uint8 and stack.is_contiguous() and tuple(stack.shape) == (B, 2, 2 + F * S, self.H, self.W)
+        phase = self._empty((B, 2, self.H, self.W), t.float32)
+        mask = self._empty((B, 2, self.H, self.W), t.uint8)
+        self._bind_stream()
+        _check(self.lib.slr_mf_decode(self.h, self._p(stack), B, F, S, black_thr, mode, self._p(phase), self._p(mask)),
+               "slr_mf_decode")
+        return phase, mask
+
+    def gray_decode(self, stack, nbits_col, nbits_row=0, black_thr=40, white_thr=0, scan_w=None, scan_h=None):
+        t = self._torch
+        B = stack.shape[0]
+        N = 2 + 2 * nbits_col + 2 * nbits_row
+        assert stack.dtype == t.uint8 and stack.is_contiguous() and tuple(stack.shape) == (B, 2, N, self.H, self.W)
+        col = self._empty((B, 2, self.H, self.W), t.int32)
+        row = self._empty((B, 2, self.H, self.W), t.int32) if nbits_row > 0 else None
+        mask = self._empty((B, 2, self.H, self.W), t.uint8)
+        self._bind_stream()
+        _check(self.lib.slr_gray_decode(self.h, self._p(stack), B, nbits_col, nbits_row, black_thr, white_thr,
+                                        scan_w if scan_w is not None else self.W,
+                                        scan_h if scan_h is not None else self.H,
+                                        self._p(col), self._p(row), self._p(mask)), "slr_gray_decode")
+        return col, row, mask
+
+    def _outputs(self, B, want_k=True, want_color=False):
+        t = self._torch
+        xyz = self._empty((B, self.H, self.W, 3), t.float32)
+        valid = self._empty((B, self.H, self.W), t.uint8)
+        k = self._empty((B, self.H, self.W), t.int32) if want_k else None
+        color = self._empty((B, self.H, self.W), t.uint8) if want_color else None
+        n = t.zeros(1, dtype=t.int64, device=self.dev)
+        return xyz, valid, k, color, n
+
+    def match_triangulate_phase(self, phase, mask, want_k=True):
+        B = phase.shape[0]
+        xyz, valid, k, _, n = self._outputs(B, want_k)
+        self._bind_stream()
+        _check(self.lib.slr_match_triangulate_phase(self.h, self._p(phase), self._p(mask), B, self._p(xyz),
+                                                    self._p(valid), self._p(k), self._p(n)),
+               "slr_match_triangulate_phase")
+        return xyz, valid, k, n
+
+    def match_triangulate_code(self, col, mask, white=None, want_k=True):
+        B = col.shape[0]
+        xyz, valid, k, color, n = self._outputs(B, want_k, white is not None)
+        self._bind_stream()
+        _check(self.lib.slr_match_triangulate_code(self.h, self._p(col), self._p(mask), B, self._p(white),
+                                                   self._p(xyz), self._p(valid), self._p(k), self._p(color),
+                                                   self._p(n)), "slr_match_triangulate_code")
+        return xyz, valid, k, color, n
+
+    def bucket_triangulate(self, col, row, mask, scan_w, scan_h):
+        t = self._torch
+        B = col.shape[0]
+        ssum = self._empty((B, scan_w * scan_h, 3), t.float32)
+        cnt = self._empty((B, scan_w * scan_h), t.uint8)
+        n = t.zeros(1, dtype=t.int64, device=self.dev)
+        self._bind_stream()
+        _check(self.lib.slr_bucket_triangulate(self.h, self._p(col), self._p(row), self._p(mask), B, scan_w, scan_h,
+                                               self._p(ssum), self._p(cnt), self._p(n)), "slr_bucket_triangulate")
+        return ssum, cnt, n
+
+    def run_mf(self, stack, F=3, S=4, black_thr=40, mode=MODE_STRICT, want_k=True, out=None):
+        B = stack.shape[0]
+        xyz, valid, k, _, n = out if out is not None else self._outputs(B, want_k)
+        self._bind_stream()
+        _check(self.lib.slr_run_mf(self.h, self._p(stack), B, F, S, black_thr, mode, self._p(xyz), self._p(valid),
+                                   self._p(k), self._p(n)), "slr_run_mf")
+        return xyz, valid, k, n
+
+    def run_ge(self, stack, nbits_col, black_thr=40, white_thr=0, scan_w=None, have_color=False, want_k=True,
+               out=None):
+        B = stack.shape[0]
+        xyz, valid, k, color, n = out if out is not None else self._outputs(B, want_k, have_color)
+        self._bind_stream()
+        _check(self.lib.slr_run_ge(self.h, self._p(stack), B, nbits_col, black_thr, white_thr,
+                                   scan_w if scan_w is not None else self.W, int(have_color), self._p(xyz),
+                                   self._p(valid), self._p(k), self._p(color), self._p(n)), "slr_run_ge")
+        return xyz, valid, k, color, n
+
+    # -- host-buffer entry points (numpy or pinned torch CPU tensors) ---------------------------
+    @staticmethod
+    def _hp(a):
+        if a is None:
+            return C.c_void_p(0)
+        if isinstance(a, np.ndarray):
+            return C.c_void_p(a.ctypes.data)
+        return C.c_void_p(a.data_ptr())
+
+    def run_mf_host(self, h_stack, h_xyz, h_valid, h_k=None, F=3, S=4, black_thr=40, mode=MODE_STRICT) -> int:
+        B = h_stack.shape[0]
+        n = C.c_ulonglong(0)
+        self._bind_stream()
+        _check(self.lib.slr_run_mf_host(self.h, self._hp(h_stack), B, F, S, black_thr, mode, self._hp(h_xyz),
+                                        self._hp(h_valid), self._hp(h_k), C.byref(n)), "slr_run_mf_host")
+        return int(n.value)
+
+    def run_ge_host(self, h_stack, h_xyz, h_valid, h_k=None, h_color=None, nbits_col=11, black_thr=40, white_thr=0,
+                    scan_w=None) -> int:
+        B = h_stack.shape[0]
+        n = C.c_ulonglong(0)
+        self._bind_stream()
+        _check(self.lib.slr_run_ge_host(self.h, self._hp(h_stack), B, nbits_col, black_thr, white_thr,
+                                        scan_w if scan_w is not None else self.W, int(h_color is not None),
+                                        self._hp(h_xyz), self._hp(h_valid), self._hp(h_k), self._hp(h_color),
+                                        C.byref(n)), "slr_run_ge_host")
+        return int(n.value)
+
+    # -- synthetic inputs ---------------------------------------------------------------------
+    def synth_mf(self, batch, proj_w=None, seed=0, integer_disparity=True, noise_dn=0.0):
+        t = self._torch
+        stack = self._empty((batch, 2, 14, self.H, self.W), t.uint8)
+        self._bind_stream()
+        _check(self.lib.slr_synth_mf(self.h, self._p(stack), batch, proj_w or self.W, seed, int(integer_disparity),
+                                     float(noise_dn)), "slr_synth_mf")
+        return stack
+
+    def synth_gray(self, batch, scan_w=None, seed=0, integer_disparity=True, noise_dn=0.0):
+        t = self._torch
+        scan_w = scan_w or self.W
+        nb = gray_num_bits(scan_w)
+        stack = self._empty((batch, 2, 2 + 2 * nb, self.H, self.W), t.uint8)
+        self._bind_stream()
+        _check(self.lib.slr_synth_gray(self.h, self._p(stack), batch, scan_w, seed, int(integer_disparity),
+                                       float(noise_dn)), "slr_synth_gray")
+        return stack

@@ -1,0 +1,219 @@
+// k1_mf_decode.cu — K1: shadow mask + multi-frequency phase decode + heterodyne unwrap.
+// Replaces MFReconstruct::computeShadows / decodePatterns / getPhase (Duke/mfreconstruct.cpp:190-269).
+//
+// HBM-bound streaming kernel: each thread owns 16 consecutive pixels of one camera view, issues all
+// N = 2 + F*S 128-bit plane loads up front (ld.global.nc, L1 no-allocate), decodes in registers and
+// writes 4 x float4 phase + 1 x uint4 mask.  Algorithmic traffic: N + 4 + 1 bytes per pixel.
+#include "slr_device.cuh"
+
+namespace {
+
+constexpr int K1_THREADS = 256;
+
+__device__ __forceinline__ int byte_of(const uint4 &v, int i)
+{
+    const uint32_t w = (i < 4) ? v.x : (i < 8) ? v.y : (i < 12) ? v.z : v.w;
+    return (int)((w >> (8 * (i & 3))) & 0xffu);
+}
+
+// strict mode, F = 3, S = 4, 16 pixels per thread
+__global__ void __launch_bounds__(K1_THREADS)
+k1_mf_decode_strict(const uint8_t *__restrict__ stack, size_t P, long long chunks_per_view, long long total_chunks,
+                    int black_thr, const float *__restrict__ g_lut, float *__restrict__ phase,
+                    uint8_t *__restrict__ mask)
+{
+    __shared__ float lut[SLR_ATAN_LUT_SIZE + 1];
+    for (int i = threadIdx.x; i < SLR_ATAN_LUT_SIZE; i += K1_THREADS) lut[i] = g_lut[i];
+    __syncthreads();
+
+    for (long long chunk = (long long)blockIdx.x * K1_THREADS + threadIdx.x; chunk < total_chunks;
+         chunk += (long long)gridDim.x * K1_THREADS) {
+        const long long view = chunk / chunks_per_view;
+        const long long c = chunk - view * chunks_per_view;
+        const uint8_t *src = stack + (size_t)view * 14 * P + (size_t)c * 16;
+        uint4 img[14];
+#pragma unroll
+        for (int n = 0; n < 14; n++) img[n] = slr::ldg_stream_u4(src + (size_t)n * P);
+
+        float ph[16];
+        uint32_t mk[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            // computeShadows (:199-204): white - black > blackThreshold
+            bool m = (byte_of(img[0], i) - byte_of(img[1], i)) > black_thr;
+            int G[12];
+#pragma unroll
+            for (int n = 0; n < 12; n++) G[n] = byte_of(img[2 + n], i);
+            float p;
+            const bool ok = slr::phase_strict(G, lut, p);
+            m = m && ok;
+            ph[i] = m ? p : slr::qnan();
+            mk[i >> 2] |= (m ? 1u : 0u) << (8 * (i & 3));
+        }
+        const size_t o = (size_t)view * P + (size_t)c * 16;
+#pragma unroll
+        for (int v = 0; v < 4; v++)
+            slr::stg_stream_f4(phase + o + 4 * v, make_float4(ph[4 * v], ph[4 * v + 1], ph[4 * v + 2], ph[4 * v + 3]));
+        slr::stg_stream_u4(mask + o, make_uint4(mk[0], mk[1], mk[2], mk[3]));
+    }
+}
+
+// strict mode, scalar fallback for P % 16 != 0 (one pixel per thread)
+__global__ void __launch_bounds__(K1_THREADS)
+k1_mf_decode_strict_scalar(const uint8_t *__restrict__ stack, size_t P, long long total, int black_thr,
+                           const float *__restrict__ g_lut, float *__restrict__ phase, uint8_t *__restrict__ mask)
+{
+    __shared__ float lut[SLR_ATAN_LUT_SIZE + 1];
+    for (int i = threadIdx.x; i < SLR_ATAN_LUT_SIZE; i += K1_THREADS) lut[i] = g_lut[i];
+    __syncthreads();
+    for (long long idx = (long long)blockIdx.x * K1_THREADS + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * K1_THREADS) {
+        const long long view = idx / (long long)P;
+        const size_t p = (size_t)(idx - view * (long long)P);
+        const uint8_t *src = stack + (size_t)view * 14 * P + p;
+        bool m = ((int)src[0] - (int)src[P]) > black_thr;
+        int G[12];
+#pragma unroll
+        for (int n = 0; n < 12; n++) G[n] = src[(size_t)(2 + n) * P];
+        float ph;
+        const bool ok = slr::phase_strict(G, lut, ph);
+        m = m && ok;
+        phase[idx] = m ? ph : slr::qnan();
+        mask[idx] = m ? 1 : 0;
+    }
+}
+
+// corrected mode, generic F (<= 8) and S (3..16): 4 pixels per thread (32-bit loads).
+struct CorrectedCoef {
+    float cs[16];
+    float sn[16];
+};
+
+template <int PX>
+__global__ void __launch_bounds__(K1_THREADS)
+k1_mf_decode_corrected(const uint8_t *__restrict__ stack, size_t P, long long chunks_per_view, long long total_chunks,
+                       int F, int S, int black_thr, CorrectedCoef coef, float *__restrict__ phase,
+                       uint8_t *__restrict__ mask)
+{
+    const int N = 2 + F * S;
+    for (long long chunk = (long long)blockIdx.x * K1_THREADS + threadIdx.x; chunk < total_chunks;
+         chunk += (long long)gridDim.x * K1_THREADS) {
+        const long long view = chunk / chunks_per_view;
+        const long long c = chunk - view * chunks_per_view;
+        const uint8_t *src = stack + (size_t)view * N * P + (size_t)c * PX;
+        uint32_t wv, bv;
+        if (PX == 4) {
+            wv = slr::ldg_stream_u32(src);
+            bv = slr::ldg_stream_u32(src + P);
+        } else {
+            wv = src[0];
+            bv = src[P];
+        }
+        float lvl[8][PX];
+        bool ok[PX];
+#pragma unroll
+        for (int i = 0; i < PX; i++) ok[i] = (int)((wv >> (8 * i)) & 0xff) - (int)((bv >> (8 * i)) & 0xff) > black_thr;
+        for (int f = 0; f < F; f++) {
+            float num[PX], den[PX];
+            int inum[PX], iden[PX];
+#pragma unroll
+            for (int i = 0; i < PX; i++) num[i] = den[i] = 0.0f, inum[i] = iden[i] = 0;
+            for (int s = 0; s < S; s++) {
+                const uint8_t *pp = src + (size_t)(2 + S * f + s) * P;
+                const uint32_t v = (PX == 4) ? slr::ldg_stream_u32(pp) : (uint32_t)pp[0];
+#pragma unroll
+                for (int i = 0; i < PX; i++) {
+                    const int g = (int)((v >> (8 * i)) & 0xff);
+                    if (S == 4) {  // exact integer form: num = G4-G2, den = G1-G3
+                        inum[i] += (s == 3) ? g : (s == 1) ? -g : 0;
+                        iden[i] += (s == 0) ? g : (s == 2) ? -g : 0;
+                    } else {
+                        num[i] = __fsub_rn(num[i], __fmul_rn((float)g, coef.sn[s]));
+                        den[i] = __fadd_rn(den[i], __fmul_rn((float)g, coef.cs[s]));
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < PX; i++) {
+                float nn = num[i], dd = den[i];
+                if (S == 4) {
+                    nn = (float)inum[i];
+                    dd = (float)iden[i];
+                    if (inum[i] == 0 && iden[i] == 0) ok[i] = false;
+                } else if (__fadd_rn(__fmul_rn(nn, nn), __fmul_rn(dd, dd)) < 0.25f) {
+                    ok[i] = false;
+                }
+                float ph = atan2f(nn, dd);
+                if (ph < 0.0f) ph = __fadd_rn(ph, SLR_TWO_PI_F);
+                lvl[f][i] = ph;
+            }
+        }
+        for (int n = F; n > 1; n--)
+            for (int j = 0; j + 1 < n; j++)
+#pragma unroll
+                for (int i = 0; i < PX; i++) lvl[j][i] = slr::wrap_2pi(__fsub_rn(lvl[j][i], lvl[j + 1][i]));
+        const size_t o = (size_t)view * P + (size_t)c * PX;
+#pragma unroll
+        for (int i = 0; i < PX; i++) {
+            const float p = __fmul_rn(__fdiv_rn(lvl[0][i], SLR_TWO_PI_F), 255.0f);
+            phase[o + i] = ok[i] ? p : slr::qnan();
+            mask[o + i] = ok[i] ? 1 : 0;
+        }
+    }
+}
+
+}  // namespace
+
+slr_status slr_launch_mf_decode(slr_engine *e, const uint8_t *d_stack, int views, int F, int S, int black_thr,
+                                int mode, float *d_phase, uint8_t *d_mask)
+{
+    const size_t P = (size_t)e->W * e->H;
+    if (mode == SLR_MODE_STRICT) {
+        SLR_REQUIRE(F == 3 && S == 4, "strict mode reproduces the reference's hard-coded 3 frequencies x 4 steps "
+                                      "(Duke/mfreconstruct.cpp:237); got F=%d S=%d", F, S);
+        const bool vec = (P % 16 == 0) && (((uintptr_t)d_stack | (uintptr_t)d_phase | (uintptr_t)d_mask) % 16 == 0);
+        if (vec) {
+            const long long cpv = (long long)(P / 16);
+            const long long total = cpv * views;
+            long long blocks = (total + K1_THREADS - 1) / K1_THREADS;
+            const long long cap = (long long)e->num_sms * 32;
+            if (blocks > cap) blocks = cap;
+            if (blocks < 1) blocks = 1;
+            k1_mf_decode_strict<<<(unsigned)blocks, K1_THREADS, 0, e->stream>>>(d_stack, P, cpv, total, black_thr,
+                                                                                e->d_atan_lut, d_phase, d_mask);
+        } else {
+            const long long total = (long long)P * views;
+            long long blocks = (total + K1_THREADS - 1) / K1_THREADS;
+            const long long cap = (long long)e->num_sms * 32;
+            if (blocks > cap) blocks = cap;
+            if (blocks < 1) blocks = 1;
+            k1_mf_decode_strict_scalar<<<(unsigned)blocks, K1_THREADS, 0, e->stream>>>(d_stack, P, total, black_thr,
+                                                                                       e->d_atan_lut, d_phase, d_mask);
+        }
+        SLR_CHECK_LAUNCH(e);
+        return SLR_OK;
+    }
+    SLR_REQUIRE(mode == SLR_MODE_CORRECTED, "unknown mode %d", mode);
+    SLR_REQUIRE(F >= 1 && F <= 8 && S >= 3 && S <= 16, "corrected mode supports 1<=F<=8, 3<=S<=16; got F=%d S=%d", F, S);
+    CorrectedCoef coef;
+    for (int s = 0; s < 16; s++) {
+        coef.cs[s] = (s < S) ? (float)cos(2.0 * 3.14159265358979323846 * s / S) : 0.0f;
+        coef.sn[s] = (s < S) ? (float)sin(2.0 * 3.14159265358979323846 * s / S) : 0.0f;
+    }
+    const bool vec = (P % 4 == 0) && (((uintptr_t)d_stack) % 4 == 0);
+    const int px = vec ? 4 : 1;
+    const long long cpv = (long long)(P / px);
+    const long long total = cpv * views;
+    long long blocks = (total + K1_THREADS - 1) / K1_THREADS;
+    const long long cap = (long long)e->num_sms * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (vec)
+        k1_mf_decode_corrected<4><<<(unsigned)blocks, K1_THREADS, 0, e->stream>>>(d_stack, P, cpv, total, F, S,
+                                                                                  black_thr, coef, d_phase, d_mask);
+    else
+        k1_mf_decode_corrected<1><<<(unsigned)blocks, K1_THREADS, 0, e->stream>>>(d_stack, P, cpv, total, F, S,
+                                                                                  black_thr, coef, d_phase, d_mask);
+    SLR_CHECK_LAUNCH(e);
+    return SLR_OK;
+}

@@ -1,0 +1,241 @@
+// slr_device.cuh — device-side building blocks shared by the sm_100a kernels:
+//   * strict-mode (reference-exact) and corrected-mode phase arithmetic
+//   * the match predicate and the Q-matrix emitter
+//   * mbarrier / TMA-bulk (cp.async.bulk) wrappers and streaming load/store helpers
+//
+// Strict-mode arithmetic uses the explicit round-to-nearest intrinsics (__fadd_rn, __dadd_rn, ...)
+// so nvcc can never contract a multiply-add into an FMA: results are bit-identical to the IEEE
+// evaluation of the reference expressions (Duke/mfreconstruct.cpp:231-269) on the host.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "slr_internal.h"
+
+namespace slr {
+
+__device__ __forceinline__ float qnan() { return __uint_as_float(SLR_QNAN_BITS); }
+
+// ------------------------------------------------------------------------------------------------
+// streaming global memory access
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream_u4(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u32(const void *p)
+{
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_u4(void *p, uint4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void stg_stream_f4(void *p, float4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier + TMA bulk copies (1-D cp.async.bulk; SASS: UBLKCP / SYNCS)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global bulk copy (bulk async-group completion)
+__device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the smem sources of all but the newest `N` bulk groups have been read
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all()
+{
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// make generic-proxy smem writes visible to the async proxy (before a bulk store reads them)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// strict mode: Duke/mfreconstruct.cpp:231-269
+// ------------------------------------------------------------------------------------------------
+#define SLR_ATAN_LUT_SIZE 511
+
+// Wrapped phase of one frequency from a = G4-G2 and b = G1-G3 (:246-261, first matching branch wins).
+// lut[q+255] = atan(float(q)).  Returns false on the degenerate branch (:254-255).
+__device__ __forceinline__ bool wrapped_phase_strict(int a, int b, const float *__restrict__ lut, float &P)
+{
+    constexpr float PI = SLR_PI_DEC;
+    constexpr float PI_3_2 = 3.0f * SLR_PI_DEC / 2.0f;  // 3*PI/2  (:250)
+    constexpr float PI_1_2 = SLR_PI_DEC / 2.0f;          // PI/2    (:252)
+    constexpr float PI_2 = 2.0f * SLR_PI_DEC;            // 2*PI    (:259)
+    if (a == 0) {
+        if (b == 0) return false;
+        P = (b > 0) ? 0.0f : PI;
+        return true;
+    }
+    if (b == 0) {
+        P = (a > 0) ? PI_3_2 : PI_1_2;
+        return true;
+    }
+    // C++ int division (truncation toward zero).  |a|,|b| <= 255: a non-integer quotient is at least
+    // 1/255 away from the nearest integer, so truncating the correctly rounded float quotient is exact.
+    const int q = __float2int_rz(__fdiv_rn((float)a, (float)b));
+    const float at = lut[q + 255];
+    if (b < 0)
+        P = __fadd_rn(at, PI);
+    else if (a > 0)
+        P = __fadd_rn(at, PI_2);
+    else
+        P = at;
+    return true;
+}
+
+// Heterodyne of :265-268.  P12/P23 are computed in double and narrowed; P123 and the scale in float.
+__device__ __forceinline__ float heterodyne_strict(float P0, float P1, float P2)
+{
+    constexpr float PI_2 = 2.0f * SLR_PI_DEC;
+    const double d01 = __dsub_rn((double)P0, (double)P1);
+    const double d12 = __dsub_rn((double)P1, (double)P2);
+    const float P12 = __double2float_rn((P0 > P1) ? d01 : __dadd_rn(d01, (double)PI_2));
+    const float P23 = __double2float_rn((P1 > P2) ? d12 : __dadd_rn(d12, (double)PI_2));
+    const float d = __fsub_rn(P12, P23);
+    const float P123 = (P12 > P23) ? d : __fadd_rn(d, PI_2);
+    return __fmul_rn(__fdiv_rn(P123, PI_2), 255.0f);
+}
+
+// One pixel, G[4*f+s] as ints.  Returns false if the pixel is dropped (degenerate branch).
+__device__ __forceinline__ bool phase_strict(const int (&G)[12], const float *__restrict__ lut, float &phase)
+{
+    float P[3];
+    bool ok = true;
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+        float p = 0.0f;
+        ok &= wrapped_phase_strict(G[4 * f + 3] - G[4 * f + 1], G[4 * f + 0] - G[4 * f + 2], lut, p);
+        P[f] = p;
+    }
+    phase = heterodyne_strict(P[0], P[1], P[2]);
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// corrected mode (atan2 + cascade of wrapped differences; no reference counterpart)
+// ------------------------------------------------------------------------------------------------
+#define SLR_TWO_PI_F 6.28318530717958647692f
+
+__device__ __forceinline__ float wrap_2pi(float d) { return (d < 0.0f) ? __fadd_rn(d, SLR_TWO_PI_F) : d; }
+
+// ------------------------------------------------------------------------------------------------
+// match predicate: Duke/mfreconstruct.cpp:295  fabs(pL - pR) < 0.1  (float difference, float fabs,
+// compared against the double 0.1 — equivalent to the float compare against 0.1f because
+// pred(0.1f) < 0.1 < 0.1f).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool phase_match(float pl, float pr) { return fabsf(__fsub_rn(pl, pr)) < 0.1f; }
+
+// Bucket of width 1/8 (> 0.1): any pR matching pL lies in bucket(pL)-1 .. bucket(pL)+1.
+// Saturating conversion keeps huge / infinite phases in the end buckets (still adjacent-safe).
+__device__ __forceinline__ int phase_bucket(float p) { return __float2int_rd(__fmul_rn(p, 8.0f)); }
+
+// ------------------------------------------------------------------------------------------------
+// emitters
+// ------------------------------------------------------------------------------------------------
+// p = Q * [x y d 1]^T in double (sums left to right), /w, narrowed to float, then the optional
+// 3x4 rigid transform.  Duke/mfreconstruct.cpp:299-323, Duke/reconstruct.cpp:570-594.
+__device__ __forceinline__ void reproject_q(const slr_calib_dev &c, double x, double y, double d, float &ox,
+                                            float &oy, float &oz)
+{
+    double r[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double s = __dmul_rn(c.Q[4 * i + 0], x);
+        s = __dadd_rn(s, __dmul_rn(c.Q[4 * i + 1], y));
+        s = __dadd_rn(s, __dmul_rn(c.Q[4 * i + 2], d));
+        s = __dadd_rn(s, __dmul_rn(c.Q[4 * i + 3], 1.0));
+        r[i] = s;
+    }
+    float px = __double2float_rn(__ddiv_rn(r[0], r[3]));
+    float py = __double2float_rn(__ddiv_rn(r[1], r[3]));
+    float pz = __double2float_rn(__ddiv_rn(r[2], r[3]));
+    if (c.has_rigid) {
+        float o[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            double s = __dmul_rn((double)c.rigid[4 * i + 0], (double)px);
+            s = __dadd_rn(s, __dmul_rn((double)c.rigid[4 * i + 1], (double)py));
+            s = __dadd_rn(s, __dmul_rn((double)c.rigid[4 * i + 2], (double)pz));
+            s = __dadd_rn(s, __dmul_rn((double)c.rigid[4 * i + 3], 1.0));
+            o[i] = __double2float_rn(s);
+        }
+        px = o[0];
+        py = o[1];
+        pz = o[2];
+    }
+    ox = px;
+    oy = py;
+    oz = pz;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u32(unsigned v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace slr

@@ -1,0 +1,524 @@
+// slr_engine.cu — engine lifetime, calibration upload, the extern "C" entry points of
+// include/slr_b200.h, host-side pattern synthesis and the host-buffer (end-to-end) pipelines.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "slr_internal.h"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void slr_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *slr_last_error(void) { return g_err; }
+extern "C" const char *slr_version(void) { return "slr_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------------
+static void free_engine(slr_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaFree(e->d_undist_lx);
+    cudaFree(e->d_undist_ly);
+    cudaFree(e->d_undist_rx);
+    cudaFree(e->d_atan_lut);
+    cudaFree(e->d_phase);
+    cudaFree(e->d_code);
+    cudaFree(e->d_mask);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(e->d_stage_in[i]);
+        cudaFree(e->d_stage_xyz[i]);
+        cudaFree(e->d_stage_valid[i]);
+        cudaFree(e->d_stage_k[i]);
+        cudaFree(e->d_stage_color[i]);
+        if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
+        if (e->ev_k[i]) cudaEventDestroy(e->ev_k[i]);
+        if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
+    }
+    cudaFree(e->d_counter);
+    if (e->h_counter) cudaFreeHost(e->h_counter);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->copy_in) cudaStreamDestroy(e->copy_in);
+    if (e->copy_out) cudaStreamDestroy(e->copy_out);
+    delete e;
+}
+
+extern "C" slr_status slr_create(slr_engine **out, int device, int width, int height, int max_batch)
+{
+    SLR_REQUIRE(out != nullptr, "slr_create: out is NULL");
+    *out = nullptr;
+    SLR_REQUIRE(width > 0 && height > 0 && max_batch > 0, "slr_create: bad size %dx%d batch %d", width, height, max_batch);
+    SLR_REQUIRE(width <= 65535 && height <= 65535, "slr_create: image larger than 65535 not supported");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        slr_set_error("slr_create: no CUDA device (%s); libslr_b200 has no CPU fallback",
+                      ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0");
+        return SLR_ERR_CUDA;
+    }
+    SLR_REQUIRE(device >= 0 && device < ndev, "slr_create: device %d out of range (%d devices)", device, ndev);
+    SLR_CHECK_CUDA(cudaSetDevice(device));
+    slr_engine *e = new (std::nothrow) slr_engine();
+    if (!e) {
+        slr_set_error("slr_create: out of host memory");
+        return SLR_ERR_NOMEM;
+    }
+    e->device = device;
+    e->W = width;
+    e->H = height;
+    e->max_batch = max_batch;
+    cudaDeviceProp prop;
+    cudaError_t err = cudaGetDeviceProperties(&prop, device);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && err == cudaSuccess; i++) {
+        err = cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming);
+    }
+    const size_t P = (size_t)width * height;
+    if (err == cudaSuccess) err = cudaMalloc(&e->d_undist_lx, P * sizeof(float));
+    if (err == cudaSuccess) err = cudaMalloc(&e->d_undist_ly, P * sizeof(float));
+    if (err == cudaSuccess) err = cudaMalloc(&e->d_undist_rx, P * sizeof(float));
+    if (err == cudaSuccess) err = cudaMalloc(&e->d_atan_lut, 512 * sizeof(float));
+    if (err == cudaSuccess) err = cudaMalloc(&e->d_counter, sizeof(unsigned long long));
+    if (err == cudaSuccess) err = cudaMallocHost(&e->h_counter, sizeof(unsigned long long));
+    if (err == cudaSuccess) {
+        // atan(float(q)), q = (G4-G2)/(G1-G3) in C++ int division (Duke/mfreconstruct.cpp:257-261):
+        // only 511 arguments exist, so the table is built with the host libm and the device result
+        // is bit-identical to the host evaluation.
+        float lut[512];
+        for (int q = -255; q <= 255; q++) lut[q + 255] = atanf((float)q);
+        lut[511] = 0.0f;
+        err = cudaMemcpy(e->d_atan_lut, lut, sizeof(lut), cudaMemcpyHostToDevice);
+    }
+    if (err != cudaSuccess) {
+        slr_set_error("slr_create: %s", cudaGetErrorString(err));
+        free_engine(e);
+        return SLR_ERR_CUDA;
+    }
+    e->num_sms = prop.multiProcessorCount;
+    e->stream = e->own_stream;
+    *out = e;
+    return SLR_OK;
+}
+
+extern "C" slr_status slr_destroy(slr_engine *e)
+{
+    if (!e) return SLR_OK;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    free_engine(e);
+    return SLR_OK;
+}
+
+extern "C" slr_status slr_set_stream(slr_engine *e, void *cuda_stream)
+{
+    SLR_REQUIRE(e != nullptr, "slr_set_stream: engine is NULL");
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return SLR_OK;
+}
+
+extern "C" slr_status slr_synchronize(slr_engine *e)
+{
+    SLR_REQUIRE(e != nullptr, "slr_synchronize: engine is NULL");
+    SLR_CHECK_CUDA(cudaSetDevice(e->device));
+    SLR_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    return SLR_OK;
+}
+
+extern "C" unsigned long long slr_kernel_launches(const slr_engine *e) { return e ? e->launches : 0ULL; }
+
+extern "C" slr_status slr_set_calib(slr_engine *e, const slr_camera cams[2], const double Q[16],
+                                    const float *rigid3x4)
+{
+    SLR_REQUIRE(e && cams && Q, "slr_set_calib: NULL argument");
+    SLR_CHECK_CUDA(cudaSetDevice(e->device));
+    e->cams[0] = cams[0];
+    e->cams[1] = cams[1];
+    memcpy(e->calib.Q, Q, sizeof(double) * 16);
+    e->calib.has_rigid = rigid3x4 ? 1 : 0;
+    memset(e->calib.rigid, 0, sizeof(e->calib.rigid));
+    if (rigid3x4) memcpy(e->calib.rigid, rigid3x4, sizeof(float) * 12);
+    slr_status st = slr_launch_undistort_maps(e);
+    if (st != SLR_OK) return st;
+    e->calib_set = true;
+    return SLR_OK;
+}
+
+static slr_status ensure_scratch(slr_engine *e, bool need_phase, bool need_code)
+{
+    const size_t n = (size_t)e->max_batch * 2 * e->W * e->H;
+    if (!e->d_mask) SLR_CHECK_CUDA(cudaMalloc(&e->d_mask, n));
+    if (need_phase && !e->d_phase) SLR_CHECK_CUDA(cudaMalloc(&e->d_phase, n * sizeof(float)));
+    if (need_code && !e->d_code) SLR_CHECK_CUDA(cudaMalloc(&e->d_code, n * sizeof(int32_t)));
+    return SLR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side pattern synthesis (a1, a2)
+// ------------------------------------------------------------------------------------------------
+extern "C" int slr_gray_num_bits(int n)
+{
+    // GrayCodes::calNumOfImgs: (int)ceil(log(double(n))/log(2.0))   Duke/graycodes.cpp:24-25
+    return n > 0 ? (int)ceil(log((double)n) / log(2.0)) : 0;
+}
+
+extern "C" int slr_gray_num_imgs(int scan_w, int scan_h, int use_epi)
+{
+    const int nc = slr_gray_num_bits(scan_w), nr = slr_gray_num_bits(scan_h);
+    return use_epi ? 2 + 2 * nc : 2 + 2 * nc + 2 * nr;
+}
+
+extern "C" slr_status slr_generate_gray_patterns(uint8_t *h_out, int W, int H, int use_epi)
+{
+    SLR_REQUIRE(h_out && W > 0 && H > 0, "slr_generate_gray_patterns: bad argument");
+    const int nc = slr_gray_num_bits(W), nr = slr_gray_num_bits(H);
+    const size_t P = (size_t)W * H;
+    memset(h_out, 255, P);
+    memset(h_out + P, 0, P);
+    // Image 2+2c carries Gray bit (nc-1-c) of the column index (MSB first), 3+2c its inverse:
+    // the index mapping of GrayCodes::generateGrays (Duke/graycodes.cpp:63-85) with g = j ^ (j >> 1).
+    std::vector<uint8_t> line((size_t)W);
+    for (int c = 0; c < nc; c++) {
+        uint8_t *img = h_out + (size_t)(2 + 2 * c) * P, *inv = h_out + (size_t)(3 + 2 * c) * P;
+        for (int j = 0; j < W; j++) line[j] = (((j ^ (j >> 1)) >> (nc - 1 - c)) & 1) ? 255 : 0;
+        for (int i = 0; i < H; i++) {
+            memcpy(img + (size_t)i * W, line.data(), (size_t)W);
+            for (int j = 0; j < W; j++) inv[(size_t)i * W + j] = (uint8_t)(255 - line[j]);
+        }
+    }
+    if (!use_epi) {
+        for (int c = 0; c < nr; c++) {
+            uint8_t *img = h_out + (size_t)(2 + 2 * nc + 2 * c) * P, *inv = h_out + (size_t)(3 + 2 * nc + 2 * c) * P;
+            for (int i = 0; i < H; i++) {
+                const uint8_t v = (((i ^ (i >> 1)) >> (nr - 1 - c)) & 1) ? 255 : 0;
+                memset(img + (size_t)i * W, v, (size_t)W);
+                memset(inv + (size_t)i * W, 255 - v, (size_t)W);
+            }
+        }
+    }
+    return SLR_OK;
+}
+
+extern "C" slr_status slr_generate_mf_patterns(uint8_t *h_out, int projW, int projH)
+{
+    SLR_REQUIRE(h_out && projW > 0 && projH > 0, "slr_generate_mf_patterns: bad argument");
+    const size_t P = (size_t)projW * projH;
+    memset(h_out, 255, P);
+    memset(h_out + P, 0, P);
+    static const int freq[3] = {70, 64, 59};  // Duke/multifrequency.cpp:3
+    const double PI = 3.1416;                 // Duke/multifrequency.h:5
+    std::vector<uint8_t> line((size_t)projW);
+    for (int f = 0; f < 3; f++)
+        for (int s = 0; s < 4; s++) {
+            for (int w = 0; w < projW; w++) {
+                // 135+79*cos(float(PI*2*w*frequency[f]/projW+PI*phi/2))   Duke/multifrequency.cpp:27
+                const double arg = PI * 2 * (double)w * (double)freq[f] / (double)projW + PI * (double)s / 2;
+                const float v = 135.0f + 79.0f * cosf((float)arg);
+                line[w] = (uint8_t)v;
+            }
+            uint8_t *img = h_out + (size_t)(2 + 4 * f + s) * P;
+            for (int h = 0; h < projH; h++) memcpy(img + (size_t)h * projW, line.data(), (size_t)projW);
+        }
+    return SLR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-pointer entry points
+// ------------------------------------------------------------------------------------------------
+#define SLR_ENTER(e)                                                     \
+    SLR_REQUIRE((e) != nullptr, "%s: engine is NULL", __func__);         \
+    SLR_CHECK_CUDA(cudaSetDevice((e)->device))
+
+extern "C" slr_status slr_mf_decode(slr_engine *e, const uint8_t *d_stack, int batch, int F, int S,
+                                    int black_thr, int mode, float *d_phase, uint8_t *d_mask)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(d_stack && d_phase && d_mask && batch > 0, "slr_mf_decode: bad argument");
+    return slr_launch_mf_decode(e, d_stack, batch * 2, F, S, black_thr, mode, d_phase, d_mask);
+}
+
+extern "C" slr_status slr_gray_decode(slr_engine *e, const uint8_t *d_stack, int batch, int nbits_col,
+                                      int nbits_row, int black_thr, int white_thr, int scan_w, int scan_h,
+                                      int32_t *d_col, int32_t *d_row, uint8_t *d_mask)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(d_stack && d_col && d_mask && batch > 0, "slr_gray_decode: bad argument");
+    SLR_REQUIRE(nbits_col >= 1 && nbits_col <= 16 && nbits_row >= 0 && nbits_row <= 16,
+                "slr_gray_decode: bit counts out of range (col %d, row %d)", nbits_col, nbits_row);
+    SLR_REQUIRE(nbits_row == 0 || d_row != nullptr, "slr_gray_decode: d_row is NULL but nbits_row > 0");
+    return slr_launch_gray_decode(e, d_stack, batch * 2, nbits_col, nbits_row, black_thr, white_thr, scan_w,
+                                  scan_h, d_col, d_row, d_mask);
+}
+
+extern "C" slr_status slr_match_triangulate_phase(slr_engine *e, const float *d_phase, const uint8_t *d_mask,
+                                                  int batch, float *d_xyz, uint8_t *d_valid, int32_t *d_match_k,
+                                                  unsigned long long *d_n_points)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(d_phase && d_mask && d_xyz && d_valid && batch > 0, "slr_match_triangulate_phase: bad argument");
+    if (!e->calib_set) {
+        slr_set_error("slr_match_triangulate_phase: call slr_set_calib first");
+        return SLR_ERR_STATE;
+    }
+    return slr_launch_match_phase(e, d_phase, d_mask, batch, d_xyz, d_valid, d_match_k, d_n_points);
+}
+
+extern "C" slr_status slr_match_triangulate_code(slr_engine *e, const int32_t *d_col, const uint8_t *d_mask,
+                                                 int batch, const uint8_t *d_white, float *d_xyz,
+                                                 uint8_t *d_valid, int32_t *d_match_k, uint8_t *d_color,
+                                                 unsigned long long *d_n_points)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(d_col && d_mask && d_xyz && d_valid && batch > 0, "slr_match_triangulate_code: bad argument");
+    SLR_REQUIRE((d_color == nullptr) == (d_white == nullptr), "slr_match_triangulate_code: d_white and d_color go together");
+    if (!e->calib_set) {
+        slr_set_error("slr_match_triangulate_code: call slr_set_calib first");
+        return SLR_ERR_STATE;
+    }
+    return slr_launch_match_code(e, d_col, d_mask, batch, d_white, (size_t)e->W * e->H, d_xyz, d_valid, d_match_k,
+                                 d_color, d_n_points);
+}
+
+extern "C" slr_status slr_bucket_triangulate(slr_engine *e, const int32_t *d_col, const int32_t *d_row,
+                                             const uint8_t *d_mask, int batch, int scan_w, int scan_h,
+                                             float *d_sum, uint8_t *d_cnt, unsigned long long *d_n_cells)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(d_col && d_row && d_mask && d_sum && d_cnt && batch > 0 && scan_w > 0 && scan_h > 0,
+                "slr_bucket_triangulate: bad argument");
+    if (!e->calib_set) {
+        slr_set_error("slr_bucket_triangulate: call slr_set_calib first");
+        return SLR_ERR_STATE;
+    }
+    return slr_launch_bucket_triangulate(e, d_col, d_row, d_mask, batch, scan_w, scan_h, d_sum, d_cnt, d_n_cells);
+}
+
+extern "C" slr_status slr_run_mf(slr_engine *e, const uint8_t *d_stack, int batch, int F, int S, int black_thr,
+                                 int mode, float *d_xyz, uint8_t *d_valid, int32_t *d_match_k,
+                                 unsigned long long *d_n_points)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(d_stack && d_xyz && d_valid && batch > 0, "slr_run_mf: bad argument");
+    if (!e->calib_set) {
+        slr_set_error("slr_run_mf: call slr_set_calib first");
+        return SLR_ERR_STATE;
+    }
+    return slr_launch_fused_mf(e, d_stack, batch, F, S, black_thr, mode, d_xyz, d_valid, d_match_k, d_n_points);
+}
+
+extern "C" slr_status slr_run_ge(slr_engine *e, const uint8_t *d_stack, int batch, int nbits_col, int black_thr,
+                                 int white_thr, int scan_w, int have_color, float *d_xyz, uint8_t *d_valid,
+                                 int32_t *d_match_k, uint8_t *d_color, unsigned long long *d_n_points)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(d_stack && d_xyz && d_valid && batch > 0, "slr_run_ge: bad argument");
+    SLR_REQUIRE(!have_color || d_color, "slr_run_ge: have_color set but d_color is NULL");
+    if (!e->calib_set) {
+        slr_set_error("slr_run_ge: call slr_set_calib first");
+        return SLR_ERR_STATE;
+    }
+    return slr_launch_fused_ge(e, d_stack, batch, nbits_col, black_thr, white_thr, scan_w, have_color, d_xyz,
+                               d_valid, d_match_k, d_color, d_n_points);
+}
+
+extern "C" slr_status slr_synth_mf(slr_engine *e, uint8_t *d_stack, int batch, int proj_w, unsigned seed,
+                                   int integer_disparity, float noise_dn)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(d_stack && batch > 0 && batch <= 32767 && proj_w > 0, "slr_synth_mf: bad argument");
+    return slr_launch_synth_mf(e, d_stack, batch, proj_w, seed, integer_disparity, noise_dn);
+}
+
+extern "C" slr_status slr_synth_gray(slr_engine *e, uint8_t *d_stack, int batch, int scan_w, unsigned seed,
+                                     int integer_disparity, float noise_dn)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(d_stack && batch > 0 && batch <= 32767 && scan_w > 1, "slr_synth_gray: bad argument");
+    return slr_launch_synth_gray(e, d_stack, batch, scan_w, seed, integer_disparity, noise_dn);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer pipelines
+// ------------------------------------------------------------------------------------------------
+extern "C" slr_status slr_host_alloc(void **out, size_t bytes)
+{
+    SLR_REQUIRE(out != nullptr, "slr_host_alloc: out is NULL");
+    SLR_CHECK_CUDA(cudaMallocHost(out, bytes));
+    return SLR_OK;
+}
+
+extern "C" slr_status slr_host_free(void *p)
+{
+    if (p) SLR_CHECK_CUDA(cudaFreeHost(p));
+    return SLR_OK;
+}
+
+static slr_status ensure_stage(slr_engine *e, size_t in_bytes_per_scan, bool want_color)
+{
+    const size_t P = (size_t)e->W * e->H;
+    for (int i = 0; i < 2; i++) {
+        if (e->stage_in_bytes < in_bytes_per_scan) {
+            if (e->d_stage_in[i]) SLR_CHECK_CUDA(cudaFree(e->d_stage_in[i]));
+            e->d_stage_in[i] = nullptr;
+            SLR_CHECK_CUDA(cudaMalloc(&e->d_stage_in[i], in_bytes_per_scan));
+        }
+        if (!e->d_stage_xyz[i]) SLR_CHECK_CUDA(cudaMalloc(&e->d_stage_xyz[i], P * 3 * sizeof(float)));
+        if (!e->d_stage_valid[i]) SLR_CHECK_CUDA(cudaMalloc(&e->d_stage_valid[i], P));
+        if (!e->d_stage_k[i]) SLR_CHECK_CUDA(cudaMalloc(&e->d_stage_k[i], P * sizeof(int32_t)));
+        if (want_color && !e->d_stage_color[i]) SLR_CHECK_CUDA(cudaMalloc(&e->d_stage_color[i], P));
+    }
+    if (e->stage_in_bytes < in_bytes_per_scan) e->stage_in_bytes = in_bytes_per_scan;
+    return SLR_OK;
+}
+
+// Scan-by-scan software pipeline over three streams: H2D of scan s+1 overlaps the kernels of scan s
+// and the D2H of scan s-1 (PCIe is full duplex; the kernels take microseconds, the copies ~1 ms).
+template <typename LaunchFn>
+static slr_status host_pipeline(slr_engine *e, const uint8_t *h_stack, size_t in_bytes, int batch, bool color,
+                                float *h_xyz, uint8_t *h_valid, int32_t *h_match_k, uint8_t *h_color,
+                                unsigned long long *h_n_points, LaunchFn launch)
+{
+    const size_t P = (size_t)e->W * e->H;
+    slr_status st = ensure_stage(e, in_bytes, color);
+    if (st != SLR_OK) return st;
+    cudaStream_t cs = e->stream;
+    SLR_CHECK_CUDA(cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), cs));
+    for (int s = 0; s < batch; s++) {
+        const int b = s & 1;
+        // stage_in[b] is free once the kernels of scan s-2 are done
+        SLR_CHECK_CUDA(cudaStreamWaitEvent(e->copy_in, e->ev_k[b], 0));
+        SLR_CHECK_CUDA(cudaMemcpyAsync(e->d_stage_in[b], h_stack + (size_t)s * in_bytes, in_bytes,
+                                       cudaMemcpyHostToDevice, e->copy_in));
+        SLR_CHECK_CUDA(cudaEventRecord(e->ev_in[b], e->copy_in));
+        // outputs of buffer b are free once the D2H of scan s-2 is done
+        SLR_CHECK_CUDA(cudaStreamWaitEvent(cs, e->ev_in[b], 0));
+        SLR_CHECK_CUDA(cudaStreamWaitEvent(cs, e->ev_out[b], 0));
+        st = launch(e->d_stage_in[b], e->d_stage_xyz[b], e->d_stage_valid[b], e->d_stage_k[b], e->d_stage_color[b]);
+        if (st != SLR_OK) return st;
+        SLR_CHECK_CUDA(cudaEventRecord(e->ev_k[b], cs));
+        SLR_CHECK_CUDA(cudaStreamWaitEvent(e->copy_out, e->ev_k[b], 0));
+        SLR_CHECK_CUDA(cudaMemcpyAsync(h_xyz + (size_t)s * P * 3, e->d_stage_xyz[b], P * 3 * sizeof(float),
+                                       cudaMemcpyDeviceToHost, e->copy_out));
+        SLR_CHECK_CUDA(cudaMemcpyAsync(h_valid + (size_t)s * P, e->d_stage_valid[b], P, cudaMemcpyDeviceToHost,
+                                       e->copy_out));
+        if (h_match_k)
+            SLR_CHECK_CUDA(cudaMemcpyAsync(h_match_k + (size_t)s * P, e->d_stage_k[b], P * sizeof(int32_t),
+                                           cudaMemcpyDeviceToHost, e->copy_out));
+        if (color && h_color)
+            SLR_CHECK_CUDA(cudaMemcpyAsync(h_color + (size_t)s * P, e->d_stage_color[b], P, cudaMemcpyDeviceToHost,
+                                           e->copy_out));
+        SLR_CHECK_CUDA(cudaEventRecord(e->ev_out[b], e->copy_out));
+    }
+    SLR_CHECK_CUDA(cudaMemcpyAsync(e->h_counter, e->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, cs));
+    SLR_CHECK_CUDA(cudaStreamSynchronize(cs));
+    SLR_CHECK_CUDA(cudaStreamSynchronize(e->copy_out));
+    SLR_CHECK_CUDA(cudaStreamSynchronize(e->copy_in));
+    if (h_n_points) *h_n_points = *e->h_counter;
+    return SLR_OK;
+}
+
+extern "C" slr_status slr_run_mf_host(slr_engine *e, const uint8_t *h_stack, int batch, int F, int S,
+                                      int black_thr, int mode, float *h_xyz, uint8_t *h_valid,
+                                      int32_t *h_match_k, unsigned long long *h_n_points)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(h_stack && h_xyz && h_valid && batch > 0, "slr_run_mf_host: bad argument");
+    SLR_REQUIRE(F >= 1 && S >= 3 && F * S <= 128, "slr_run_mf_host: bad F/S");
+    if (!e->calib_set) {
+        slr_set_error("slr_run_mf_host: call slr_set_calib first");
+        return SLR_ERR_STATE;
+    }
+    const size_t in_bytes = (size_t)2 * (2 + F * S) * e->W * e->H;
+    return host_pipeline(e, h_stack, in_bytes, batch, false, h_xyz, h_valid, h_match_k, nullptr, h_n_points,
+                         [&](uint8_t *d_in, float *d_xyz, uint8_t *d_valid, int32_t *d_k, uint8_t *) {
+                             return slr_launch_fused_mf(e, d_in, 1, F, S, black_thr, mode, d_xyz, d_valid,
+                                                        h_match_k ? d_k : nullptr, e->d_counter);
+                         });
+}
+
+extern "C" slr_status slr_run_ge_host(slr_engine *e, const uint8_t *h_stack, int batch, int nbits_col,
+                                      int black_thr, int white_thr, int scan_w, int have_color, float *h_xyz,
+                                      uint8_t *h_valid, int32_t *h_match_k, uint8_t *h_color,
+                                      unsigned long long *h_n_points)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(h_stack && h_xyz && h_valid && batch > 0, "slr_run_ge_host: bad argument");
+    SLR_REQUIRE(nbits_col >= 1 && nbits_col <= 16, "slr_run_ge_host: bad nbits_col %d", nbits_col);
+    SLR_REQUIRE(!have_color || h_color, "slr_run_ge_host: have_color set but h_color is NULL");
+    if (!e->calib_set) {
+        slr_set_error("slr_run_ge_host: call slr_set_calib first");
+        return SLR_ERR_STATE;
+    }
+    const size_t in_bytes = (size_t)2 * (2 + 2 * nbits_col) * e->W * e->H;
+    return host_pipeline(e, h_stack, in_bytes, batch, have_color != 0, h_xyz, h_valid, h_match_k, h_color,
+                         h_n_points,
+                         [&](uint8_t *d_in, float *d_xyz, uint8_t *d_valid, int32_t *d_k, uint8_t *d_col) {
+                             return slr_launch_fused_ge(e, d_in, 1, nbits_col, black_thr, white_thr, scan_w,
+                                                        have_color, d_xyz, d_valid, h_match_k ? d_k : nullptr,
+                                                        have_color ? d_col : nullptr, e->d_counter);
+                         });
+}
+
+// ------------------------------------------------------------------------------------------------
+// un-fused pipelines (first implementation of the fused entry points; kept as the fallback for
+// shapes the fused kernels do not cover).  Chunked by max_batch through the engine's scratch.
+// ------------------------------------------------------------------------------------------------
+slr_status slr_unfused_mf(slr_engine *e, const uint8_t *d_stack, int batch, int F, int S, int black_thr, int mode,
+                          float *d_xyz, uint8_t *d_valid, int32_t *d_match_k, unsigned long long *d_n_points)
+{
+    slr_status st = ensure_scratch(e, true, false);
+    if (st != SLR_OK) return st;
+    const size_t P = (size_t)e->W * e->H;
+    const size_t N = (size_t)(2 + F * S);
+    for (int b0 = 0; b0 < batch; b0 += e->max_batch) {
+        const int nb = (batch - b0 < e->max_batch) ? batch - b0 : e->max_batch;
+        st = slr_launch_mf_decode(e, d_stack + (size_t)b0 * 2 * N * P, nb * 2, F, S, black_thr, mode, e->d_phase,
+                                  e->d_mask);
+        if (st != SLR_OK) return st;
+        st = slr_launch_match_phase(e, e->d_phase, e->d_mask, nb, d_xyz + (size_t)b0 * P * 3, d_valid + (size_t)b0 * P,
+                                    d_match_k ? d_match_k + (size_t)b0 * P : nullptr, d_n_points);
+        if (st != SLR_OK) return st;
+    }
+    return SLR_OK;
+}
+
+slr_status slr_unfused_ge(slr_engine *e, const uint8_t *d_stack, int batch, int nbits_col, int black_thr,
+                          int white_thr, int scan_w, int have_color, float *d_xyz, uint8_t *d_valid,
+                          int32_t *d_match_k, uint8_t *d_color, unsigned long long *d_n_points)
+{
+    slr_status st = ensure_scratch(e, false, true);
+    if (st != SLR_OK) return st;
+    const size_t P = (size_t)e->W * e->H;
+    const size_t N = (size_t)(2 + 2 * nbits_col);
+    for (int b0 = 0; b0 < batch; b0 += e->max_batch) {
+        const int nb = (batch - b0 < e->max_batch) ? batch - b0 : e->max_batch;
+        const uint8_t *stk = d_stack + (size_t)b0 * 2 * N * P;
+        st = slr_launch_gray_decode(e, stk, nb * 2, nbits_col, 0, black_thr, white_thr, scan_w, 0, e->d_code, nullptr,
+                                    e->d_mask);
+        if (st != SLR_OK) return st;
+        // white image of view v is plane 0 of that view: stride between views = N*P bytes
+        st = slr_launch_match_code(e, e->d_code, e->d_mask, nb, have_color ? stk : nullptr, N * P,
+                                   d_xyz + (size_t)b0 * P * 3, d_valid + (size_t)b0 * P,
+                                   d_match_k ? d_match_k + (size_t)b0 * P : nullptr,
+                                   (have_color && d_color) ? d_color + (size_t)b0 * P : nullptr, d_n_points);
+        if (st != SLR_OK) return st;
+    }
+    return SLR_OK;
+}

@@ -1,0 +1,109 @@
+// slr_internal.h — engine state and host-side helpers shared by the .cu files of libslr_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "slr_b200.h"
+
+#define SLR_QNAN_BITS 0x7FC00000u
+
+// Reference constants.  Duke/mfreconstruct.cpp:5 `float PI = 3.1416;`
+#define SLR_PI_DEC 3.1416f
+
+struct slr_calib_dev {
+    // Q (stereoRect::Q, 4x4 CV_64F) and the optional 3x4 rigid transform, passed to kernels by value.
+    double Q[16];
+    float rigid[12];
+    int has_rigid;
+};
+
+struct slr_engine {
+    int device = 0;
+    int W = 0, H = 0, max_batch = 0;
+    int num_sms = 0;
+    cudaStream_t own_stream = nullptr;   // created by the engine
+    cudaStream_t stream = nullptr;       // the stream work is issued on (own or caller's)
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host pipeline streams
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+
+    bool calib_set = false;
+    slr_camera cams[2];
+    slr_calib_dev calib;
+    // Utilities::undistortPoints maps, float [H][W]: left x, left y, right x.
+    float *d_undist_lx = nullptr, *d_undist_ly = nullptr, *d_undist_rx = nullptr;
+    // atan(float(q)) for q in [-255, 255] (index q+255), built on the host with the host libm.
+    float *d_atan_lut = nullptr;
+
+    // scratch for the un-fused pipelines / host entry points
+    float *d_phase = nullptr;      // [max_batch][2][H][W]
+    int32_t *d_code = nullptr;     // [max_batch][2][H][W]
+    uint8_t *d_mask = nullptr;     // [max_batch][2][H][W]
+    // host pipeline staging (double buffered, one scan each)
+    uint8_t *d_stage_in[2] = {nullptr, nullptr};
+    size_t stage_in_bytes = 0;
+    float *d_stage_xyz[2] = {nullptr, nullptr};
+    uint8_t *d_stage_valid[2] = {nullptr, nullptr};
+    int32_t *d_stage_k[2] = {nullptr, nullptr};
+    uint8_t *d_stage_color[2] = {nullptr, nullptr};
+    unsigned long long *d_counter = nullptr;  // device point counter
+    unsigned long long *h_counter = nullptr;  // pinned
+
+    unsigned long long launches = 0;
+};
+
+void slr_set_error(const char *fmt, ...);
+
+#define SLR_CHECK_CUDA(expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            slr_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return SLR_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+#define SLR_REQUIRE(cond, ...)            \
+    do {                                  \
+        if (!(cond)) {                    \
+            slr_set_error(__VA_ARGS__);   \
+            return SLR_ERR_INVALID;       \
+        }                                 \
+    } while (0)
+
+#define SLR_CHECK_LAUNCH(e)                                  \
+    do {                                                     \
+        (e)->launches++;                                     \
+        SLR_CHECK_CUDA(cudaGetLastError());                  \
+    } while (0)
+
+// kernel launchers (defined in the k*.cu files)
+slr_status slr_launch_mf_decode(slr_engine *e, const uint8_t *d_stack, int views, int F, int S,
+                                int black_thr, int mode, float *d_phase, uint8_t *d_mask);
+slr_status slr_launch_match_phase(slr_engine *e, const float *d_phase, const uint8_t *d_mask, int batch,
+                                  float *d_xyz, uint8_t *d_valid, int32_t *d_match_k,
+                                  unsigned long long *d_n_points);
+slr_status slr_launch_gray_decode(slr_engine *e, const uint8_t *d_stack, int views, int nbits_col,
+                                  int nbits_row, int black_thr, int white_thr, int scan_w, int scan_h,
+                                  int32_t *d_col, int32_t *d_row, uint8_t *d_mask);
+slr_status slr_launch_match_code(slr_engine *e, const int32_t *d_col, const uint8_t *d_mask, int batch,
+                                 const uint8_t *d_white, size_t white_view_stride,
+                                 float *d_xyz, uint8_t *d_valid, int32_t *d_match_k, uint8_t *d_color,
+                                 unsigned long long *d_n_points);
+slr_status slr_launch_bucket_triangulate(slr_engine *e, const int32_t *d_col, const int32_t *d_row,
+                                         const uint8_t *d_mask, int batch, int scan_w, int scan_h,
+                                         float *d_sum, uint8_t *d_cnt, unsigned long long *d_n_cells);
+slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch, int F, int S,
+                               int black_thr, int mode, float *d_xyz, uint8_t *d_valid,
+                               int32_t *d_match_k, unsigned long long *d_n_points);
+slr_status slr_launch_fused_ge(slr_engine *e, const uint8_t *d_stack, int batch, int nbits_col,
+                               int black_thr, int white_thr, int scan_w, int have_color,
+                               float *d_xyz, uint8_t *d_valid, int32_t *d_match_k, uint8_t *d_color,
+                               unsigned long long *d_n_points);
+slr_status slr_launch_undistort_maps(slr_engine *e);
+slr_status slr_launch_synth_mf(slr_engine *e, uint8_t *d_stack, int batch, int proj_w, unsigned seed,
+                               int integer_disparity, float noise_dn);
+slr_status slr_launch_synth_gray(slr_engine *e, uint8_t *d_stack, int batch, int scan_w, unsigned seed,
+                                 int integer_disparity, float noise_dn);

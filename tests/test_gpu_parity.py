@@ -1,0 +1,299 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the
+same inputs.  Bars: Gray indices / masks / match columns bit-exact; strict-mode phase and XYZ are
+also compared bit-for-bit (the kernels use the same IEEE operation sequence), with the north-star
+tolerance (1e-4 relative) written as the fallback bar for floating point; corrected mode 1e-4."""
+import numpy as np
+import pytest
+
+import slr_b200
+from slr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4          # BASELINE.json north_star: "within 1e-4 relative on unwrapped phase and XYZ"
+
+
+def _t(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_float_parity(gpu, cpu, what):
+    gpu, cpu = np.asarray(gpu), np.asarray(cpu)
+    assert (np.isnan(gpu) == np.isnan(cpu)).all(), f"{what}: NaN pattern differs"
+    ok = ~np.isnan(cpu)
+    assert np.allclose(gpu[ok], cpu[ok], rtol=RTOL, atol=1e-6), f"{what}: outside 1e-4 relative"
+    exact = (bits(gpu) == bits(cpu)).mean()
+    assert exact == 1.0, f"{what}: only {exact:.6f} of values bit-exact"
+
+
+def all_pairs_stack():
+    """A 14-plane stack whose pixels realise every (a, b) = (G4-G2, G1-G3) in [-255, 255]^2 at frequency 0
+    and shuffled pairs at frequencies 1, 2 (exhaustive for getPhase's per-frequency branch table)."""
+    a, b = np.meshgrid(np.arange(-255, 256), np.arange(-255, 256), indexing="ij")
+    a, b = a.ravel(), b.ravel()
+    n = a.size                                   # 261121
+    W = 512
+    H = (n + W - 1) // W
+    pad = W * H - n
+    rng = np.random.default_rng(0)
+    st = np.zeros((14, H * W), np.uint8)
+    st[0] = 255
+    st[1] = 0
+    perm = [np.arange(n), rng.permutation(n), rng.permutation(n)]
+    for f in range(3):
+        aa, bb = a[perm[f]], b[perm[f]]
+        G = np.zeros((4, n), np.int64)
+        G[3] = np.maximum(aa, 0)                 # G4
+        G[1] = np.maximum(-aa, 0)                # G2
+        G[0] = np.maximum(bb, 0)                 # G1
+        G[2] = np.maximum(-bb, 0)                # G3
+        st[2 + 4 * f:6 + 4 * f, :n] = G
+        st[2 + 4 * f:6 + 4 * f, n:] = rng.integers(0, 256, (4, pad))
+    return st.reshape(14, H, W), W, H
+
+
+def test_k1_strict_all_difference_pairs(cuda_engine_factory, oracle):
+    st, W, H = all_pairs_stack()
+    eng = cuda_engine_factory(W, H)
+    stack = np.stack([st, st[:, ::-1].copy()])[None]            # [1, 2, 14, H, W]
+    ph, mk = eng.mf_decode(_t(stack), black_thr=40)
+    for cam in range(2):
+        ph_o, mk_o = oracle.mf_decode(stack[0, cam], black_thr=40)
+        assert (mk[0, cam].cpu().numpy() == mk_o).all()
+        assert_float_parity(ph[0, cam].cpu().numpy(), ph_o, f"strict phase cam{cam}")
+
+
+@pytest.mark.parametrize("W,H,noise", [(1280, 64, 0.0), (1280, 48, 2.0), (640, 480, 1.0), (20, 3, 0.0)])
+def test_k1_strict_synth_and_scalar_path(cuda_engine_factory, oracle, W, H, noise):
+    eng = cuda_engine_factory(W, H, 2)
+    stack = np.stack([synth.synth_mf(W, H, seed=s, noise_dn=noise) for s in (1, 2)])
+    ph, mk = eng.mf_decode(_t(stack), black_thr=40)
+    for b in range(2):
+        for cam in range(2):
+            ph_o, mk_o = oracle.mf_decode(stack[b, cam], black_thr=40)
+            assert (mk[b, cam].cpu().numpy() == mk_o).all()
+            assert_float_parity(ph[b, cam].cpu().numpy(), ph_o, "strict phase")
+
+
+@pytest.mark.parametrize("F,S", [(3, 4), (4, 8), (3, 5)])
+def test_k1_corrected_mode(cuda_engine_factory, oracle, F, S):
+    W, H = 256, 32
+    eng = cuda_engine_factory(W, H)
+    rng = np.random.default_rng(F * 10 + S)
+    # smooth fringes so the wrap points are sparse
+    x = np.arange(W)[None, None, None, :] / W
+    stack = np.zeros((1, 2, 2 + F * S, H, W), np.uint8)
+    stack[:, :, 0] = 220
+    stack[:, :, 1] = 10
+    freqs = [70, 64, 59, 55][:F]
+    for f in range(F):
+        for s in range(S):
+            v = 128 + 90 * np.cos(2 * np.pi * freqs[f] * (x + 0.013) + 2 * np.pi * s / S)
+            stack[:, :, 2 + S * f + s] = np.clip(v + rng.normal(0, 1.0, (1, 2, H, W)), 0, 255).astype(np.uint8)
+    ph, mk = eng.mf_decode(_t(stack), F=F, S=S, black_thr=40, mode=slr_b200.MODE_CORRECTED)
+    for cam in range(2):
+        ph_o, mk_o = oracle.mf_decode(stack[0, cam], F=F, S=S, black_thr=40, mode=1)
+        g = ph[0, cam].cpu().numpy()
+        assert (mk[0, cam].cpu().numpy() == mk_o).all()
+        ok = mk_o == 1
+        d = np.abs(g[ok] - ph_o[ok])
+        d = np.minimum(d, 255.0 - d)                            # the phase is circular with period 255
+        assert (d <= RTOL * 255.0).all(), d.max()
+
+
+def decode_oracle(oracle, stack):
+    """stack [B,2,14,H,W] -> phase [B,2,H,W], mask"""
+    B = stack.shape[0]
+    ph = np.empty(stack.shape[:2] + stack.shape[3:], np.float32)
+    mk = np.empty(ph.shape, np.uint8)
+    for b in range(B):
+        for cam in range(2):
+            ph[b, cam], mk[b, cam] = oracle.mf_decode(stack[b, cam], black_thr=40)
+    return ph, mk
+
+
+@pytest.mark.parametrize("W,H,intd,noise,rigid", [(1280, 32, True, 0.0, False), (1280, 24, False, 1.5, True),
+                                                  (640, 40, True, 2.0, False), (64, 8, True, 0.0, True)])
+def test_k3a_phase_match_vs_oracle(cuda_engine_factory, oracle, W, H, intd, noise, rigid):
+    eng = cuda_engine_factory(W, H, 2)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    M = np.array([[0.98, -0.17, 0.05, 12.5], [0.17, 0.98, 0.02, -3.25], [-0.05, -0.01, 0.99, 40.0]], np.float32) \
+        if rigid else None
+    eng.set_calib(cams, Q, M)
+    stack = np.stack([synth.synth_mf(W, H, seed=s, integer_disparity=intd, noise_dn=noise) for s in (11, 12)])
+    ph, mk = decode_oracle(oracle, stack)
+    xyz, valid, k, n = eng.match_triangulate_phase(_t(ph), _t(mk))
+    total = 0
+    for b in range(2):
+        xyz_o, valid_o, k_o, n_o = oracle.mf_triangulate(ph[b, 0], mk[b, 0], ph[b, 1], mk[b, 1], cams, Q, M)
+        assert (k[b].cpu().numpy() == k_o).all(), "match column differs"
+        assert (valid[b].cpu().numpy() == valid_o).all()
+        assert_float_parity(xyz[b].cpu().numpy(), xyz_o, "XYZ")
+        total += n_o
+    assert int(n.item()) == total
+    assert total > 0
+
+
+def test_k3a_edge_cases(cuda_engine_factory, oracle):
+    W, H = 64, 6
+    eng = cuda_engine_factory(W, H)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    rng = np.random.default_rng(3)
+    ph = np.zeros((1, 2, H, W), np.float32)
+    mk = np.ones((1, 2, H, W), np.uint8)
+    ph[0, :, 0] = 7.25                                             # row 0: every pixel the same phase
+    mk[0, :, 1] = 0                                                # row 1: nothing carries a phase
+    ph[0, :, 2] = rng.choice([1.0, 1.05, 1.12, 1.2, 9.0], (2, W))  # row 2: heavy duplicates near the tolerance
+    ph[0, :, 3] = rng.uniform(-200, 480, (2, W))                   # row 3: strict-mode value range
+    ph[0, 0, 4] = np.nan                                           # row 4: NaN phase under a set mask
+    ph[0, 1, 4] = rng.uniform(0, 1, W)
+    ph[0, :, 5] = rng.uniform(0, 0.5, (2, W))                      # row 5: everything within tolerance chains
+    mk[0, 1, 5, ::3] = 0
+    xyz, valid, k, n = eng.match_triangulate_phase(_t(ph), _t(mk))
+    xyz_o, valid_o, k_o, n_o = oracle.mf_triangulate(ph[0, 0], mk[0, 0], ph[0, 1], mk[0, 1], cams, Q)
+    assert (k[0].cpu().numpy() == k_o).all()
+    assert (valid[0].cpu().numpy() == valid_o).all()
+    assert_float_parity(xyz[0].cpu().numpy(), xyz_o, "XYZ edge")
+    assert int(n.item()) == n_o
+
+
+def test_run_mf_full_frame_vs_oracle(cuda_engine_factory, oracle):
+    """BASELINE config 3's MF half at full size: 1280x1024, one scan, fused entry point."""
+    W, H = 1280, 1024
+    eng = cuda_engine_factory(W, H, 2)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    stack = eng.synth_mf(2, seed=42, integer_disparity=True, noise_dn=0.0)
+    xyz, valid, k, n = eng.run_mf(stack, black_thr=40)
+    hs = stack.cpu().numpy()
+    tot = 0
+    for b in range(2):
+        xyz_o, valid_o, k_o, n_o = oracle.run_mf(hs[b], cams, Q, nthreads=oracle.max_threads())
+        assert (k[b].cpu().numpy() == k_o).all()
+        assert (valid[b].cpu().numpy() == valid_o).all()
+        assert_float_parity(xyz[b].cpu().numpy(), xyz_o, "XYZ full frame")
+        tot += n_o
+    assert int(n.item()) == tot and tot > 0.5 * 2 * W * H
+    # size-independent properties: determinism / idempotence, count == number of valid flags
+    xyz2, valid2, k2, n2 = eng.run_mf(stack, black_thr=40)
+    assert (bits(xyz2.cpu().numpy()) == bits(xyz.cpu().numpy())).all() and int(n2.item()) == int(valid2.sum().item())
+
+
+def test_run_mf_host_matches_device(cuda_engine_factory):
+    W, H = 640, 96
+    eng = cuda_engine_factory(W, H, 2)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    stack = eng.synth_mf(3, seed=7, noise_dn=1.0)
+    xyz, valid, k, n = eng.run_mf(stack)
+    h_stack = stack.cpu().numpy()
+    h_xyz = np.empty((3, H, W, 3), np.float32)
+    h_valid = np.empty((3, H, W), np.uint8)
+    h_k = np.empty((3, H, W), np.int32)
+    n_host = eng.run_mf_host(h_stack, h_xyz, h_valid, h_k)
+    assert n_host == int(n.item())
+    assert (bits(h_xyz) == bits(xyz.cpu().numpy())).all()
+    assert (h_valid == valid.cpu().numpy()).all() and (h_k == k.cpu().numpy()).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# Gray path
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("W,H,rows,white_thr,noise", [(640, 480, False, 0, 0.0), (1280, 32, False, 10, 3.0),
+                                                      (96, 80, True, 5, 2.0), (20, 3, True, 0, 0.0)])
+def test_k2_gray_decode_vs_oracle(cuda_engine_factory, oracle, W, H, rows, white_thr, noise):
+    """Config 1 (640x480, 10 bitplanes) and friends: indices and masks bit-exact."""
+    eng = cuda_engine_factory(W, H)
+    stack = synth.synth_gray(W, H, seed=5, noise_dn=noise, rows=rows)[None]
+    nc = oracle.gray_num_bits(W)
+    nr = oracle.gray_num_bits(H) if rows else 0
+    col, row, mk = eng.gray_decode(_t(stack), nc, nr, black_thr=40, white_thr=white_thr, scan_w=W, scan_h=H)
+    for cam in range(2):
+        c_o, r_o, m_o = oracle.gray_decode(stack[0, cam], nc, nr, 40, white_thr, W, H)
+        assert (col[0, cam].cpu().numpy() == c_o).all()
+        assert (mk[0, cam].cpu().numpy() == m_o).all()
+        if rows:
+            assert (row[0, cam].cpu().numpy() == r_o).all()
+
+
+@pytest.mark.parametrize("W,H,intd,noise,color", [(1280, 32, True, 0.0, False), (640, 48, False, 4.0, True),
+                                                  (64, 8, True, 6.0, True)])
+def test_k3b_code_match_vs_oracle(cuda_engine_factory, oracle, W, H, intd, noise, color):
+    eng = cuda_engine_factory(W, H)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    stack = synth.synth_gray(W, H, seed=9, integer_disparity=intd, noise_dn=noise)[None]
+    nc = oracle.gray_num_bits(W)
+    cols, mks = [], []
+    for cam in range(2):
+        c_o, _, m_o = oracle.gray_decode(stack[0, cam], nc, 0, 40, 0, W, H)
+        cols.append(c_o)
+        mks.append(m_o)
+    col = np.stack(cols)[None]
+    mk = np.stack(mks)[None]
+    white = np.ascontiguousarray(stack[:, :, 0]) if color else None
+    xyz, valid, k, colr, n = eng.match_triangulate_code(_t(col), _t(mk), _t(white) if color else None)
+    xyz_o, valid_o, k_o, col_o, n_o = oracle.ge_triangulate(col[0, 0], mk[0, 0], col[0, 1], mk[0, 1], Q,
+                                                            whiteL=white[0, 0] if color else None,
+                                                            whiteR=white[0, 1] if color else None)
+    assert (k[0].cpu().numpy() == k_o).all()
+    assert (valid[0].cpu().numpy() == valid_o).all()
+    assert_float_parity(xyz[0].cpu().numpy(), xyz_o, "GE XYZ")
+    if color:
+        assert (colr[0].cpu().numpy() == col_o).all()
+    assert int(n.item()) == n_o and n_o > 0
+
+
+def test_k3b_adversarial_chains(cuda_engine_factory, oracle):
+    """Rows built to stress the kstart chain: sparse matches, repeated codes, decreasing codes."""
+    W, H = 256, 8
+    eng = cuda_engine_factory(W, H)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    rng = np.random.default_rng(1)
+    col = np.full((1, 2, H, W), -1, np.int32)
+    col[0, :, 0] = rng.integers(0, 4, (2, W))                       # few codes, many repeats
+    col[0, 0, 1] = np.arange(W)[::-1]                               # decreasing left codes
+    col[0, 1, 1] = np.arange(W)
+    col[0, 0, 2, 200] = 7                                           # a lone left pixel at the far end
+    col[0, 1, 2] = 7
+    col[0, :, 3] = rng.integers(0, W, (2, W))                       # random
+    col[0, 0, 4] = np.repeat(np.arange(W // 4), 4)                  # runs
+    col[0, 1, 4] = np.repeat(np.arange(W // 2), 2)
+    col[0, 0, 5, ::17] = 3                                          # sparse left, all-matching right
+    col[0, 1, 5] = 3
+    col[0, 0, 6] = 5                                                # left all same, right has a single 5 late
+    col[0, 1, 6, 250] = 5
+    mk = (col >= 0).astype(np.uint8)
+    xyz, valid, k, _, n = eng.match_triangulate_code(_t(col), _t(mk))
+    xyz_o, valid_o, k_o, _, n_o = oracle.ge_triangulate(col[0, 0], mk[0, 0], col[0, 1], mk[0, 1], Q)
+    assert (k[0].cpu().numpy() == k_o).all()
+    assert (valid[0].cpu().numpy() == valid_o).all()
+    assert_float_parity(xyz[0].cpu().numpy(), xyz_o, "GE XYZ adversarial")
+    assert int(n.item()) == n_o
+
+
+def test_run_ge_full_frame_vs_oracle(cuda_engine_factory, oracle):
+    W, H = 1280, 1024
+    eng = cuda_engine_factory(W, H)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    stack = eng.synth_gray(1, seed=4, integer_disparity=False, noise_dn=2.0)
+    nc = oracle.gray_num_bits(W)
+    xyz, valid, k, colr, n = eng.run_ge(stack, nc, black_thr=40, white_thr=3, have_color=True)
+    hs = stack.cpu().numpy()
+    cols, mks = zip(*[(lambda r: (r[0], r[2]))(oracle.gray_decode(hs[0, cam], nc, 0, 40, 3, W, H)) for cam in range(2)])
+    xyz_o, valid_o, k_o, col_o, n_o = oracle.ge_triangulate(cols[0], mks[0], cols[1], mks[1], Q,
+                                                            whiteL=hs[0, 0, 0], whiteR=hs[0, 1, 0],
+                                                            nthreads=oracle.max_threads())
+    assert (k[0].cpu().numpy() == k_o).all()
+    assert (valid[0].cpu().numpy() == valid_o).all()
+    assert (colr[0].cpu().numpy() == col_o).all()
+    assert_float_parity(xyz[0].cpu().numpy(), xyz_o, "GE XYZ full frame")
+    assert int(n.item()) == n_o and n_o > 0.3 * W * H
