@@ -78,7 +78,10 @@ typedef struct {
  * Duke/reconstruct.cpp:615-621); max_batch = scans per call the host-buffer entry points stage. */
 SLR_API slr_status slr_create(slr_engine **out, int device, int width, int height, int max_batch);
 SLR_API slr_status slr_destroy(slr_engine *e);
-/* Run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the engine's own stream. */
+/* Run on a caller-owned cudaStream_t (e.g. torch's current stream).  As in the CUDA API, NULL is the
+ * legacy default stream; SLR_STREAM_OWN selects the engine's own non-blocking stream, which is also
+ * the state after slr_create. */
+#define SLR_STREAM_OWN ((void *)(intptr_t)-1)
 SLR_API slr_status slr_set_stream(slr_engine *e, void *cuda_stream);
 SLR_API slr_status slr_synchronize(slr_engine *e);
 /* Replaces stereoRect::Q (Duke/stereorect.h:21), MFReconstruct/Reconstruct::cameras[2]

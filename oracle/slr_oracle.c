@@ -248,8 +248,8 @@ static int corrected_phase(const uint8_t *const *imgs, size_t p, int F, int S,
 }
 
 /* Duke/mfreconstruct.cpp:190-228 */
-int orc_mf_decode(const uint8_t *stack, int W, int H, int F, int S, int black_thr, int mode,
-                  float *phase, uint8_t *mask)
+int orc_mf_decode_mt(const uint8_t *stack, int W, int H, int F, int S, int black_thr, int mode,
+                     float *phase, uint8_t *mask, int nthreads)
 {
     const size_t P = (size_t)W * H;
     if (F < 1 || F > 16 || S < 3 || S > 16)
@@ -265,7 +265,9 @@ int orc_mf_decode(const uint8_t *stack, int W, int H, int F, int S, int black_th
         sn[s] = (float)sin(2.0 * 3.14159265358979323846 * s / S);
     }
     orc_shadow_mask(imgs[0], imgs[1], (int)P, black_thr, mask); /* computeShadows :190-207 */
-    for (size_t p = 0; p < P; p++) {                            /* decodePatterns :215-225 */
+    /* decodePatterns :215-225.  Pixels are independent; nthreads > 1 splits them over OpenMP threads. */
+#pragma omp parallel for schedule(static) num_threads(nthreads > 1 ? nthreads : 1)
+    for (size_t p = 0; p < P; p++) {
         float ph = qnanf();
         if (mask[p]) {
             int ok;
@@ -285,6 +287,12 @@ int orc_mf_decode(const uint8_t *stack, int W, int H, int F, int S, int black_th
         phase[p] = ph;
     }
     return 0;
+}
+
+int orc_mf_decode(const uint8_t *stack, int W, int H, int F, int S, int black_thr, int mode,
+                  float *phase, uint8_t *mask)
+{
+    return orc_mf_decode_mt(stack, W, H, F, S, black_thr, mode, phase, mask, 1);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -752,8 +760,8 @@ int64_t orc_run_mf(const uint8_t *stacks, int W, int H, int F, int S, int black_
     float *ph = (float *)malloc(2 * P * sizeof(float));
     uint8_t *mk = (uint8_t *)malloc(2 * P);
     int64_t n = -1;
-    if (orc_mf_decode(stacks, W, H, F, S, black_thr, mode, ph, mk) == 0 &&
-        orc_mf_decode(stacks + N * P, W, H, F, S, black_thr, mode, ph + P, mk + P) == 0)
+    if (orc_mf_decode_mt(stacks, W, H, F, S, black_thr, mode, ph, mk, nthreads) == 0 &&
+        orc_mf_decode_mt(stacks + N * P, W, H, F, S, black_thr, mode, ph + P, mk + P, nthreads) == 0)
         n = orc_mf_triangulate(ph, mk, ph + P, mk + P, W, H, &cams[0], &cams[1], Q, rigid,
                                xyz, valid, match_k, nthreads);
     free(ph);

@@ -68,6 +68,9 @@ int  orc_wrapped_phase_strict(int a, int b, float *P);
  * phase: float[H*W] (NaN where no phase), mask: u8[H*W] (1 = pixel carries a phase). */
 int  orc_mf_decode(const uint8_t *stack, int W, int H, int F, int S, int black_thr, int mode,
                    float *phase, uint8_t *mask);
+/* same, pixels split over `nthreads` OpenMP threads (pixels are independent) */
+int  orc_mf_decode_mt(const uint8_t *stack, int W, int H, int F, int S, int black_thr, int mode,
+                      float *phase, uint8_t *mask, int nthreads);
 /* Duke/reconstruct.cpp:210-227 + 79-97 + 381-407 (nbits_row==0, GRAY_EPI) or
  * 56-74 + 325-370 (nbits_row>0, GRAY_ONLY) for one camera.
  * stack = [2+2*nbits_col+2*nbits_row][H][W]. col,row: int32[H*W] (-1 where masked). */

@@ -130,7 +130,8 @@ extern "C" slr_status slr_destroy(slr_engine *e)
 extern "C" slr_status slr_set_stream(slr_engine *e, void *cuda_stream)
 {
     SLR_REQUIRE(e != nullptr, "slr_set_stream: engine is NULL");
-    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    // NULL is the CUDA legacy default stream (what torch uses unless told otherwise), as in the CUDA API.
+    e->stream = (cuda_stream == SLR_STREAM_OWN) ? e->own_stream : (cudaStream_t)cuda_stream;
     return SLR_OK;
 }
 
