@@ -1,4 +1,30 @@
-// k_fused.cu — fused pipelines (decode + match + triangulate in one kernel).
+// k_fused.cu — the fused multi-frequency pipeline: shadow mask + phase decode + heterodyne +
+// per-row phase correspondence + Q-matrix triangulation in ONE kernel.
+// Replaces MFReconstruct::runReconstruction minus image IO (Duke/mfreconstruct.cpp:160-334).
+//
+// HBM traffic is the algorithmic minimum: every stack byte is read once (TMA bulk copies into
+// shared memory), every output byte written once (TMA bulk stores); the phase maps never exist in
+// global memory.  One persistent CTA owns one rectified row of one scan at a time:
+//
+//   [TMA]   the 2*N image rows (both cameras, all planes) of the NEXT row stream into the stage
+//           buffer while the current row is matched and triangulated;
+//   decode  4 pixels per thread from shared memory, strict mode through two small tables
+//           (exact integer quotient by reciprocal multiplication, and the finite set of wrapped
+//           phase values atan(float(q)) + {0, PI, 2PI} held as doubles), heterodyne in fp64/fp32
+//           exactly as the reference evaluates it;
+//   match   right-row phases go into an open-addressing table keyed by the exact float value
+//           (atomicCAS) holding the minimum column (atomicMin): strict-mode phases repeat heavily
+//           (a few values occupy ~7 % of a row each), and only the smallest k of equal values can be
+//           "the first k".  Distinct values are then chained by phase bucket (width 1/8 > 0.1) and each
+//           left pixel probes the three buckets that can hold a match with the exact predicate,
+//           keeping the minimum k  ==  the reference's first-k linear scan, exactly;
+//   emit    Q reprojection in fp64 with the precomputed undistortPoints maps, staged in smem,
+//           written by TMA bulk stores.
+//
+// Rows are visited row-index-major (all scans' row i back to back) so the undistort-map row stays
+// hot in L2 while the image stacks stream through with an evict-first policy.
+#include <limits.h>
+
 #include "slr_device.cuh"
 
 slr_status slr_unfused_mf(slr_engine *e, const uint8_t *d_stack, int batch, int F, int S, int black_thr, int mode,
@@ -7,11 +33,424 @@ slr_status slr_unfused_ge(slr_engine *e, const uint8_t *d_stack, int batch, int 
                           int white_thr, int scan_w, int have_color, float *d_xyz, uint8_t *d_valid,
                           int32_t *d_match_k, uint8_t *d_color, unsigned long long *d_n_points);
 
+namespace {
+
+constexpr int FUSED_MAX_THREADS = 512;
+constexpr int FUSED_MAX_CHUNKS = 2;  // 4-pixel chunks per thread per camera row
+constexpr uint32_t KEY_EMPTY = 0xFFFFFFFFu;
+
+struct FusedParams {
+    const uint8_t *stack;  // [batch][2][N][H][W]
+    int W, H, batch, F, S, N;
+    int T, logT;           // dedupe table / bucket heads size (power of two)
+    int black_thr;
+    const float *lx, *ly, *rx;
+    const double *ptab;    // strict: [4][512] wrapped-phase values; see build_strict_tables()
+    const uint32_t *mtab;  // strict: [256] reciprocal multipliers
+    float cs[16], sn[16];  // corrected: cos/sin(2 pi s / S)
+    float *xyz;
+    uint8_t *valid;
+    int32_t *match_k;
+    unsigned long long *n_points;
+    slr_calib_dev calib;
+};
+
+__device__ __forceinline__ uint64_t make_evict_first_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar,
+                                                 uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            slr::smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(slr::smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+// ---- strict decode of one pixel from table lookups (Duke/mfreconstruct.cpp:239-268) ----------------
+// Returns the wrapped phase of one frequency as a double holding the reference's float value.
+__device__ __forceinline__ double wrapped_strict_tab(int G1, int G2, int G3, int G4, const double *ptab,
+                                                     const uint32_t *mtab, bool &ok)
+{
+    const int a = G4 - G2, b = G1 - G3;
+    const int ua = abs(a), ub = abs(b);
+    // floor(ua/ub) for 0 <= ua,ub <= 255 via M = floor(65536/ub)+1: the excess ua/65536 < 1/256 <= 1/ub can never
+    // reach the next integer because a non-integer quotient has a fractional part <= 1 - 1/ub.
+    const int q = (int)(((uint32_t)ua * mtab[ub]) >> 16);
+    const int qs = ((a ^ b) < 0) ? -q : q;              // C++ int division truncates toward zero
+    int idx = ((b < 0) ? 512 : ((a > 0) ? 1024 : 0)) + 256 + qs;
+    if (b == 0) {
+        idx = 1536 + ((a > 0) ? 1 : 0);                 // :250 / :252
+        ok = ok && (a != 0);                            // :254 degenerate
+    }
+    return ptab[idx];
+}
+
+__device__ __forceinline__ float heterodyne_strict_d(double P0, double P1, double P2)
+{
+    constexpr float PI_2 = 2.0f * SLR_PI_DEC;
+    const double c = (double)PI_2;
+    double d01 = __dsub_rn(P0, P1);
+    double d12 = __dsub_rn(P1, P2);
+    if (!(P0 > P1)) d01 = __dadd_rn(d01, c);
+    if (!(P1 > P2)) d12 = __dadd_rn(d12, c);
+    const float P12 = __double2float_rn(d01);
+    const float P23 = __double2float_rn(d12);
+    const float d = __fsub_rn(P12, P23);
+    const float P123 = (P12 > P23) ? d : __fadd_rn(d, PI_2);
+    return __fmul_rn(__fdiv_rn(P123, PI_2), 255.0f);
+}
+
+template <int MODE>
+__device__ __forceinline__ void decode_chunk(const uint8_t *__restrict__ rows, int W, int c, const FusedParams &p,
+                                             const double *s_ptab, const uint32_t *s_mtab, float (&ph)[4],
+                                             bool (&ok)[4])
+{
+    // rows = [N][W] u8 for one camera in shared memory; c = 4-pixel chunk index
+    const uint32_t *base = reinterpret_cast<const uint32_t *>(rows) + c;
+    const int wstride = W >> 2;
+    const uint32_t wv = base[0], bv = base[wstride];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        ok[i] = (int)((wv >> (8 * i)) & 0xff) - (int)((bv >> (8 * i)) & 0xff) > p.black_thr;  // computeShadows
+    if (MODE == SLR_MODE_STRICT) {
+        double P[3][4];
+#pragma unroll
+        for (int f = 0; f < 3; f++) {
+            const uint32_t g1 = base[(2 + 4 * f) * wstride], g2 = base[(3 + 4 * f) * wstride];
+            const uint32_t g3 = base[(4 + 4 * f) * wstride], g4 = base[(5 + 4 * f) * wstride];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int sh = 8 * i;
+                P[f][i] = wrapped_strict_tab((g1 >> sh) & 0xff, (g2 >> sh) & 0xff, (g3 >> sh) & 0xff, (g4 >> sh) & 0xff,
+                                             s_ptab, s_mtab, ok[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) ph[i] = heterodyne_strict_d(P[0][i], P[1][i], P[2][i]);
+    } else {
+        float lvl[8][4];
+        const int F = p.F, S = p.S;
+        for (int f = 0; f < F; f++) {
+            float num[4] = {0, 0, 0, 0}, den[4] = {0, 0, 0, 0};
+            int inum[4] = {0, 0, 0, 0}, iden[4] = {0, 0, 0, 0};
+            for (int s = 0; s < S; s++) {
+                const uint32_t v = base[(2 + S * f + s) * wstride];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int g = (int)((v >> (8 * i)) & 0xff);
+                    if (S == 4) {
+                        inum[i] += (s == 3) ? g : (s == 1) ? -g : 0;
+                        iden[i] += (s == 0) ? g : (s == 2) ? -g : 0;
+                    } else {
+                        num[i] = __fsub_rn(num[i], __fmul_rn((float)g, p.sn[s]));
+                        den[i] = __fadd_rn(den[i], __fmul_rn((float)g, p.cs[s]));
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float nn = num[i], dd = den[i];
+                if (S == 4) {
+                    nn = (float)inum[i];
+                    dd = (float)iden[i];
+                    if (inum[i] == 0 && iden[i] == 0) ok[i] = false;
+                } else if (__fadd_rn(__fmul_rn(nn, nn), __fmul_rn(dd, dd)) < 0.25f) {
+                    ok[i] = false;
+                }
+                float a = atan2f(nn, dd);
+                if (a < 0.0f) a = __fadd_rn(a, SLR_TWO_PI_F);
+                lvl[f][i] = a;
+            }
+        }
+        for (int n = F; n > 1; n--)
+            for (int j = 0; j + 1 < n; j++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) lvl[j][i] = slr::wrap_2pi(__fsub_rn(lvl[j][i], lvl[j + 1][i]));
+#pragma unroll
+        for (int i = 0; i < 4; i++) ph[i] = __fmul_rn(__fdiv_rn(lvl[0][i], SLR_TWO_PI_F), 255.0f);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(FUSED_MAX_THREADS, 1)
+k_fused_mf(const FusedParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int W = p.W, N = p.N, T = p.T;
+    const long long rows = (long long)p.batch * p.H;
+    if ((long long)blockIdx.x >= rows) return;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+
+    // ---- shared memory carve-up ----
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+    unsigned char *stage = smem + 16;                               // [2][N][W] u8
+    const size_t stage_bytes = (size_t)2 * N * W;
+    uint32_t *keys = reinterpret_cast<uint32_t *>(stage + stage_bytes);  // [T]
+    int *mink = reinterpret_cast<int *>(keys + T);                  // [T]
+    int *head = mink + T;                                           // [T]
+    int *nxt = head + T;                                            // [T]
+    float *o_xyz = reinterpret_cast<float *>(nxt + T);              // [3W]
+    int *o_k = reinterpret_cast<int *>(o_xyz + 3 * W);              // [W]
+    uint8_t *o_valid = reinterpret_cast<uint8_t *>(o_k + W);        // [W]
+    double *s_ptab = reinterpret_cast<double *>(o_valid + W);       // [2048] (strict)
+    uint32_t *s_mtab = reinterpret_cast<uint32_t *>(s_ptab + 2048); // [256]  (strict)
+
+    if (MODE == SLR_MODE_STRICT) {
+        for (int i = tid; i < 2048; i += nthr) s_ptab[i] = p.ptab[i];
+        for (int i = tid; i < 256; i += nthr) s_mtab[i] = p.mtab[i];
+    }
+    uint64_t policy = 0;
+    if (tid == 0) {
+        slr::mbar_init(bar, 1);
+        slr::mbar_fence_init();
+        policy = make_evict_first_policy();
+    }
+    __syncthreads();
+
+    // row-index-major visiting order: r -> (i = r / batch, b = r % batch)
+    auto issue_row = [&](long long r) {
+        const int i = (int)(r / p.batch);
+        const int b = (int)(r - (long long)i * p.batch);
+        slr::mbar_expect_tx(bar, (uint32_t)stage_bytes);
+        const uint8_t *src = p.stack + ((size_t)b * 2 * N * p.H + i) * W;
+        for (int v = 0; v < 2 * N; v++)   // plane v of this scan (cam-major, then image index)
+            tma_load_1d_hint(stage + (size_t)v * W, src + (size_t)v * p.H * W, (uint32_t)W, bar, policy);
+    };
+    if (tid == 0) issue_row(blockIdx.x);
+
+    const int nchunks = W >> 2;
+    unsigned n_local = 0;
+    int it = 0;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x, ++it) {
+        const int i = (int)(r / p.batch);
+        const int b = (int)(r - (long long)i * p.batch);
+
+        // clear the tables while the stage fills
+        for (int t = tid; t < T; t += nthr) {
+            keys[t] = KEY_EMPTY;
+            mink[t] = INT_MAX;
+            head[t] = -1;
+        }
+        slr::mbar_wait(bar, it & 1);
+
+        // ---- decode LEFT into registers (no table access yet) ----
+        float pl[FUSED_MAX_CHUNKS][4];
+        bool okl[FUSED_MAX_CHUNKS][4];
+#pragma unroll
+        for (int cc = 0; cc < FUSED_MAX_CHUNKS; cc++) {
+            const int c = tid + cc * nthr;
+#pragma unroll
+            for (int q = 0; q < 4; q++) okl[cc][q] = false, pl[cc][q] = 0.0f;
+            if (c < nchunks) decode_chunk<MODE>(stage, W, c, p, s_ptab, s_mtab, pl[cc], okl[cc]);
+        }
+        __syncthreads();  // tables cleared
+
+        // ---- decode RIGHT and insert (value -> min column) ----
+#pragma unroll
+        for (int cc = 0; cc < FUSED_MAX_CHUNKS; cc++) {
+            const int c = tid + cc * nthr;
+            if (c < nchunks) {
+                float pr[4];
+                bool okr[4];
+                decode_chunk<MODE>(stage + (size_t)N * W, W, c, p, s_ptab, s_mtab, pr, okr);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (okr[q]) {
+                        const uint32_t key = __float_as_uint(__fadd_rn(pr[q], 0.0f));  // -0 -> +0
+                        uint32_t h = (key * 2654435761u) >> (32 - p.logT);
+                        while (true) {
+                            const uint32_t old = atomicCAS(&keys[h], KEY_EMPTY, key);
+                            if (old == KEY_EMPTY || old == key) {
+                                atomicMin(&mink[h], 4 * c + q);
+                                break;
+                            }
+                            h = (h + 1) & (T - 1);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();  // stage fully consumed, table complete
+
+        if (tid == 0 && r + gridDim.x < rows) issue_row(r + gridDim.x);  // prefetch the next row
+
+        // ---- chain the distinct values by phase bucket ----
+        for (int t = tid; t < T; t += nthr) {
+            const uint32_t key = keys[t];
+            if (key != KEY_EMPTY) {
+                const int slot = slr::phase_bucket(__uint_as_float(key)) & (T - 1);
+                nxt[t] = atomicExch(&head[slot], t);
+            }
+        }
+        if (tid == 0) slr::tma_store_wait_read<0>();  // previous row's staged outputs have left smem
+        __syncthreads();
+
+        // ---- query + emit ----
+        const size_t map_row = (size_t)i * W;
+#pragma unroll
+        for (int cc = 0; cc < FUSED_MAX_CHUNKS; cc++) {
+            const int c = tid + cc * nthr;
+            if (c < nchunks) {
+                float4 lxv = make_float4(0, 0, 0, 0), lyv = lxv;
+                bool anyl = okl[cc][0] || okl[cc][1] || okl[cc][2] || okl[cc][3];
+                if (anyl) {
+                    lxv = __ldg(reinterpret_cast<const float4 *>(p.lx + map_row) + c);
+                    lyv = __ldg(reinterpret_cast<const float4 *>(p.ly + map_row) + c);
+                }
+                const float lxa[4] = {lxv.x, lxv.y, lxv.z, lxv.w}, lya[4] = {lyv.x, lyv.y, lyv.z, lyv.w};
+                uint32_t vmask = 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int j = 4 * c + q;
+                    int best = INT_MAX;
+                    if (okl[cc][q]) {
+                        const float v = pl[cc][q];
+                        const int b0 = slr::phase_bucket(v);
+#pragma unroll
+                        for (int db = -1; db <= 1; db++) {
+                            int t = head[(b0 + db) & (T - 1)];
+                            while (t >= 0) {
+                                if (slr::phase_match(v, __uint_as_float(keys[t]))) best = min(best, mink[t]);
+                                t = nxt[t];
+                            }
+                        }
+                    }
+                    float X = slr::qnan(), Y = slr::qnan(), Z = slr::qnan();
+                    const bool hit = (best != INT_MAX);
+                    if (hit) {
+                        const float urx = __ldg(p.rx + map_row + best);
+                        const float disp = __fsub_rn(lxa[q], urx);
+                        slr::reproject_q(p.calib, (double)lxa[q], (double)lya[q], (double)disp, X, Y, Z);
+                        n_local++;
+                        vmask |= 1u << (8 * q);
+                    }
+                    o_xyz[3 * j + 0] = X;
+                    o_xyz[3 * j + 1] = Y;
+                    o_xyz[3 * j + 2] = Z;
+                    o_k[j] = hit ? best : -1;
+                }
+                reinterpret_cast<uint32_t *>(o_valid)[c] = vmask;
+            }
+        }
+        slr::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            const size_t orow = ((size_t)b * p.H + i) * W;
+            slr::tma_store_1d(p.xyz + orow * 3, o_xyz, 12 * W);
+            slr::tma_store_1d(p.valid + orow, o_valid, W);
+            if (p.match_k) slr::tma_store_1d(p.match_k + orow, o_k, 4 * W);
+            slr::tma_store_commit();
+        }
+    }
+    if (tid == 0) slr::tma_store_wait_all<0>();
+    if (p.n_points) {
+        const unsigned long long s = slr::warp_sum_u32(n_local);
+        if ((tid & 31) == 0 && s) atomicAdd(p.n_points, s);
+    }
+}
+
+}  // namespace
+
+// strict-mode tables, built once per engine on the host with the host libm:
+//   ptab[cs*512 + 256 + q]  (double holding the reference's float wrapped phase)
+//      cs = 0: b > 0, a <= 0   atan(float(q))            (Duke/mfreconstruct.cpp:261, and :246 via q = 0)
+//      cs = 1: b < 0           atan(float(q)) + PI       (:257, and :248 via q = 0)
+//      cs = 2: b > 0, a > 0    atan(float(q)) + 2*PI     (:259)
+//      cs = 3: b == 0          [0] = PI/2 (a < 0, :252), [1] = 3*PI/2 (a > 0, :250)
+//   mtab[ub] = floor(65536/ub) + 1  (mtab[0] = 0)
+slr_status slr_build_strict_tables(slr_engine *e)
+{
+    static double ptab[2048];
+    static uint32_t mtab[256];
+    const float PI = SLR_PI_DEC;
+    for (int i = 0; i < 2048; i++) ptab[i] = 0.0;
+    for (int q = -255; q <= 255; q++) {
+        const float at = atanf((float)q);
+        ptab[0 * 512 + 256 + q] = (double)at;
+        ptab[1 * 512 + 256 + q] = (double)(at + PI);
+        ptab[2 * 512 + 256 + q] = (double)(at + 2.0f * PI);
+    }
+    ptab[1536 + 0] = (double)(PI / 2.0f);
+    ptab[1536 + 1] = (double)(3.0f * PI / 2.0f);
+    mtab[0] = 0;
+    for (int ub = 1; ub < 256; ub++) mtab[ub] = 65536u / (uint32_t)ub + 1u;
+    if (!e->d_ptab) SLR_CHECK_CUDA(cudaMalloc(&e->d_ptab, sizeof(ptab)));
+    if (!e->d_mtab) SLR_CHECK_CUDA(cudaMalloc(&e->d_mtab, sizeof(mtab)));
+    SLR_CHECK_CUDA(cudaMemcpy(e->d_ptab, ptab, sizeof(ptab), cudaMemcpyHostToDevice));
+    SLR_CHECK_CUDA(cudaMemcpy(e->d_mtab, mtab, sizeof(mtab), cudaMemcpyHostToDevice));
+    return SLR_OK;
+}
+
+static size_t fused_smem_bytes(int W, int N, int T)
+{
+    return 16 + (size_t)2 * N * W + (size_t)16 * T + (size_t)12 * W + (size_t)4 * W + (size_t)W + 2048 * 8 + 256 * 4;
+}
+
 slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch, int F, int S, int black_thr,
                                int mode, float *d_xyz, uint8_t *d_valid, int32_t *d_match_k,
                                unsigned long long *d_n_points)
 {
-    return slr_unfused_mf(e, d_stack, batch, F, S, black_thr, mode, d_xyz, d_valid, d_match_k, d_n_points);
+    if (mode == SLR_MODE_STRICT)
+        SLR_REQUIRE(F == 3 && S == 4, "strict mode reproduces the reference's hard-coded 3 frequencies x 4 steps "
+                                      "(Duke/mfreconstruct.cpp:237); got F=%d S=%d", F, S);
+    else
+        SLR_REQUIRE(mode == SLR_MODE_CORRECTED && F >= 1 && F <= 8 && S >= 3 && S <= 16,
+                    "corrected mode supports 1<=F<=8, 3<=S<=16; got mode %d F=%d S=%d", mode, F, S);
+    const int W = e->W, N = 2 + F * S;
+    int T = 64, logT = 6;
+    while (T < W || (double)W / T > 0.7) T <<= 1, logT++;
+    const size_t smem = fused_smem_bytes(W, N, T);
+    const int nchunks = W / 4;
+    const int per = (nchunks + FUSED_MAX_THREADS - 1) / FUSED_MAX_THREADS;
+    const bool aligned = ((uintptr_t)d_stack | (uintptr_t)d_xyz | (uintptr_t)d_valid | (uintptr_t)d_match_k) % 16 == 0;
+    if (W % 16 != 0 || smem > 227 * 1024 || per > FUSED_MAX_CHUNKS || !aligned || batch > 65535)
+        return slr_unfused_mf(e, d_stack, batch, F, S, black_thr, mode, d_xyz, d_valid, d_match_k, d_n_points);
+
+    int threads = ((nchunks + per - 1) / per + 31) / 32 * 32;
+    if (threads < 64) threads = 64;
+    FusedParams p;
+    p.stack = d_stack;
+    p.W = W;
+    p.H = e->H;
+    p.batch = batch;
+    p.F = F;
+    p.S = S;
+    p.N = N;
+    p.T = T;
+    p.logT = logT;
+    p.black_thr = black_thr;
+    p.lx = e->d_undist_lx;
+    p.ly = e->d_undist_ly;
+    p.rx = e->d_undist_rx;
+    p.ptab = e->d_ptab;
+    p.mtab = e->d_mtab;
+    for (int s = 0; s < 16; s++) {
+        p.cs[s] = (s < S) ? (float)cos(2.0 * 3.14159265358979323846 * s / S) : 0.0f;
+        p.sn[s] = (s < S) ? (float)sin(2.0 * 3.14159265358979323846 * s / S) : 0.0f;
+    }
+    p.xyz = d_xyz;
+    p.valid = d_valid;
+    p.match_k = d_match_k;
+    p.n_points = d_n_points;
+    p.calib = e->calib;
+
+    auto kern = (mode == SLR_MODE_STRICT) ? k_fused_mf<SLR_MODE_STRICT> : k_fused_mf<SLR_MODE_CORRECTED>;
+    SLR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    SLR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ < 1) occ = 1;
+    long long grid = (long long)e->num_sms * occ;
+    const long long rows = (long long)batch * e->H;
+    if (grid > rows) grid = rows;
+    if (grid < 1) return SLR_OK;
+    kern<<<(unsigned)grid, threads, smem, e->stream>>>(p);
+    SLR_CHECK_LAUNCH(e);
+    return SLR_OK;
 }
 
 slr_status slr_launch_fused_ge(slr_engine *e, const uint8_t *d_stack, int batch, int nbits_col, int black_thr,

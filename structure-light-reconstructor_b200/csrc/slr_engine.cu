@@ -36,6 +36,8 @@ static void free_engine(slr_engine *e)
     cudaFree(e->d_undist_ly);
     cudaFree(e->d_undist_rx);
     cudaFree(e->d_atan_lut);
+    cudaFree(e->d_ptab);
+    cudaFree(e->d_mtab);
     cudaFree(e->d_phase);
     cudaFree(e->d_code);
     cudaFree(e->d_mask);
@@ -114,6 +116,10 @@ extern "C" slr_status slr_create(slr_engine **out, int device, int width, int he
     }
     e->num_sms = prop.multiProcessorCount;
     e->stream = e->own_stream;
+    if (slr_build_strict_tables(e) != SLR_OK) {
+        free_engine(e);
+        return SLR_ERR_CUDA;
+    }
     *out = e;
     return SLR_OK;
 }

@@ -36,6 +36,9 @@ struct slr_engine {
     float *d_undist_lx = nullptr, *d_undist_ly = nullptr, *d_undist_rx = nullptr;
     // atan(float(q)) for q in [-255, 255] (index q+255), built on the host with the host libm.
     float *d_atan_lut = nullptr;
+    // strict-mode tables of the fused kernel (k_fused.cu: slr_build_strict_tables)
+    double *d_ptab = nullptr;
+    uint32_t *d_mtab = nullptr;
 
     // scratch for the un-fused pipelines / host entry points
     float *d_phase = nullptr;      // [max_batch][2][H][W]
@@ -103,6 +106,7 @@ slr_status slr_launch_fused_ge(slr_engine *e, const uint8_t *d_stack, int batch,
                                float *d_xyz, uint8_t *d_valid, int32_t *d_match_k, uint8_t *d_color,
                                unsigned long long *d_n_points);
 slr_status slr_launch_undistort_maps(slr_engine *e);
+slr_status slr_build_strict_tables(slr_engine *e);
 slr_status slr_launch_synth_mf(slr_engine *e, uint8_t *d_stack, int batch, int proj_w, unsigned seed,
                                int integer_disparity, float noise_dn);
 slr_status slr_launch_synth_gray(slr_engine *e, uint8_t *d_stack, int batch, int scan_w, unsigned seed,

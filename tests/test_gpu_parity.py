@@ -297,3 +297,29 @@ def test_run_ge_full_frame_vs_oracle(cuda_engine_factory, oracle):
     assert (colr[0].cpu().numpy() == col_o).all()
     assert_float_parity(xyz[0].cpu().numpy(), xyz_o, "GE XYZ full frame")
     assert int(n.item()) == n_o and n_o > 0.3 * W * H
+
+
+@pytest.mark.parametrize("mode,F,S,W,H", [(0, 3, 4, 1280, 40), (1, 3, 4, 1280, 40), (1, 4, 8, 640, 24), (0, 3, 4, 2048, 16),
+                                         (0, 3, 4, 4096, 8), (0, 3, 4, 48, 5)])
+def test_fused_equals_unfused_kernels(cuda_engine_factory, mode, F, S, W, H):
+    """slr_run_mf (one fused kernel where the shape allows) against K1 + K3a run back to back: same device
+    arithmetic, so every output must be identical, in both decode modes and for widths that take the
+    two-chunk (2048), un-fused fallback (4096) and tiny-row (48) routes."""
+    import torch
+    eng = cuda_engine_factory(W, H, 2)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    rng = np.random.default_rng(W + F)
+    if F == 3 and S == 4:
+        stack = np.stack([synth.synth_mf(W, H, seed=s, noise_dn=1.0, integer_disparity=(mode == 0)) for s in (3, 4)])
+    else:
+        stack = rng.integers(0, 256, (2, 2, 2 + F * S, H, W)).astype(np.uint8)
+        stack[:, :, 0] = 230
+        stack[:, :, 1] = 12
+    st = _t(stack)
+    xyz, valid, k, n = eng.run_mf(st, F=F, S=S, black_thr=40, mode=mode)
+    ph, mk = eng.mf_decode(st, F=F, S=S, black_thr=40, mode=mode)
+    xyz2, valid2, k2, n2 = eng.match_triangulate_phase(ph, mk)
+    assert torch.equal(k, k2) and torch.equal(valid, valid2)
+    assert (bits(xyz.cpu().numpy()) == bits(xyz2.cpu().numpy())).all()
+    assert int(n.item()) == int(n2.item()) == int(valid.sum().item())
