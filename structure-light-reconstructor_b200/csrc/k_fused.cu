@@ -15,11 +15,13 @@
 //   match   right-row phases go into an open-addressing table keyed by the exact float value
 //           (atomicCAS) holding the minimum column (atomicMin): strict-mode phases repeat heavily
 //           (a few values occupy ~7 % of a row each), and only the smallest k of equal values can be
-//           "the first k".  Distinct values are then chained by phase bucket (width 1/8 > 0.1) and each
-//           left pixel probes the three buckets that can hold a match with the exact predicate,
-//           keeping the minimum k  ==  the reference's first-k linear scan, exactly;
-//   emit    Q reprojection in fp64 with the precomputed undistortPoints maps, staged in smem,
-//           written by TMA bulk stores.
+//           "the first k".  Each distinct value is then filed under the one or two phase buckets
+//           (width 1/4) its +-0.1 match window touches, so a left pixel walks a single short chain,
+//           applies the exact predicate and keeps the minimum k  ==  the reference's first-k linear
+//           scan, exactly;
+//   emit    Q reprojection in fp64 with the precomputed undistortPoints maps; each thread owns four
+//           consecutive pixels and writes its 48 B of XYZ / 4 B of valid / 16 B of match_k with
+//           128-bit streaming stores.
 //
 // Rows are visited row-index-major (all scans' row i back to back) so the undistort-map row stays
 // hot in L2 while the image stacks stream through with an evict-first policy.
@@ -71,8 +73,23 @@ __device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gme
         : "memory");
 }
 
+// byte i of a 32-bit word, zero extended: one PRMT
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return __byte_perm(w, 0, 0x4440 + i); }
+
+// Window buckets.  Bucket width 1/4; a right value pR is filed under every bucket that the interval
+// [pR - 0.11, pR + 0.11] touches (one or two), so a left value only probes its own bucket: any pL with
+// fabs(pL - pR) < 0.1 lies inside that interval, and the clamp keeps the mapping monotone for huge values
+// (where float spacing exceeds the margin every such value shares the end bucket).
+__device__ __forceinline__ int window_bucket(float p)
+{
+    return __float2int_rd(__fmul_rn(fminf(fmaxf(p, -30000.0f), 30000.0f), 4.0f));
+}
+
 // ---- strict decode of one pixel from table lookups (Duke/mfreconstruct.cpp:239-268) ----------------
 // Returns the wrapped phase of one frequency as a double holding the reference's float value.
+// ptab rows (512 doubles each, entry 256 + signed quotient):
+//   0: b > 0, a <= 0 -> atan(q)          1: b < 0 -> atan(q) + PI        2: b > 0, a > 0 -> atan(q) + 2PI
+//   3: b == 0 -> 3PI/2 (a > 0) / PI/2 (a < 0); mtab[0] = 65536 makes the "quotient" there equal to a.
 __device__ __forceinline__ double wrapped_strict_tab(int G1, int G2, int G3, int G4, const double *ptab,
                                                      const uint32_t *mtab, bool &ok)
 {
@@ -81,18 +98,18 @@ __device__ __forceinline__ double wrapped_strict_tab(int G1, int G2, int G3, int
     // floor(ua/ub) for 0 <= ua,ub <= 255 via M = floor(65536/ub)+1: the excess ua/65536 < 1/256 <= 1/ub can never
     // reach the next integer because a non-integer quotient has a fractional part <= 1 - 1/ub.
     const int q = (int)(((uint32_t)ua * mtab[ub]) >> 16);
-    const int qs = ((a ^ b) < 0) ? -q : q;              // C++ int division truncates toward zero
-    int idx = ((b < 0) ? 512 : ((a > 0) ? 1024 : 0)) + 256 + qs;
-    if (b == 0) {
-        idx = 1536 + ((a > 0) ? 1 : 0);                 // :250 / :252
-        ok = ok && (a != 0);                            // :254 degenerate
-    }
-    return ptab[idx];
+    const int sg = (a ^ b) >> 31;                       // C++ int division truncates toward zero
+    const int qs = (q ^ sg) - sg;
+    int row = (b < 0) ? 512 : ((a > 0) ? 1024 : 0);
+    row = (ub == 0) ? 1536 : row;                       // :250 / :252
+    ok = ok && ((ua | ub) != 0);                        // :254 degenerate
+    return ptab[row + 256 + qs];
 }
 
 __device__ __forceinline__ float heterodyne_strict_d(double P0, double P1, double P2)
 {
     constexpr float PI_2 = 2.0f * SLR_PI_DEC;
+    constexpr float RPI_2 = 1.0f / PI_2;                // RN(1/(2*PI))
     const double c = (double)PI_2;
     double d01 = __dsub_rn(P0, P1);
     double d12 = __dsub_rn(P1, P2);
@@ -102,7 +119,14 @@ __device__ __forceinline__ float heterodyne_strict_d(double P0, double P1, doubl
     const float P23 = __double2float_rn(d12);
     const float d = __fsub_rn(P12, P23);
     const float P123 = (P12 > P23) ? d : __fadd_rn(d, PI_2);
-    return __fmul_rn(__fdiv_rn(P123, PI_2), 255.0f);
+    // P123 / (2*PI), correctly rounded, without the generic division routine: with rc = RN(1/c),
+    // q0 = RN(x*rc), rem = x - c*q0 (exact in an FMA), RN(q0 + rem*rc) == RN(x/c).  Verified
+    // exhaustively on the host against IEEE division for every float with 2^-100 <= |x| < 32 and x = +0
+    // (scratch/div_check.c); P123 is +0-free of sign issues and a multiple of 2^-24, so it is in range.
+    const float q0 = __fmul_rn(P123, RPI_2);
+    const float rem = __fmaf_rn(-q0, PI_2, P123);
+    const float quo = __fmaf_rn(rem, RPI_2, q0);
+    return __fmul_rn(quo, 255.0f);
 }
 
 template <int MODE>
@@ -115,8 +139,7 @@ __device__ __forceinline__ void decode_chunk(const uint8_t *__restrict__ rows, i
     const int wstride = W >> 2;
     const uint32_t wv = base[0], bv = base[wstride];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-        ok[i] = (int)((wv >> (8 * i)) & 0xff) - (int)((bv >> (8 * i)) & 0xff) > p.black_thr;  // computeShadows
+    for (int i = 0; i < 4; i++) ok[i] = (int)byte_of(wv, i) - (int)byte_of(bv, i) > p.black_thr;  // computeShadows
     if (MODE == SLR_MODE_STRICT) {
         double P[3][4];
 #pragma unroll
@@ -124,11 +147,9 @@ __device__ __forceinline__ void decode_chunk(const uint8_t *__restrict__ rows, i
             const uint32_t g1 = base[(2 + 4 * f) * wstride], g2 = base[(3 + 4 * f) * wstride];
             const uint32_t g3 = base[(4 + 4 * f) * wstride], g4 = base[(5 + 4 * f) * wstride];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int sh = 8 * i;
-                P[f][i] = wrapped_strict_tab((g1 >> sh) & 0xff, (g2 >> sh) & 0xff, (g3 >> sh) & 0xff, (g4 >> sh) & 0xff,
-                                             s_ptab, s_mtab, ok[i]);
-            }
+            for (int i = 0; i < 4; i++)
+                P[f][i] = wrapped_strict_tab(byte_of(g1, i), byte_of(g2, i), byte_of(g3, i), byte_of(g4, i), s_ptab,
+                                             s_mtab, ok[i]);
         }
 #pragma unroll
         for (int i = 0; i < 4; i++) ph[i] = heterodyne_strict_d(P[0][i], P[1][i], P[2][i]);
@@ -142,7 +163,7 @@ __device__ __forceinline__ void decode_chunk(const uint8_t *__restrict__ rows, i
                 const uint32_t v = base[(2 + S * f + s) * wstride];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const int g = (int)((v >> (8 * i)) & 0xff);
+                    const int g = (int)byte_of(v, i);
                     if (S == 4) {
                         inum[i] += (s == 3) ? g : (s == 1) ? -g : 0;
                         iden[i] += (s == 0) ? g : (s == 2) ? -g : 0;
@@ -176,8 +197,10 @@ __device__ __forceinline__ void decode_chunk(const uint8_t *__restrict__ rows, i
     }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(FUSED_MAX_THREADS, 1)
+// MAXT/MINB: launch bounds.  Rows up to 1280 wide run 320-thread CTAs, two per SM (<= 102 registers);
+// wider rows run up to 512 threads, one CTA per SM.
+template <int MODE, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 k_fused_mf(const FusedParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -192,12 +215,10 @@ k_fused_mf(const FusedParams p)
     const size_t stage_bytes = (size_t)2 * N * W;
     uint32_t *keys = reinterpret_cast<uint32_t *>(stage + stage_bytes);  // [T]
     int *mink = reinterpret_cast<int *>(keys + T);                  // [T]
-    int *head = mink + T;                                           // [T]
-    int *nxt = head + T;                                            // [T]
-    float *o_xyz = reinterpret_cast<float *>(nxt + T);              // [3W]
-    int *o_k = reinterpret_cast<int *>(o_xyz + 3 * W);              // [W]
-    uint8_t *o_valid = reinterpret_cast<uint8_t *>(o_k + W);        // [W]
-    double *s_ptab = reinterpret_cast<double *>(o_valid + W);       // [2048] (strict)
+    int *nxt = mink + T;                                            // [2T] node n = entry + T*(0|1)
+    int *head = nxt + 2 * T;                                        // [HB = 2T] bucket heads
+    const int HB = 2 * T;
+    double *s_ptab = reinterpret_cast<double *>(head + HB);         // [2048] (strict)
     uint32_t *s_mtab = reinterpret_cast<uint32_t *>(s_ptab + 2048); // [256]  (strict)
 
     if (MODE == SLR_MODE_STRICT) {
@@ -235,6 +256,7 @@ k_fused_mf(const FusedParams p)
             keys[t] = KEY_EMPTY;
             mink[t] = INT_MAX;
             head[t] = -1;
+            head[t + T] = -1;
         }
         slr::mbar_wait(bar, it & 1);
 
@@ -279,45 +301,47 @@ k_fused_mf(const FusedParams p)
 
         if (tid == 0 && r + gridDim.x < rows) issue_row(r + gridDim.x);  // prefetch the next row
 
-        // ---- chain the distinct values by phase bucket ----
+        // ---- file every distinct value under the bucket(s) its match window touches ----
         for (int t = tid; t < T; t += nthr) {
             const uint32_t key = keys[t];
             if (key != KEY_EMPTY) {
-                const int slot = slr::phase_bucket(__uint_as_float(key)) & (T - 1);
-                nxt[t] = atomicExch(&head[slot], t);
+                const float v = __uint_as_float(key);
+                const int lo = window_bucket(__fsub_rn(v, 0.11f)), hi = window_bucket(__fadd_rn(v, 0.11f));
+                nxt[t] = atomicExch(&head[lo & (HB - 1)], t);
+                if (hi != lo) nxt[t + T] = atomicExch(&head[hi & (HB - 1)], t + T);
             }
         }
-        if (tid == 0) slr::tma_store_wait_read<0>();  // previous row's staged outputs have left smem
         __syncthreads();
 
-        // ---- query + emit ----
+        // ---- query + emit (each thread owns 4 consecutive left pixels per chunk) ----
         const size_t map_row = (size_t)i * W;
+        const size_t orow = ((size_t)b * p.H + i) * W;
 #pragma unroll
         for (int cc = 0; cc < FUSED_MAX_CHUNKS; cc++) {
             const int c = tid + cc * nthr;
             if (c < nchunks) {
                 float4 lxv = make_float4(0, 0, 0, 0), lyv = lxv;
-                bool anyl = okl[cc][0] || okl[cc][1] || okl[cc][2] || okl[cc][3];
+                const bool anyl = okl[cc][0] || okl[cc][1] || okl[cc][2] || okl[cc][3];
                 if (anyl) {
                     lxv = __ldg(reinterpret_cast<const float4 *>(p.lx + map_row) + c);
                     lyv = __ldg(reinterpret_cast<const float4 *>(p.ly + map_row) + c);
                 }
                 const float lxa[4] = {lxv.x, lxv.y, lxv.z, lxv.w}, lya[4] = {lyv.x, lyv.y, lyv.z, lyv.w};
                 uint32_t vmask = 0;
+                float o[12];
+                int ok4[4];
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const int j = 4 * c + q;
                     int best = INT_MAX;
                     if (okl[cc][q]) {
                         const float v = pl[cc][q];
-                        const int b0 = slr::phase_bucket(v);
-#pragma unroll
-                        for (int db = -1; db <= 1; db++) {
-                            int t = head[(b0 + db) & (T - 1)];
-                            while (t >= 0) {
-                                if (slr::phase_match(v, __uint_as_float(keys[t]))) best = min(best, mink[t]);
-                                t = nxt[t];
-                            }
+                        int t = head[window_bucket(v) & (HB - 1)];
+                        while (t >= 0) {
+                            const int e = t & (T - 1);
+                            const float pr = __uint_as_float(keys[e]);
+                            const int kk = mink[e];
+                            t = nxt[t];
+                            if (slr::phase_match(v, pr)) best = min(best, kk);
                         }
                     }
                     float X = slr::qnan(), Y = slr::qnan(), Z = slr::qnan();
@@ -329,25 +353,24 @@ k_fused_mf(const FusedParams p)
                         n_local++;
                         vmask |= 1u << (8 * q);
                     }
-                    o_xyz[3 * j + 0] = X;
-                    o_xyz[3 * j + 1] = Y;
-                    o_xyz[3 * j + 2] = Z;
-                    o_k[j] = hit ? best : -1;
+                    o[3 * q + 0] = X;
+                    o[3 * q + 1] = Y;
+                    o[3 * q + 2] = Z;
+                    ok4[q] = hit ? best : -1;
                 }
-                reinterpret_cast<uint32_t *>(o_valid)[c] = vmask;
+                float4 *dst = reinterpret_cast<float4 *>(p.xyz + (orow + 4 * (size_t)c) * 3);
+                slr::stg_stream_f4(dst + 0, make_float4(o[0], o[1], o[2], o[3]));
+                slr::stg_stream_f4(dst + 1, make_float4(o[4], o[5], o[6], o[7]));
+                slr::stg_stream_f4(dst + 2, make_float4(o[8], o[9], o[10], o[11]));
+                reinterpret_cast<uint32_t *>(p.valid + orow)[c] = vmask;
+                if (p.match_k)
+                    slr::stg_stream_u4(p.match_k + orow + 4 * (size_t)c,
+                                       make_uint4((uint32_t)ok4[0], (uint32_t)ok4[1], (uint32_t)ok4[2], (uint32_t)ok4[3]));
             }
         }
-        slr::fence_proxy_async();
+        // the next iteration clears the tables: every thread must be done probing them
         __syncthreads();
-        if (tid == 0) {
-            const size_t orow = ((size_t)b * p.H + i) * W;
-            slr::tma_store_1d(p.xyz + orow * 3, o_xyz, 12 * W);
-            slr::tma_store_1d(p.valid + orow, o_valid, W);
-            if (p.match_k) slr::tma_store_1d(p.match_k + orow, o_k, 4 * W);
-            slr::tma_store_commit();
-        }
     }
-    if (tid == 0) slr::tma_store_wait_all<0>();
     if (p.n_points) {
         const unsigned long long s = slr::warp_sum_u32(n_local);
         if ((tid & 31) == 0 && s) atomicAdd(p.n_points, s);
@@ -361,8 +384,8 @@ k_fused_mf(const FusedParams p)
 //      cs = 0: b > 0, a <= 0   atan(float(q))            (Duke/mfreconstruct.cpp:261, and :246 via q = 0)
 //      cs = 1: b < 0           atan(float(q)) + PI       (:257, and :248 via q = 0)
 //      cs = 2: b > 0, a > 0    atan(float(q)) + 2*PI     (:259)
-//      cs = 3: b == 0          [0] = PI/2 (a < 0, :252), [1] = 3*PI/2 (a > 0, :250)
-//   mtab[ub] = floor(65536/ub) + 1  (mtab[0] = 0)
+//      cs = 3: b == 0          256 + a: PI/2 (a < 0, :252), 3*PI/2 (a > 0, :250)
+//   mtab[ub] = floor(65536/ub) + 1  (mtab[0] = 65536)
 slr_status slr_build_strict_tables(slr_engine *e)
 {
     static double ptab[2048];
@@ -375,9 +398,11 @@ slr_status slr_build_strict_tables(slr_engine *e)
         ptab[1 * 512 + 256 + q] = (double)(at + PI);
         ptab[2 * 512 + 256 + q] = (double)(at + 2.0f * PI);
     }
-    ptab[1536 + 0] = (double)(PI / 2.0f);
-    ptab[1536 + 1] = (double)(3.0f * PI / 2.0f);
-    mtab[0] = 0;
+    for (int q = 1; q <= 255; q++) {
+        ptab[1536 + 256 + q] = (double)(3.0f * PI / 2.0f);   // b == 0, a > 0 (:250)
+        ptab[1536 + 256 - q] = (double)(PI / 2.0f);          // b == 0, a < 0 (:252)
+    }
+    mtab[0] = 65536u;   // b == 0: the "quotient" is |a| itself (selects within row 3)
     for (int ub = 1; ub < 256; ub++) mtab[ub] = 65536u / (uint32_t)ub + 1u;
     if (!e->d_ptab) SLR_CHECK_CUDA(cudaMalloc(&e->d_ptab, sizeof(ptab)));
     if (!e->d_mtab) SLR_CHECK_CUDA(cudaMalloc(&e->d_mtab, sizeof(mtab)));
@@ -388,7 +413,7 @@ slr_status slr_build_strict_tables(slr_engine *e)
 
 static size_t fused_smem_bytes(int W, int N, int T)
 {
-    return 16 + (size_t)2 * N * W + (size_t)16 * T + (size_t)12 * W + (size_t)4 * W + (size_t)W + 2048 * 8 + 256 * 4;
+    return 16 + (size_t)2 * N * W + (size_t)24 * T + 2048 * 8 + 256 * 4;
 }
 
 slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch, int F, int S, int black_thr,
@@ -439,7 +464,12 @@ slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch,
     p.n_points = d_n_points;
     p.calib = e->calib;
 
-    auto kern = (mode == SLR_MODE_STRICT) ? k_fused_mf<SLR_MODE_STRICT> : k_fused_mf<SLR_MODE_CORRECTED>;
+    void (*kern)(const FusedParams);
+    if (threads <= 320)
+        kern = (mode == SLR_MODE_STRICT) ? k_fused_mf<SLR_MODE_STRICT, 320, 2> : k_fused_mf<SLR_MODE_CORRECTED, 320, 2>;
+    else
+        kern = (mode == SLR_MODE_STRICT) ? k_fused_mf<SLR_MODE_STRICT, FUSED_MAX_THREADS, 1>
+                                         : k_fused_mf<SLR_MODE_CORRECTED, FUSED_MAX_THREADS, 1>;
     SLR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     SLR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));

@@ -206,7 +206,7 @@ __device__ __forceinline__ void reproject_q(const slr_calib_dev &c, double x, do
         double s = __dmul_rn(c.Q[4 * i + 0], x);
         s = __dadd_rn(s, __dmul_rn(c.Q[4 * i + 1], y));
         s = __dadd_rn(s, __dmul_rn(c.Q[4 * i + 2], d));
-        s = __dadd_rn(s, __dmul_rn(c.Q[4 * i + 3], 1.0));
+        s = __dadd_rn(s, c.Q[4 * i + 3]);  // Q[i][3] * 1 is exact
         r[i] = s;
     }
     float px = __double2float_rn(__ddiv_rn(r[0], r[3]));
@@ -219,7 +219,7 @@ __device__ __forceinline__ void reproject_q(const slr_calib_dev &c, double x, do
             double s = __dmul_rn((double)c.rigid[4 * i + 0], (double)px);
             s = __dadd_rn(s, __dmul_rn((double)c.rigid[4 * i + 1], (double)py));
             s = __dadd_rn(s, __dmul_rn((double)c.rigid[4 * i + 2], (double)pz));
-            s = __dadd_rn(s, __dmul_rn((double)c.rigid[4 * i + 3], 1.0));
+            s = __dadd_rn(s, (double)c.rigid[4 * i + 3]);
             o[i] = __double2float_rn(s);
         }
         px = o[0];
