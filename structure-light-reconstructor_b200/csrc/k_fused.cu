@@ -19,13 +19,14 @@
 //           (width 1/4) its +-0.1 match window touches, so a left pixel walks a single short chain,
 //           applies the exact predicate and keeps the minimum k  ==  the reference's first-k linear
 //           scan, exactly;
-//   emit    Q reprojection in fp64 with the precomputed undistortPoints maps; each thread owns four
-//           consecutive pixels and writes its 48 B of XYZ / 4 B of valid / 16 B of match_k with
-//           128-bit streaming stores.
+//   emit    warps take 32-pixel groups of the left row from a shared counter (chain lengths vary along
+//           a row, so static assignment leaves warps idle at the barrier); Q reprojection in fp64 with
+//           the precomputed undistortPoints maps; XYZ / valid / match_k written straight from registers.
 //
 // Rows are visited row-index-major (all scans' row i back to back) so the undistort-map row stays
 // hot in L2 while the image stacks stream through with an evict-first policy.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "slr_device.cuh"
 
@@ -38,7 +39,6 @@ slr_status slr_unfused_ge(slr_engine *e, const uint8_t *d_stack, int batch, int 
 namespace {
 
 constexpr int FUSED_MAX_THREADS = 512;
-constexpr int FUSED_MAX_CHUNKS = 2;  // 4-pixel chunks per thread per camera row
 constexpr uint32_t KEY_EMPTY = 0xFFFFFFFFu;
 
 struct FusedParams {
@@ -211,14 +211,16 @@ k_fused_mf(const FusedParams p)
 
     // ---- shared memory carve-up ----
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+    int *grp_ctr = reinterpret_cast<int *>(smem + 8);               // dynamic query-group counter
     unsigned char *stage = smem + 16;                               // [2][N][W] u8
     const size_t stage_bytes = (size_t)2 * N * W;
-    uint32_t *keys = reinterpret_cast<uint32_t *>(stage + stage_bytes);  // [T]
-    int *mink = reinterpret_cast<int *>(keys + T);                  // [T]
-    int *nxt = mink + T;                                            // [2T] node n = entry + T*(0|1)
-    int *head = nxt + 2 * T;                                        // [HB = 2T] bucket heads
+    uint32_t *keys = reinterpret_cast<uint32_t *>(stage + stage_bytes);  // [T]   distinct right phases (float bits)
+    int *mink = reinterpret_cast<int *>(keys + T);                  // [T]   smallest right column of that phase
+    int *head = mink + T;                                           // [HB = 2T] bucket heads
     const int HB = 2 * T;
-    double *s_ptab = reinterpret_cast<double *>(head + HB);         // [2048] (strict)
+    int *nxt = head + HB;                                           // [2T]  node n = entry + T*(0|1)
+    float *s_pl = reinterpret_cast<float *>(nxt + 2 * T);           // [W]   left phases (NaN = none)
+    double *s_ptab = reinterpret_cast<double *>(s_pl + W);          // [2048] (strict)
     uint32_t *s_mtab = reinterpret_cast<uint32_t *>(s_ptab + 2048); // [256]  (strict)
 
     if (MODE == SLR_MODE_STRICT) {
@@ -245,48 +247,54 @@ k_fused_mf(const FusedParams p)
     if (tid == 0) issue_row(blockIdx.x);
 
     const int nchunks = W >> 2;
+    const int ngroups = (W + 31) >> 5;
+    const int lane = tid & 31;
     unsigned n_local = 0;
     int it = 0;
     for (long long r = blockIdx.x; r < rows; r += gridDim.x, ++it) {
         const int i = (int)(r / p.batch);
         const int b = (int)(r - (long long)i * p.batch);
 
-        // clear the tables while the stage fills
-        for (int t = tid; t < T; t += nthr) {
-            keys[t] = KEY_EMPTY;
-            mink[t] = INT_MAX;
-            head[t] = -1;
-            head[t + T] = -1;
+        // ---- clear the tables while the stage fills: keys = EMPTY, mink = INT_MAX, heads = -1 ----
+        {
+            uint4 *k4 = reinterpret_cast<uint4 *>(keys);
+            uint4 *m4 = reinterpret_cast<uint4 *>(mink);
+            uint4 *h4 = reinterpret_cast<uint4 *>(head);
+            const uint4 e4 = make_uint4(KEY_EMPTY, KEY_EMPTY, KEY_EMPTY, KEY_EMPTY);
+            const uint4 x4 = make_uint4(0x7fffffffu, 0x7fffffffu, 0x7fffffffu, 0x7fffffffu);
+            for (int t = tid; t < (T >> 2); t += nthr) {
+                k4[t] = e4;
+                m4[t] = x4;
+                h4[t] = e4;
+                h4[t + (T >> 2)] = e4;
+            }
+            if (tid == 0) *grp_ctr = 0;
         }
         slr::mbar_wait(bar, it & 1);
+        __syncthreads();  // tables cleared, stage landed
 
-        // ---- decode LEFT into registers (no table access yet) ----
-        float pl[FUSED_MAX_CHUNKS][4];
-        bool okl[FUSED_MAX_CHUNKS][4];
-#pragma unroll
-        for (int cc = 0; cc < FUSED_MAX_CHUNKS; cc++) {
-            const int c = tid + cc * nthr;
-#pragma unroll
-            for (int q = 0; q < 4; q++) okl[cc][q] = false, pl[cc][q] = 0.0f;
-            if (c < nchunks) decode_chunk<MODE>(stage, W, c, p, s_ptab, s_mtab, pl[cc], okl[cc]);
-        }
-        __syncthreads();  // tables cleared
-
-        // ---- decode RIGHT and insert (value -> min column) ----
-#pragma unroll
-        for (int cc = 0; cc < FUSED_MAX_CHUNKS; cc++) {
-            const int c = tid + cc * nthr;
-            if (c < nchunks) {
-                float pr[4];
-                bool okr[4];
-                decode_chunk<MODE>(stage + (size_t)N * W, W, c, p, s_ptab, s_mtab, pr, okr);
+        // ---- decode: tasks [0, nchunks) = right 4-pixel chunks, [nchunks, 2 nchunks) = left chunks ----
+        for (int task = tid; task < 2 * nchunks; task += nthr) {
+            float ph[4];
+            bool ok[4];
+            if (task < nchunks) {
+                const int c = task;
+                decode_chunk<MODE>(stage + (size_t)N * W, W, c, p, s_ptab, s_mtab, ph, ok);
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    if (okr[q]) {
-                        const uint32_t key = __float_as_uint(__fadd_rn(pr[q], 0.0f));  // -0 -> +0
+                    if (ok[q]) {
+                        // value -> min column, deduplicated; the thread that claims a new value also files it
+                        // under the bucket(s) its +-0.1 match window touches
+                        const float v = __fadd_rn(ph[q], 0.0f);  // -0 -> +0
+                        const uint32_t key = __float_as_uint(v);
                         uint32_t h = (key * 2654435761u) >> (32 - p.logT);
                         while (true) {
                             const uint32_t old = atomicCAS(&keys[h], KEY_EMPTY, key);
+                            if (old == KEY_EMPTY) {
+                                const int lo = window_bucket(__fsub_rn(v, 0.11f)), hi = window_bucket(__fadd_rn(v, 0.11f));
+                                nxt[h] = atomicExch(&head[lo & (HB - 1)], (int)h);
+                                if (hi != lo) nxt[h + T] = atomicExch(&head[hi & (HB - 1)], (int)h + T);
+                            }
                             if (old == KEY_EMPTY || old == key) {
                                 atomicMin(&mink[h], 4 * c + q);
                                 break;
@@ -295,80 +303,58 @@ k_fused_mf(const FusedParams p)
                         }
                     }
                 }
+            } else {
+                const int c = task - nchunks;
+                decode_chunk<MODE>(stage, W, c, p, s_ptab, s_mtab, ph, ok);
+                reinterpret_cast<float4 *>(s_pl)[c] = make_float4(ok[0] ? ph[0] : slr::qnan(), ok[1] ? ph[1] : slr::qnan(),
+                                                                  ok[2] ? ph[2] : slr::qnan(), ok[3] ? ph[3] : slr::qnan());
             }
         }
-        __syncthreads();  // stage fully consumed, table complete
+        __syncthreads();  // stage consumed, table + chains + left phases complete
 
         if (tid == 0 && r + gridDim.x < rows) issue_row(r + gridDim.x);  // prefetch the next row
 
-        // ---- file every distinct value under the bucket(s) its match window touches ----
-        for (int t = tid; t < T; t += nthr) {
-            const uint32_t key = keys[t];
-            if (key != KEY_EMPTY) {
-                const float v = __uint_as_float(key);
-                const int lo = window_bucket(__fsub_rn(v, 0.11f)), hi = window_bucket(__fadd_rn(v, 0.11f));
-                nxt[t] = atomicExch(&head[lo & (HB - 1)], t);
-                if (hi != lo) nxt[t + T] = atomicExch(&head[hi & (HB - 1)], t + T);
-            }
-        }
-        __syncthreads();
-
-        // ---- query + emit (each thread owns 4 consecutive left pixels per chunk) ----
+        // ---- query + emit: warps take 32-pixel groups dynamically (chain lengths vary along the row) ----
         const size_t map_row = (size_t)i * W;
         const size_t orow = ((size_t)b * p.H + i) * W;
-#pragma unroll
-        for (int cc = 0; cc < FUSED_MAX_CHUNKS; cc++) {
-            const int c = tid + cc * nthr;
-            if (c < nchunks) {
-                float4 lxv = make_float4(0, 0, 0, 0), lyv = lxv;
-                const bool anyl = okl[cc][0] || okl[cc][1] || okl[cc][2] || okl[cc][3];
-                if (anyl) {
-                    lxv = __ldg(reinterpret_cast<const float4 *>(p.lx + map_row) + c);
-                    lyv = __ldg(reinterpret_cast<const float4 *>(p.ly + map_row) + c);
-                }
-                const float lxa[4] = {lxv.x, lxv.y, lxv.z, lxv.w}, lya[4] = {lyv.x, lyv.y, lyv.z, lyv.w};
-                uint32_t vmask = 0;
-                float o[12];
-                int ok4[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    int best = INT_MAX;
-                    if (okl[cc][q]) {
-                        const float v = pl[cc][q];
-                        int t = head[window_bucket(v) & (HB - 1)];
-                        while (t >= 0) {
-                            const int e = t & (T - 1);
-                            const float pr = __uint_as_float(keys[e]);
-                            const int kk = mink[e];
-                            t = nxt[t];
-                            if (slr::phase_match(v, pr)) best = min(best, kk);
-                        }
+        for (;;) {
+            int g = 0;
+            if (lane == 0) g = atomicAdd(grp_ctr, 1);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            if (g >= ngroups) break;
+            const int j = (g << 5) + lane;
+            if (j < W) {
+                const float v = s_pl[j];
+                int best = INT_MAX;
+                if (v == v) {
+                    int t = head[window_bucket(v) & (HB - 1)];
+                    while (t >= 0) {
+                        const int e = t & (T - 1);
+                        const float pr = __uint_as_float(keys[e]);
+                        const int kk = mink[e];
+                        t = nxt[t];
+                        if (slr::phase_match(v, pr)) best = min(best, kk);
                     }
-                    float X = slr::qnan(), Y = slr::qnan(), Z = slr::qnan();
-                    const bool hit = (best != INT_MAX);
-                    if (hit) {
-                        const float urx = __ldg(p.rx + map_row + best);
-                        const float disp = __fsub_rn(lxa[q], urx);
-                        slr::reproject_q(p.calib, (double)lxa[q], (double)lya[q], (double)disp, X, Y, Z);
-                        n_local++;
-                        vmask |= 1u << (8 * q);
-                    }
-                    o[3 * q + 0] = X;
-                    o[3 * q + 1] = Y;
-                    o[3 * q + 2] = Z;
-                    ok4[q] = hit ? best : -1;
                 }
-                float4 *dst = reinterpret_cast<float4 *>(p.xyz + (orow + 4 * (size_t)c) * 3);
-                slr::stg_stream_f4(dst + 0, make_float4(o[0], o[1], o[2], o[3]));
-                slr::stg_stream_f4(dst + 1, make_float4(o[4], o[5], o[6], o[7]));
-                slr::stg_stream_f4(dst + 2, make_float4(o[8], o[9], o[10], o[11]));
-                reinterpret_cast<uint32_t *>(p.valid + orow)[c] = vmask;
-                if (p.match_k)
-                    slr::stg_stream_u4(p.match_k + orow + 4 * (size_t)c,
-                                       make_uint4((uint32_t)ok4[0], (uint32_t)ok4[1], (uint32_t)ok4[2], (uint32_t)ok4[3]));
+                float X = slr::qnan(), Y = slr::qnan(), Z = slr::qnan();
+                const bool hit = (best != INT_MAX);
+                if (hit) {
+                    const float ulx = __ldg(p.lx + map_row + j);
+                    const float uly = __ldg(p.ly + map_row + j);
+                    const float urx = __ldg(p.rx + map_row + best);
+                    const float disp = __fsub_rn(ulx, urx);
+                    slr::reproject_q(p.calib, (double)ulx, (double)uly, (double)disp, X, Y, Z);
+                    n_local++;
+                }
+                float *dst = p.xyz + (orow + j) * 3;
+                dst[0] = X;
+                dst[1] = Y;
+                dst[2] = Z;
+                p.valid[orow + j] = hit ? 1 : 0;
+                if (p.match_k) p.match_k[orow + j] = hit ? best : -1;
             }
         }
-        // the next iteration clears the tables: every thread must be done probing them
+        // the next iteration clears the tables: every warp must be done probing them
         __syncthreads();
     }
     if (p.n_points) {
@@ -413,7 +399,7 @@ slr_status slr_build_strict_tables(slr_engine *e)
 
 static size_t fused_smem_bytes(int W, int N, int T)
 {
-    return 16 + (size_t)2 * N * W + (size_t)24 * T + 2048 * 8 + 256 * 4;
+    return 16 + (size_t)2 * N * W + (size_t)24 * T + (size_t)4 * W + 2048 * 8 + 256 * 4;
 }
 
 slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch, int F, int S, int black_thr,
@@ -431,13 +417,17 @@ slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch,
     while (T < W || (double)W / T > 0.7) T <<= 1, logT++;
     const size_t smem = fused_smem_bytes(W, N, T);
     const int nchunks = W / 4;
-    const int per = (nchunks + FUSED_MAX_THREADS - 1) / FUSED_MAX_THREADS;
+    const int per = (nchunks + FUSED_MAX_THREADS - 1) / FUSED_MAX_THREADS;  // decode rounds per camera
     const bool aligned = ((uintptr_t)d_stack | (uintptr_t)d_xyz | (uintptr_t)d_valid | (uintptr_t)d_match_k) % 16 == 0;
-    if (W % 16 != 0 || smem > 227 * 1024 || per > FUSED_MAX_CHUNKS || !aligned || batch > 65535)
+    if (W % 16 != 0 || smem > 227 * 1024 || !aligned || batch > 65535)
         return slr_unfused_mf(e, d_stack, batch, F, S, black_thr, mode, d_xyz, d_valid, d_match_k, d_n_points);
 
     int threads = ((nchunks + per - 1) / per + 31) / 32 * 32;
     if (threads < 64) threads = 64;
+    if (const char *ev = getenv("SLR_FUSED_THREADS")) {  // tuning knob (bench experiments)
+        const int t = atoi(ev);
+        if (t >= 64 && t <= FUSED_MAX_THREADS && t % 32 == 0) threads = t;
+    }
     FusedParams p;
     p.stack = d_stack;
     p.W = W;
@@ -467,6 +457,8 @@ slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch,
     void (*kern)(const FusedParams);
     if (threads <= 320)
         kern = (mode == SLR_MODE_STRICT) ? k_fused_mf<SLR_MODE_STRICT, 320, 2> : k_fused_mf<SLR_MODE_CORRECTED, 320, 2>;
+    else if (threads <= 384)
+        kern = (mode == SLR_MODE_STRICT) ? k_fused_mf<SLR_MODE_STRICT, 384, 2> : k_fused_mf<SLR_MODE_CORRECTED, 384, 2>;
     else
         kern = (mode == SLR_MODE_STRICT) ? k_fused_mf<SLR_MODE_STRICT, FUSED_MAX_THREADS, 1>
                                          : k_fused_mf<SLR_MODE_CORRECTED, FUSED_MAX_THREADS, 1>;
