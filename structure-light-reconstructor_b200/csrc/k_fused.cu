@@ -46,6 +46,7 @@ struct FusedParams {
     int W, H, batch, F, S, N;
     int T, logT;           // dedupe table / bucket heads size (power of two)
     int black_thr;
+    int stagger_ns, num_sms;
     const float *lx, *ly, *rx;
     const double *ptab;    // strict: [4][512] wrapped-phase values; see build_strict_tables()
     const uint32_t *mtab;  // strict: [256] reciprocal multipliers
@@ -214,9 +215,9 @@ k_fused_mf(const FusedParams p)
     int *grp_ctr = reinterpret_cast<int *>(smem + 8);               // dynamic query-group counter
     unsigned char *stage = smem + 16;                               // [2][N][W] u8
     const size_t stage_bytes = (size_t)2 * N * W;
-    uint32_t *keys = reinterpret_cast<uint32_t *>(stage + stage_bytes);  // [T]   distinct right phases (float bits)
-    int *mink = reinterpret_cast<int *>(keys + T);                  // [T]   smallest right column of that phase
-    int *head = mink + T;                                           // [HB = 2T] bucket heads
+    // [T] entries {x = distinct right phase (float bits), y = smallest right column carrying it}
+    uint2 *ent = reinterpret_cast<uint2 *>(stage + stage_bytes);
+    int *head = reinterpret_cast<int *>(ent + T);                   // [HB = 2T] bucket heads
     const int HB = 2 * T;
     int *nxt = head + HB;                                           // [2T]  node n = entry + T*(0|1)
     float *s_pl = reinterpret_cast<float *>(nxt + 2 * T);           // [W]   left phases (NaN = none)
@@ -236,37 +237,39 @@ k_fused_mf(const FusedParams p)
     __syncthreads();
 
     // row-index-major visiting order: r -> (i = r / batch, b = r % batch)
-    auto issue_row = [&](long long r) {
-        const int i = (int)(r / p.batch);
-        const int b = (int)(r - (long long)i * p.batch);
+    auto issue_row = [&](unsigned r) {
+        const int i = (int)(r / (unsigned)p.batch);
+        const int b = (int)(r - (unsigned)i * (unsigned)p.batch);
         slr::mbar_expect_tx(bar, (uint32_t)stage_bytes);
         const uint8_t *src = p.stack + ((size_t)b * 2 * N * p.H + i) * W;
         for (int v = 0; v < 2 * N; v++)   // plane v of this scan (cam-major, then image index)
             tma_load_1d_hint(stage + (size_t)v * W, src + (size_t)v * p.H * W, (uint32_t)W, bar, policy);
     };
     if (tid == 0) issue_row(blockIdx.x);
+    // CTAs that share an SM would otherwise march in lock step (identical rows): the ALU-bound decode phases and
+    // the shared-memory-bound match phases of both would coincide.  Delay the second wave by part of a row.
+    if (p.stagger_ns > 0 && blockIdx.x >= (unsigned)p.num_sms) {
+        for (int w = 0; w < p.stagger_ns; w += 500) __nanosleep(500);
+    }
 
     const int nchunks = W >> 2;
-    const int ngroups = (W + 31) >> 5;
+    const int ngroups = (W + 63) >> 6;
     const int lane = tid & 31;
     unsigned n_local = 0;
     int it = 0;
-    for (long long r = blockIdx.x; r < rows; r += gridDim.x, ++it) {
-        const int i = (int)(r / p.batch);
-        const int b = (int)(r - (long long)i * p.batch);
+    for (unsigned r = blockIdx.x; r < (unsigned)rows; r += gridDim.x, ++it) {
+        const int i = (int)(r / (unsigned)p.batch);
+        const int b = (int)(r - (unsigned)i * (unsigned)p.batch);
 
         // ---- clear the tables while the stage fills: keys = EMPTY, mink = INT_MAX, heads = -1 ----
         {
-            uint4 *k4 = reinterpret_cast<uint4 *>(keys);
-            uint4 *m4 = reinterpret_cast<uint4 *>(mink);
+            uint4 *e4p = reinterpret_cast<uint4 *>(ent);   // two entries per vector
             uint4 *h4 = reinterpret_cast<uint4 *>(head);
-            const uint4 e4 = make_uint4(KEY_EMPTY, KEY_EMPTY, KEY_EMPTY, KEY_EMPTY);
-            const uint4 x4 = make_uint4(0x7fffffffu, 0x7fffffffu, 0x7fffffffu, 0x7fffffffu);
-            for (int t = tid; t < (T >> 2); t += nthr) {
-                k4[t] = e4;
-                m4[t] = x4;
-                h4[t] = e4;
-                h4[t + (T >> 2)] = e4;
+            const uint4 e4 = make_uint4(KEY_EMPTY, 0x7fffffffu, KEY_EMPTY, 0x7fffffffu);
+            const uint4 m4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            for (int t = tid; t < (T >> 1); t += nthr) {
+                e4p[t] = e4;
+                h4[t] = m4;
             }
             if (tid == 0) *grp_ctr = 0;
         }
@@ -280,27 +283,33 @@ k_fused_mf(const FusedParams p)
             if (task < nchunks) {
                 const int c = task;
                 decode_chunk<MODE>(stage + (size_t)N * W, W, c, p, s_ptab, s_mtab, ph, ok);
+                // value -> min column, deduplicated.  The four pixels' first probes are issued back to back
+                // (independent atomics in flight); the thread that claims a new value also files it under the
+                // bucket(s) its +-0.1 match window touches.
+                uint32_t key[4], h[4], old[4];
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    if (ok[q]) {
-                        // value -> min column, deduplicated; the thread that claims a new value also files it
-                        // under the bucket(s) its +-0.1 match window touches
-                        const float v = __fadd_rn(ph[q], 0.0f);  // -0 -> +0
-                        const uint32_t key = __float_as_uint(v);
-                        uint32_t h = (key * 2654435761u) >> (32 - p.logT);
-                        while (true) {
-                            const uint32_t old = atomicCAS(&keys[h], KEY_EMPTY, key);
-                            if (old == KEY_EMPTY) {
-                                const int lo = window_bucket(__fsub_rn(v, 0.11f)), hi = window_bucket(__fadd_rn(v, 0.11f));
-                                nxt[h] = atomicExch(&head[lo & (HB - 1)], (int)h);
-                                if (hi != lo) nxt[h + T] = atomicExch(&head[hi & (HB - 1)], (int)h + T);
-                            }
-                            if (old == KEY_EMPTY || old == key) {
-                                atomicMin(&mink[h], 4 * c + q);
-                                break;
-                            }
-                            h = (h + 1) & (T - 1);
-                        }
+                    key[q] = __float_as_uint(__fadd_rn(ph[q], 0.0f));  // -0 -> +0
+                    h[q] = (key[q] * 2654435761u) >> (32 - p.logT);
+                    old[q] = ok[q] ? atomicCAS(&ent[h[q]].x, KEY_EMPTY, key[q]) : key[q];
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    while (old[q] != KEY_EMPTY && old[q] != key[q]) {  // collision: linear probing
+                        h[q] = (h[q] + 1) & (T - 1);
+                        old[q] = atomicCAS(&ent[h[q]].x, KEY_EMPTY, key[q]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (ok[q]) atomicMin(reinterpret_cast<int *>(&ent[h[q]].y), 4 * c + q);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (ok[q] && old[q] == KEY_EMPTY) {
+                        const float v = __uint_as_float(key[q]);
+                        const int lo = window_bucket(__fsub_rn(v, 0.11f)), hi = window_bucket(__fadd_rn(v, 0.11f));
+                        nxt[h[q]] = atomicExch(&head[lo & (HB - 1)], (int)h[q]);
+                        if (hi != lo) nxt[h[q] + T] = atomicExch(&head[hi & (HB - 1)], (int)h[q] + T);
                     }
                 }
             } else {
@@ -312,46 +321,65 @@ k_fused_mf(const FusedParams p)
         }
         __syncthreads();  // stage consumed, table + chains + left phases complete
 
-        if (tid == 0 && r + gridDim.x < rows) issue_row(r + gridDim.x);  // prefetch the next row
+        if (tid == 0 && r + gridDim.x < (unsigned)rows) issue_row(r + gridDim.x);  // prefetch the next row
 
-        // ---- query + emit: warps take 32-pixel groups dynamically (chain lengths vary along the row) ----
-        const size_t map_row = (size_t)i * W;
+        // ---- query + emit: warps take 64-pixel groups dynamically (chain lengths vary along the row);
+        //      each lane owns two pixels of the group ----
+        const float *lx_row = p.lx + (size_t)i * W, *ly_row = p.ly + (size_t)i * W, *rx_row = p.rx + (size_t)i * W;
         const size_t orow = ((size_t)b * p.H + i) * W;
+        float *xyz_row = p.xyz + orow * 3;
+        uint8_t *valid_row = p.valid + orow;
+        int32_t *k_row = p.match_k ? p.match_k + orow : nullptr;
         for (;;) {
             int g = 0;
             if (lane == 0) g = atomicAdd(grp_ctr, 1);
             g = __shfl_sync(0xffffffffu, g, 0);
             if (g >= ngroups) break;
-            const int j = (g << 5) + lane;
-            if (j < W) {
-                const float v = s_pl[j];
-                int best = INT_MAX;
-                if (v == v) {
-                    int t = head[window_bucket(v) & (HB - 1)];
-                    while (t >= 0) {
-                        const int e = t & (T - 1);
-                        const float pr = __uint_as_float(keys[e]);
-                        const int kk = mink[e];
-                        t = nxt[t];
-                        if (slr::phase_match(v, pr)) best = min(best, kk);
+            const int j0 = (g << 6) + lane, j1 = j0 + 32;
+            const float v0 = (j0 < W) ? s_pl[j0] : slr::qnan();
+            const float v1 = (j1 < W) ? s_pl[j1] : slr::qnan();
+            // the undistort-map values of both pixels are requested now so that their L2 latency overlaps the walk
+            const float ulx0 = (v0 == v0) ? __ldg(lx_row + j0) : 0.0f, uly0 = (v0 == v0) ? __ldg(ly_row + j0) : 0.0f;
+            const float ulx1 = (v1 == v1) ? __ldg(lx_row + j1) : 0.0f, uly1 = (v1 == v1) ? __ldg(ly_row + j1) : 0.0f;
+            int best0 = INT_MAX, best1 = INT_MAX;
+            if (v0 == v0) {
+                int t = head[window_bucket(v0) & (HB - 1)];
+                while (t >= 0) {
+                    const uint2 e = ent[t & (T - 1)];
+                    t = nxt[t];
+                    if (slr::phase_match(v0, __uint_as_float(e.x))) best0 = min(best0, (int)e.y);
+                }
+            }
+            if (v1 == v1) {
+                int t = head[window_bucket(v1) & (HB - 1)];
+                while (t >= 0) {
+                    const uint2 e = ent[t & (T - 1)];
+                    t = nxt[t];
+                    if (slr::phase_match(v1, __uint_as_float(e.x))) best1 = min(best1, (int)e.y);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int j = u ? j1 : j0;
+                const int best = u ? best1 : best0;
+                if (j < W) {
+                    float X = slr::qnan(), Y = slr::qnan(), Z = slr::qnan();
+                    const bool hit = (best != INT_MAX);
+                    if (hit) {
+                        const float ulx = u ? ulx1 : ulx0;
+                        const float uly = u ? uly1 : uly0;
+                        const float urx = __ldg(rx_row + best);
+                        const float disp = __fsub_rn(ulx, urx);
+                        slr::reproject_q(p.calib, (double)ulx, (double)uly, (double)disp, X, Y, Z);
+                        n_local++;
                     }
+                    float *dst = xyz_row + 3 * j;
+                    dst[0] = X;
+                    dst[1] = Y;
+                    dst[2] = Z;
+                    valid_row[j] = hit ? 1 : 0;
+                    if (k_row) k_row[j] = hit ? best : -1;
                 }
-                float X = slr::qnan(), Y = slr::qnan(), Z = slr::qnan();
-                const bool hit = (best != INT_MAX);
-                if (hit) {
-                    const float ulx = __ldg(p.lx + map_row + j);
-                    const float uly = __ldg(p.ly + map_row + j);
-                    const float urx = __ldg(p.rx + map_row + best);
-                    const float disp = __fsub_rn(ulx, urx);
-                    slr::reproject_q(p.calib, (double)ulx, (double)uly, (double)disp, X, Y, Z);
-                    n_local++;
-                }
-                float *dst = p.xyz + (orow + j) * 3;
-                dst[0] = X;
-                dst[1] = Y;
-                dst[2] = Z;
-                p.valid[orow + j] = hit ? 1 : 0;
-                if (p.match_k) p.match_k[orow + j] = hit ? best : -1;
             }
         }
         // the next iteration clears the tables: every warp must be done probing them
@@ -417,12 +445,16 @@ slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch,
     while (T < W || (double)W / T > 0.7) T <<= 1, logT++;
     const size_t smem = fused_smem_bytes(W, N, T);
     const int nchunks = W / 4;
-    const int per = (nchunks + FUSED_MAX_THREADS - 1) / FUSED_MAX_THREADS;  // decode rounds per camera
     const bool aligned = ((uintptr_t)d_stack | (uintptr_t)d_xyz | (uintptr_t)d_valid | (uintptr_t)d_match_k) % 16 == 0;
-    if (W % 16 != 0 || smem > 227 * 1024 || !aligned || batch > 65535)
+    if (W % 16 != 0 || smem > 227 * 1024 || !aligned || batch > 65535 || (long long)batch * e->H >= (1LL << 31))
         return slr_unfused_mf(e, d_stack, batch, F, S, black_thr, mode, d_xyz, d_valid, d_match_k, d_n_points);
 
-    int threads = ((nchunks + per - 1) / per + 31) / 32 * 32;
+    // decode tasks per row = 2*nchunks; a little more than one even share per round measured best (the extra
+    // warps help the shared-memory-latency-bound match phase): 1280-wide rows -> 384 threads, two CTAs per SM
+    const int tasks = 2 * nchunks;
+    const int rounds = (tasks + FUSED_MAX_THREADS - 1) / FUSED_MAX_THREADS;
+    int threads = ((tasks + rounds - 1) / rounds + 31) / 32 * 32 + 64;
+    if (threads > FUSED_MAX_THREADS) threads = FUSED_MAX_THREADS;
     if (threads < 64) threads = 64;
     if (const char *ev = getenv("SLR_FUSED_THREADS")) {  // tuning knob (bench experiments)
         const int t = atoi(ev);
@@ -439,6 +471,9 @@ slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch,
     p.T = T;
     p.logT = logT;
     p.black_thr = black_thr;
+    p.num_sms = e->num_sms;
+    p.stagger_ns = 0;
+    if (const char *ev = getenv("SLR_FUSED_STAGGER_NS")) p.stagger_ns = atoi(ev);
     p.lx = e->d_undist_lx;
     p.ly = e->d_undist_ly;
     p.rx = e->d_undist_rx;
@@ -459,6 +494,10 @@ slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch,
         kern = (mode == SLR_MODE_STRICT) ? k_fused_mf<SLR_MODE_STRICT, 320, 2> : k_fused_mf<SLR_MODE_CORRECTED, 320, 2>;
     else if (threads <= 384)
         kern = (mode == SLR_MODE_STRICT) ? k_fused_mf<SLR_MODE_STRICT, 384, 2> : k_fused_mf<SLR_MODE_CORRECTED, 384, 2>;
+    else if (threads <= 448 && 2 * smem + 4096 <= 227 * 1024)
+        kern = (mode == SLR_MODE_STRICT) ? k_fused_mf<SLR_MODE_STRICT, 448, 2> : k_fused_mf<SLR_MODE_CORRECTED, 448, 2>;
+    else if (2 * smem + 4096 <= 227 * 1024)
+        kern = (mode == SLR_MODE_STRICT) ? k_fused_mf<SLR_MODE_STRICT, 512, 2> : k_fused_mf<SLR_MODE_CORRECTED, 512, 2>;
     else
         kern = (mode == SLR_MODE_STRICT) ? k_fused_mf<SLR_MODE_STRICT, FUSED_MAX_THREADS, 1>
                                          : k_fused_mf<SLR_MODE_CORRECTED, FUSED_MAX_THREADS, 1>;

@@ -201,13 +201,24 @@ __device__ __forceinline__ void reproject_q(const slr_calib_dev &c, double x, do
                                             float &oy, float &oz)
 {
     double r[4];
+    if (c.q_std && !(d == 0.0 && c.Q[15] == 0.0)) {
+        // Q = [q00 0 0 q03; 0 q11 0 q13; 0 0 0 q23; 0 0 q32 q33] with q03, q13, q23 != 0 (what cv::stereoRectify
+        // produces).  The skipped products are +-0 and x + (+-0) == x unless x is itself a zero, in which case the
+        // following addition of a non-zero constant absorbs the sign: the four sums below are bit-identical to
+        // the dense evaluation.  (d == 0 with q33 == 0 gives W = +-0, whose sign the dense order decides.)
+        r[0] = __dadd_rn(__dmul_rn(c.Q[0], x), c.Q[3]);
+        r[1] = __dadd_rn(__dmul_rn(c.Q[5], y), c.Q[7]);
+        r[2] = c.Q[11];
+        r[3] = __dadd_rn(__dmul_rn(c.Q[14], d), c.Q[15]);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        double s = __dmul_rn(c.Q[4 * i + 0], x);
-        s = __dadd_rn(s, __dmul_rn(c.Q[4 * i + 1], y));
-        s = __dadd_rn(s, __dmul_rn(c.Q[4 * i + 2], d));
-        s = __dadd_rn(s, c.Q[4 * i + 3]);  // Q[i][3] * 1 is exact
-        r[i] = s;
+        for (int i = 0; i < 4; i++) {
+            double s = __dmul_rn(c.Q[4 * i + 0], x);
+            s = __dadd_rn(s, __dmul_rn(c.Q[4 * i + 1], y));
+            s = __dadd_rn(s, __dmul_rn(c.Q[4 * i + 2], d));
+            s = __dadd_rn(s, c.Q[4 * i + 3]);  // Q[i][3] * 1 is exact
+            r[i] = s;
+        }
     }
     float px = __double2float_rn(__ddiv_rn(r[0], r[3]));
     float py = __double2float_rn(__ddiv_rn(r[1], r[3]));

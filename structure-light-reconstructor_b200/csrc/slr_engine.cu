@@ -162,6 +162,16 @@ extern "C" slr_status slr_set_calib(slr_engine *e, const slr_camera cams[2], con
     e->calib.has_rigid = rigid3x4 ? 1 : 0;
     memset(e->calib.rigid, 0, sizeof(e->calib.rigid));
     if (rigid3x4) memcpy(e->calib.rigid, rigid3x4, sizeof(float) * 12);
+    {
+        const double *q = e->calib.Q;
+        const bool zeros = q[1] == 0 && q[2] == 0 && q[4] == 0 && q[6] == 0 && q[8] == 0 && q[9] == 0 && q[10] == 0 &&
+                           q[12] == 0 && q[13] == 0;
+        // the sign of a zero coefficient matters for the skipped +-0 terms only through the cases excluded in
+        // reproject_q; non-zero, finite constants are required where they absorb a zero sum
+        const bool consts = q[3] != 0 && q[7] != 0 && q[11] != 0 && isfinite(q[0]) && isfinite(q[3]) && isfinite(q[5]) &&
+                            isfinite(q[7]) && isfinite(q[11]) && isfinite(q[14]) && isfinite(q[15]);
+        e->calib.q_std = (zeros && consts) ? 1 : 0;
+    }
     slr_status st = slr_launch_undistort_maps(e);
     if (st != SLR_OK) return st;
     e->calib_set = true;

@@ -18,6 +18,7 @@ struct slr_calib_dev {
     double Q[16];
     float rigid[12];
     int has_rigid;
+    int q_std;  // Q has the cv::stereoRectify sparsity pattern (see reproject_q)
 };
 
 struct slr_engine {

@@ -139,6 +139,26 @@ def test_k3a_phase_match_vs_oracle(cuda_engine_factory, oracle, W, H, intd, nois
     assert total > 0
 
 
+def test_k3a_dense_q_and_zero_disparity(cuda_engine_factory, oracle):
+    """A dense (non-stereoRectify-shaped) Q takes the generic emitter; a zero disparity with Q[3][3] == 0
+    divides by zero exactly as the reference's double arithmetic does (inf / nan patterns must agree)."""
+    W, H = 64, 4
+    eng = cuda_engine_factory(W, H)
+    cams, Q = slr_b200.synthetic_rig(W, H, distort=False)
+    cams = [slr_b200.Camera(fc=(900, 900), cc=(32, 2)), slr_b200.Camera(fc=(900, 900), cc=(32, 2))]
+    rng = np.random.default_rng(5)
+    ph = np.zeros((1, 2, H, W), np.float32)
+    ph[0, :, :] = (np.arange(W, dtype=np.float32) * 0.7)[None, None, :]      # zero disparity everywhere
+    ph[0, 0, 2:, 5:] = ph[0, 1, 2:, :-5]                                     # rows 2,3: disparity 5
+    mk = np.ones((1, 2, H, W), np.uint8)
+    for Qm in (Q, Q + rng.normal(0, 0.01, (4, 4)), np.where(Q == 0, -0.0, Q)):
+        eng.set_calib(cams, Qm)
+        xyz, valid, k, n = eng.match_triangulate_phase(_t(ph), _t(mk))
+        xyz_o, valid_o, k_o, n_o = oracle.mf_triangulate(ph[0, 0], mk[0, 0], ph[0, 1], mk[0, 1], cams, Qm)
+        assert (k[0].cpu().numpy() == k_o).all() and int(n.item()) == n_o
+        assert (bits(xyz[0].cpu().numpy()) == bits(xyz_o)).all()
+
+
 def test_k3a_edge_cases(cuda_engine_factory, oracle):
     W, H = 64, 6
     eng = cuda_engine_factory(W, H)
