@@ -383,15 +383,21 @@ void orc_undistort_point(float px, float py, const orc_camera *cam, float *ox, f
     *oy = (float)((double)(float)(y * fy) + cy);
 }
 
-/* Duke/reconstruct.cpp:310-322:  p <- R^T p + (-R^T t), CV_32F */
+/* Duke/reconstruct.cpp:310-322:  tmp = -R^T * t ; tmpPoint = R^T * p ; p = tmp + tmpPoint  (CV_32F Mats).
+ * The two 3x3 * 3x1 products are cv::Mat arithmetic (third party): each element is accumulated in double,
+ * k ascending, and narrowed to float (OpenCV's CV_32F gemm uses a double accumulator); the unary minus is
+ * applied to the transposed matrix first, as the expression parses; the final sum is a float addition. */
 void orc_cam2world(const orc_camera *cam, float p[3])
 {
     const float *R = cam->R, *t = cam->t;
     float o[3];
     for (int i = 0; i < 3; i++) {
-        float rt = R[0 * 3 + i] * t[0] + R[1 * 3 + i] * t[1] + R[2 * 3 + i] * t[2];
-        float rp = R[0 * 3 + i] * p[0] + R[1 * 3 + i] * p[1] + R[2 * 3 + i] * p[2];
-        o[i] = -rt + rp;
+        double st = 0.0, sp = 0.0;
+        for (int k = 0; k < 3; k++) {
+            st += (double)(-R[k * 3 + i]) * (double)t[k];
+            sp += (double)R[k * 3 + i] * (double)p[k];
+        }
+        o[i] = (float)st + (float)sp;
     }
     p[0] = o[0];
     p[1] = o[1];
@@ -745,6 +751,31 @@ void orc_pointcloud_from_dense(const float *xyz, const uint8_t *valid, int W, in
                 count[q] = (uint8_t)(count[q] + 1);
             }
         }
+}
+
+/* PointCloudImage::addPoint applied to a sequence of (i_w, j_h, point) calls: pointcloudimage.cpp:86-97 with
+ * setPoint :28-37.  The u8 count wraps at 256, after which the next add RESETS the sum (num == 0 -> setPoint). */
+void orc_pointcloud_add(int w, int h, const int32_t *iw, const int32_t *jh, const float *pts, int n,
+                        float *points, uint8_t *count)
+{
+    memset(points, 0, (size_t)w * h * 3 * sizeof(float));
+    memset(count, 0, (size_t)w * h);
+    for (int k = 0; k < n; k++) {
+        if (iw[k] >= w || jh[k] >= h)               /* :88 */
+            continue;
+        size_t q = (size_t)jh[k] * w + iw[k];
+        if (count[q] == 0) {                        /* :91-92 */
+            points[q * 3 + 0] = pts[3 * k + 0];
+            points[q * 3 + 1] = pts[3 * k + 1];
+            points[q * 3 + 2] = pts[3 * k + 2];
+            count[q] = 1;
+        } else {                                    /* :93-95  point + p */
+            points[q * 3 + 0] = pts[3 * k + 0] + points[q * 3 + 0];
+            points[q * 3 + 1] = pts[3 * k + 1] + points[q * 3 + 1];
+            points[q * 3 + 2] = pts[3 * k + 2] + points[q * 3 + 2];
+            count[q] = (uint8_t)(count[q] + 1);
+        }
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -123,6 +123,10 @@ int64_t orc_gray_triangulate(const int32_t *colL, const int32_t *rowL, const uin
 void orc_pointcloud_from_dense(const float *xyz, const uint8_t *valid, int W, int H,
                                int scan_w, int scan_h, float *points, uint8_t *count);
 
+/* Duke/pointcloudimage.cpp:28-37, 86-97 for an arbitrary addPoint(i_w, j_h, p) sequence (u8 count wraps). */
+void orc_pointcloud_add(int w, int h, const int32_t *iw, const int32_t *jh, const float *pts, int n,
+                        float *points, uint8_t *count);
+
 /* ---- whole-pipeline conveniences used by bench.py's CPU legs ------------------------------ */
 /* MF pipeline on one scan: stacks = [2][14][H][W].  Returns points; *n_pixels unused. */
 int64_t orc_run_mf(const uint8_t *stacks, int W, int H, int F, int S, int black_thr, int mode,
