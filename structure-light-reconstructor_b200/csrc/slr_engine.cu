@@ -52,6 +52,7 @@ static void free_engine(slr_engine *e)
         if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
     }
     cudaFree(e->d_counter);
+    cudaFree(e->d_bucket_scratch);
     if (e->h_counter) cudaFreeHost(e->h_counter);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_in) cudaStreamDestroy(e->copy_in);

@@ -55,6 +55,9 @@ struct slr_engine {
     unsigned long long *d_counter = nullptr;  // device point counter
     unsigned long long *h_counter = nullptr;  // pinned
 
+    void *d_bucket_scratch = nullptr;  // K3c counting-sort scratch (one scan)
+    size_t bucket_scratch_bytes = 0;
+
     unsigned long long launches = 0;
 };
 

@@ -343,3 +343,60 @@ def test_fused_equals_unfused_kernels(cuda_engine_factory, mode, F, S, W, H):
     assert torch.equal(k, k2) and torch.equal(valid, valid2)
     assert (bits(xyz.cpu().numpy()) == bits(xyz2.cpu().numpy())).all()
     assert int(n.item()) == int(n2.item()) == int(valid.sum().item())
+
+
+# ---------------------------------------------------------------------------------------------
+# Gray-only (un-rectified, projector-cell buckets, ray-ray midpoints)
+# ---------------------------------------------------------------------------------------------
+def _cases():
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import cases
+    return cases
+
+
+@pytest.mark.parametrize("W,H,rigid,noise", [(48, 40, False, 2.0), (96, 64, True, 3.0)])
+def test_k3c_bucket_triangulate_vs_oracle(cuda_engine_factory, oracle, W, H, rigid, noise):
+    cases = _cases()
+    eng = cuda_engine_factory(W, H, 2)
+    cams = cases.gray_only_rig(W, H)
+    _, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q, cases.RIGID if rigid else None)
+    stack = np.stack([synth.synth_gray(W, H, seed=s, noise_dn=noise, rows=True, integer_disparity=True) for s in (41, 42)])
+    nc, nr = oracle.gray_num_bits(W), oracle.gray_num_bits(H)
+    col, row, mk = eng.gray_decode(_t(stack), nc, nr, black_thr=40, white_thr=3, scan_w=W, scan_h=H)
+    ssum, cnt, n = eng.bucket_triangulate(col, row, mk, W, H)
+    total = 0
+    for b in range(2):
+        d = [oracle.gray_decode(stack[b, cam], nc, nr, 40, 3, W, H) for cam in range(2)]
+        for cam in range(2):
+            assert (col[b, cam].cpu().numpy() == d[cam][0]).all() and (row[b, cam].cpu().numpy() == d[cam][1]).all()
+        s_o, c_o, n_o = oracle.gray_triangulate(d[0][0], d[0][1], d[0][2], d[1][0], d[1][1], d[1][2], W, H, cams,
+                                                cases.RIGID if rigid else None)
+        assert (cnt[b].cpu().numpy() == c_o).all()
+        g = ssum[b].cpu().numpy()
+        assert (bits(g[c_o > 0]) == bits(s_o[c_o > 0])).all()
+        total += n_o
+    assert int(n.item()) == total and total > 20
+
+
+def test_k3c_many_points_per_cell_wraps_like_the_reference(cuda_engine_factory, oracle):
+    """All camera pixels decode to a handful of projector cells: > 255 pair midpoints per cell, so the reference's
+    u8 count wraps and the sum restarts (pointcloudimage.cpp:91-95); ordering of the pair walk matters."""
+    cases = _cases()
+    W, H = 32, 24
+    eng = cuda_engine_factory(W, H)
+    cams = cases.gray_only_rig(W, H)
+    _, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    rng = np.random.default_rng(2)
+    col = rng.integers(0, 2, (1, 2, H, W)).astype(np.int32)          # 2 x 2 cells, ~190 pixels each per camera
+    row = rng.integers(0, 2, (1, 2, H, W)).astype(np.int32)
+    mk = (rng.random((1, 2, H, W)) < 0.9).astype(np.uint8)
+    col[mk == 0] = -1
+    row[mk == 0] = -1
+    ssum, cnt, n = eng.bucket_triangulate(_t(col), _t(row), _t(mk), W, H)
+    s_o, c_o, n_o = oracle.gray_triangulate(col[0, 0], row[0, 0], mk[0, 0], col[0, 1], row[0, 1], mk[0, 1], W, H, cams)
+    assert (cnt[0].cpu().numpy() == c_o).all() and int(n.item()) == n_o
+    assert (bits(ssum[0].cpu().numpy()[c_o > 0]) == bits(s_o[c_o > 0])).all()
