@@ -102,6 +102,17 @@ SLR_API slr_status slr_generate_gray_patterns(uint8_t *h_out, int W, int H, int 
 /* MultiFrequency::generateMutiFreq, Duke/multifrequency.cpp:14-33.  h_out = [14][projH][projW] */
 SLR_API slr_status slr_generate_mf_patterns(uint8_t *h_out, int projW, int projH);
 
+/* ---- K0: rectification on load ------------------------------------------------ */
+/* stereoRect::calParameters' maps: cv::initUndistortRectifyMap(..., CV_16SC2, map1, map2), Duke/stereorect.cpp:42-43.
+ * h_map1 = int16 [2][H][W][2] (integer source x, y), h_map2 = uint16 [2][H][W] (5+5 fractional bits). */
+SLR_API slr_status slr_set_rectify_maps(slr_engine *e, const int16_t *h_map1, const uint16_t *h_map2);
+/* stereoRect::doStereoRectify == cv::remap(INTER_LINEAR) on every image of both cameras' stacks,
+ * Duke/stereorect.cpp:26-34.  d_raw, d_out = [batch][2][n_images][H][W]; not in place. */
+SLR_API slr_status slr_rectify_stack(slr_engine *e, const uint8_t *d_raw, int batch, int n_images, uint8_t *d_out);
+/* raw != 0: the host-buffer entry points (slr_run_*_host) take RAW camera stacks and rectify them on the GPU
+ * first, as MFReconstruct::loadCamImgs / Reconstruct::loadCamImgs do on the CPU. */
+SLR_API slr_status slr_set_host_input_raw(slr_engine *e, int raw);
+
 /* ---- K1: multi-frequency phase decode -------------------------------------------------------- */
 /* MFReconstruct::computeShadows + decodePatterns + getPhase, Duke/mfreconstruct.cpp:190-269. */
 SLR_API slr_status slr_mf_decode(slr_engine *e, const uint8_t *d_stack, int batch, int F, int S,

@@ -779,6 +779,37 @@ void orc_pointcloud_add(int w, int h, const int32_t *iw, const int32_t *jh, cons
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* N1: stereoRect::doStereoRectify == cv::remap(img, out, map1, map2, INTER_LINEAR)               */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Duke/stereorect.cpp:26-34 with the CV_16SC2 fixed-point maps of :42-43.  OpenCV 2.4 imgproc (third party,
+ * restated from the published algorithm): map1 = integer source coordinates, map2 = 5+5 fractional bits;
+ * weights = bilinear products scaled to 2^15 and stored as shorts (the (0,0) entry saturates to 32767 and the
+ * table normalisation gives the missing 1 to the diagonal tap); result = (sum + 2^14) >> 15;
+ * BORDER_CONSTANT, value 0. */
+void orc_remap_linear(const uint8_t *src, int W, int H, const int16_t *map1, const uint16_t *map2, uint8_t *dst)
+{
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const size_t o = (size_t)y * W + x;
+            const int sx = map1[2 * o], sy = map1[2 * o + 1];
+            const int a = map2[o] & 1023, fx = a & 31, fy = a >> 5;
+            int w[4] = {(32 - fx) * (32 - fy) * 32, fx * (32 - fy) * 32, (32 - fx) * fy * 32, fx * fy * 32};
+            if (a == 0) {
+                w[0] = 32767;
+                w[3] = 1;
+            }
+            int sum = 0;
+            for (int t = 0; t < 4; t++) {
+                const int xx = sx + (t & 1), yy = sy + (t >> 1);
+                const int v = (xx >= 0 && xx < W && yy >= 0 && yy < H) ? src[(size_t)yy * W + xx] : 0;
+                sum += v * w[t];
+            }
+            dst[o] = (uint8_t)((sum + (1 << 14)) >> 15);
+        }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* whole MF pipeline for one scan (Duke/mfreconstruct.cpp:160-187 minus image IO)               */
 /* ------------------------------------------------------------------------------------------ */
 

@@ -127,6 +127,9 @@ void orc_pointcloud_from_dense(const float *xyz, const uint8_t *valid, int W, in
 void orc_pointcloud_add(int w, int h, const int32_t *iw, const int32_t *jh, const float *pts, int n,
                         float *points, uint8_t *count);
 
+/* Duke/stereorect.cpp:26-34: cv::remap(INTER_LINEAR) with CV_16SC2 maps (map1 = [H][W][2] int16, map2 = [H][W] u16) */
+void orc_remap_linear(const uint8_t *src, int W, int H, const int16_t *map1, const uint16_t *map2, uint8_t *dst);
+
 /* ---- whole-pipeline conveniences used by bench.py's CPU legs ------------------------------ */
 /* MF pipeline on one scan: stacks = [2][14][H][W].  Returns points; *n_pixels unused. */
 int64_t orc_run_mf(const uint8_t *stacks, int W, int H, int F, int S, int black_thr, int mode,

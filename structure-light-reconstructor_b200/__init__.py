@@ -59,7 +59,7 @@ EXPORTS = [
     "slr_generate_mf_patterns", "slr_mf_decode", "slr_gray_decode", "slr_match_triangulate_phase",
     "slr_match_triangulate_code", "slr_bucket_triangulate", "slr_run_mf", "slr_run_ge", "slr_run_mf_host",
     "slr_run_ge_host", "slr_host_alloc", "slr_host_free", "slr_synth_mf", "slr_synth_gray",
-    "slr_kernel_launches",
+    "slr_kernel_launches", "slr_set_rectify_maps", "slr_rectify_stack", "slr_set_host_input_raw",
 ]
 
 
@@ -98,6 +98,9 @@ def capi():
     lib.slr_host_free.argtypes = [vp]
     lib.slr_synth_mf.argtypes = [vp, vp, i32, i32, u32, i32, C.c_float]
     lib.slr_synth_gray.argtypes = [vp, vp, i32, i32, u32, i32, C.c_float]
+    lib.slr_set_rectify_maps.argtypes = [vp, vp, vp]
+    lib.slr_rectify_stack.argtypes = [vp, vp, i32, i32, vp]
+    lib.slr_set_host_input_raw.argtypes = [vp, i32]
     lib.slr_kernel_launches.argtypes = [vp]
     lib.slr_kernel_launches.restype = C.c_ulonglong
     _lib = lib
@@ -199,6 +202,25 @@ class Engine:
                                       r.ctypes.data_as(C.POINTER(C.c_float)) if r is not None else None),
                "slr_set_calib")
         self.synchronize()
+
+    def set_rectify_maps(self, map1, map2):
+        """map1: int16 [2,H,W,2], map2: uint16 [2,H,W] (cv::initUndistortRectifyMap CV_16SC2 layout)"""
+        m1 = np.ascontiguousarray(map1, np.int16)
+        m2 = np.ascontiguousarray(map2, np.uint16)
+        assert m1.shape == (2, self.H, self.W, 2) and m2.shape == (2, self.H, self.W)
+        self._bind_stream()
+        _check(self.lib.slr_set_rectify_maps(self.h, C.c_void_p(m1.ctypes.data), C.c_void_p(m2.ctypes.data)),
+               "slr_set_rectify_maps")
+
+    def rectify_stack(self, raw):
+        out = self._torch.empty_like(raw)
+        B, _, N = raw.shape[:3]
+        self._bind_stream()
+        _check(self.lib.slr_rectify_stack(self.h, self._p(raw), B, N, self._p(out)), "slr_rectify_stack")
+        return out
+
+    def set_host_input_raw(self, raw: bool):
+        _check(self.lib.slr_set_host_input_raw(self.h, int(raw)), "slr_set_host_input_raw")
 
     # -- kernels ----------------------------------------------------------------------------
     def mf_decode(self, stack, F=3, S=4, black_thr=40, mode=MODE_STRICT):

@@ -53,6 +53,10 @@ static void free_engine(slr_engine *e)
     }
     cudaFree(e->d_counter);
     cudaFree(e->d_bucket_scratch);
+    cudaFree(e->d_map1);
+    cudaFree(e->d_map2);
+    cudaFree(e->d_stage_rect[0]);
+    cudaFree(e->d_stage_rect[1]);
     if (e->h_counter) cudaFreeHost(e->h_counter);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_in) cudaStreamDestroy(e->copy_in);
@@ -373,6 +377,46 @@ extern "C" slr_status slr_synth_gray(slr_engine *e, uint8_t *d_stack, int batch,
 }
 
 // ------------------------------------------------------------------------------------------------
+// K0: rectification on load
+// ------------------------------------------------------------------------------------------------
+extern "C" slr_status slr_set_rectify_maps(slr_engine *e, const int16_t *h_map1, const uint16_t *h_map2)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(h_map1 && h_map2, "slr_set_rectify_maps: NULL map");
+    const size_t P = (size_t)e->W * e->H;
+    if (!e->d_map1) SLR_CHECK_CUDA(cudaMalloc(&e->d_map1, 2 * P * 2 * sizeof(int16_t)));
+    if (!e->d_map2) SLR_CHECK_CUDA(cudaMalloc(&e->d_map2, 2 * P * sizeof(uint16_t)));
+    SLR_CHECK_CUDA(cudaMemcpyAsync(e->d_map1, h_map1, 2 * P * 2 * sizeof(int16_t), cudaMemcpyHostToDevice, e->stream));
+    SLR_CHECK_CUDA(cudaMemcpyAsync(e->d_map2, h_map2, 2 * P * sizeof(uint16_t), cudaMemcpyHostToDevice, e->stream));
+    SLR_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    e->maps_set = true;
+    return SLR_OK;
+}
+
+extern "C" slr_status slr_rectify_stack(slr_engine *e, const uint8_t *d_raw, int batch, int n_images, uint8_t *d_out)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(d_raw && d_out && d_raw != d_out && batch > 0 && n_images > 0 && batch <= 32767,
+                "slr_rectify_stack: bad argument (in-place is not supported)");
+    if (!e->maps_set) {
+        slr_set_error("slr_rectify_stack: call slr_set_rectify_maps first");
+        return SLR_ERR_STATE;
+    }
+    return slr_launch_rectify(e, d_raw, batch, n_images, d_out);
+}
+
+extern "C" slr_status slr_set_host_input_raw(slr_engine *e, int raw)
+{
+    SLR_ENTER(e);
+    if (raw && !e->maps_set) {
+        slr_set_error("slr_set_host_input_raw: call slr_set_rectify_maps first");
+        return SLR_ERR_STATE;
+    }
+    e->host_input_raw = raw != 0;
+    return SLR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-buffer pipelines
 // ------------------------------------------------------------------------------------------------
 extern "C" slr_status slr_host_alloc(void **out, size_t bytes)
@@ -403,6 +447,14 @@ static slr_status ensure_stage(slr_engine *e, size_t in_bytes_per_scan, bool wan
         if (want_color && !e->d_stage_color[i]) SLR_CHECK_CUDA(cudaMalloc(&e->d_stage_color[i], P));
     }
     if (e->stage_in_bytes < in_bytes_per_scan) e->stage_in_bytes = in_bytes_per_scan;
+    if (e->host_input_raw && e->stage_rect_bytes < in_bytes_per_scan) {
+        for (int i = 0; i < 2; i++) {
+            if (e->d_stage_rect[i]) SLR_CHECK_CUDA(cudaFree(e->d_stage_rect[i]));
+            e->d_stage_rect[i] = nullptr;
+            SLR_CHECK_CUDA(cudaMalloc(&e->d_stage_rect[i], in_bytes_per_scan));
+        }
+        e->stage_rect_bytes = in_bytes_per_scan;
+    }
     return SLR_OK;
 }
 
@@ -428,7 +480,13 @@ static slr_status host_pipeline(slr_engine *e, const uint8_t *h_stack, size_t in
         // outputs of buffer b are free once the D2H of scan s-2 is done
         SLR_CHECK_CUDA(cudaStreamWaitEvent(cs, e->ev_in[b], 0));
         SLR_CHECK_CUDA(cudaStreamWaitEvent(cs, e->ev_out[b], 0));
-        st = launch(e->d_stage_in[b], e->d_stage_xyz[b], e->d_stage_valid[b], e->d_stage_k[b], e->d_stage_color[b]);
+        uint8_t *d_in = e->d_stage_in[b];
+        if (e->host_input_raw) {  // K0: rectify the raw camera images on the GPU (stereoRect::doStereoRectify)
+            st = slr_launch_rectify(e, d_in, 1, (int)(in_bytes / (2 * P)), e->d_stage_rect[b]);
+            if (st != SLR_OK) return st;
+            d_in = e->d_stage_rect[b];
+        }
+        st = launch(d_in, e->d_stage_xyz[b], e->d_stage_valid[b], e->d_stage_k[b], e->d_stage_color[b]);
         if (st != SLR_OK) return st;
         SLR_CHECK_CUDA(cudaEventRecord(e->ev_k[b], cs));
         SLR_CHECK_CUDA(cudaStreamWaitEvent(e->copy_out, e->ev_k[b], 0));

@@ -55,6 +55,14 @@ struct slr_engine {
     unsigned long long *d_counter = nullptr;  // device point counter
     unsigned long long *h_counter = nullptr;  // pinned
 
+    // K0 rectification maps (cv::initUndistortRectifyMap, CV_16SC2): [2][H][W] short2 and [2][H][W] u16
+    int16_t *d_map1 = nullptr;
+    uint16_t *d_map2 = nullptr;
+    bool maps_set = false;
+    bool host_input_raw = false;     // host entry points rectify the uploaded stacks first
+    uint8_t *d_stage_rect[2] = {nullptr, nullptr};
+    size_t stage_rect_bytes = 0;
+
     void *d_bucket_scratch = nullptr;  // K3c counting-sort scratch (one scan)
     size_t bucket_scratch_bytes = 0;
 
@@ -110,6 +118,7 @@ slr_status slr_launch_fused_ge(slr_engine *e, const uint8_t *d_stack, int batch,
                                float *d_xyz, uint8_t *d_valid, int32_t *d_match_k, uint8_t *d_color,
                                unsigned long long *d_n_points);
 slr_status slr_launch_undistort_maps(slr_engine *e);
+slr_status slr_launch_rectify(slr_engine *e, const uint8_t *d_raw, int batch, int N, uint8_t *d_out);
 slr_status slr_build_strict_tables(slr_engine *e);
 slr_status slr_launch_synth_mf(slr_engine *e, uint8_t *d_stack, int batch, int proj_w, unsigned seed,
                                int integer_disparity, float noise_dn);

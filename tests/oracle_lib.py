@@ -203,6 +203,16 @@ class Oracle:
                                 mk.ctypes.data, nthreads)
         return xyz, valid, mk, int(n)
 
+    def remap_linear(self, src, map1, map2):
+        src = np.ascontiguousarray(src, np.uint8)
+        H, W = src.shape
+        m1 = np.ascontiguousarray(map1, np.int16)
+        m2 = np.ascontiguousarray(map2, np.uint16)
+        dst = np.empty((H, W), np.uint8)
+        self.lib.orc_remap_linear(C.c_void_p(src.ctypes.data), W, H, C.c_void_p(m1.ctypes.data), C.c_void_p(m2.ctypes.data),
+                                  C.c_void_p(dst.ctypes.data))
+        return dst
+
     def max_threads(self):
         return self.lib.orc_max_threads()
 

@@ -400,3 +400,57 @@ def test_k3c_many_points_per_cell_wraps_like_the_reference(cuda_engine_factory, 
     s_o, c_o, n_o = oracle.gray_triangulate(col[0, 0], row[0, 0], mk[0, 0], col[0, 1], row[0, 1], mk[0, 1], W, H, cams)
     assert (cnt[0].cpu().numpy() == c_o).all() and int(n.item()) == n_o
     assert (bits(ssum[0].cpu().numpy()[c_o > 0]) == bits(s_o[c_o > 0])).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# K0: rectification on load — stereoRect::doStereoRectify == cv::remap(INTER_LINEAR)
+# ---------------------------------------------------------------------------------------------
+def _warp_maps(W, H, seed):
+    cv2 = pytest.importorskip("cv2")
+    xs, ys = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32))
+    maps1, maps2 = [], []
+    for cam in range(2):
+        mx = xs * (1.01 - 0.02 * cam) - 5 + 3 * np.sin(ys / 17 + seed)
+        my = ys * 0.99 + 2 - 4 * cam + 2 * np.cos(xs / 23)
+        mx[:3], my[:3] = xs[:3], ys[:3]                  # exact integer coordinates: the (0,0) weight entry
+        m1, m2 = cv2.convertMaps(mx, my, cv2.CV_16SC2)
+        maps1.append(m1)
+        maps2.append(m2)
+    return np.stack(maps1), np.stack(maps2)
+
+
+def test_k0_rectify_vs_oracle_and_opencv(cuda_engine_factory, oracle):
+    cv2 = pytest.importorskip("cv2")
+    W, H, N = 320, 96, 5
+    eng = cuda_engine_factory(W, H, 2)
+    m1, m2 = _warp_maps(W, H, 0.3)
+    eng.set_rectify_maps(m1, m2)
+    rng = np.random.default_rng(8)
+    raw = rng.integers(0, 256, (2, 2, N, H, W)).astype(np.uint8)
+    out = eng.rectify_stack(_t(raw)).cpu().numpy()
+    for b in range(2):
+        for cam in range(2):
+            for n in range(N):
+                exp = oracle.remap_linear(raw[b, cam, n], m1[cam], m2[cam])
+                assert (out[b, cam, n] == exp).all()
+            assert (cv2.remap(raw[b, cam, 0], m1[cam], m2[cam], cv2.INTER_LINEAR) == out[b, cam, 0]).all()
+
+
+def test_host_pipeline_with_raw_input_equals_rectify_then_run(cuda_engine_factory):
+    W, H = 640, 48
+    eng = cuda_engine_factory(W, H, 2)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    m1, m2 = _warp_maps(W, H, 1.1)
+    eng.set_rectify_maps(m1, m2)
+    raw = np.stack([synth.synth_mf(W, H, seed=s, noise_dn=1.0) for s in (5, 6, 7)])
+    rect = eng.rectify_stack(_t(raw))
+    xyz, valid, k, n = eng.run_mf(rect)
+    h_xyz = np.empty((3, H, W, 3), np.float32)
+    h_valid = np.empty((3, H, W), np.uint8)
+    h_k = np.empty((3, H, W), np.int32)
+    eng.set_host_input_raw(True)
+    n_host = eng.run_mf_host(raw, h_xyz, h_valid, h_k)
+    eng.set_host_input_raw(False)
+    assert n_host == int(n.item()) and n_host > 0
+    assert (bits(h_xyz) == bits(xyz.cpu().numpy())).all() and (h_k == k.cpu().numpy()).all()
