@@ -177,6 +177,12 @@ SLR_API slr_status slr_run_ge_host(slr_engine *e, const uint8_t *h_stack, int ba
                                    int black_thr, int white_thr, int scan_w, int have_color,
                                    float *h_xyz, uint8_t *h_valid, int32_t *h_match_k, uint8_t *h_color,
                                    unsigned long long *h_n_points);
+/* Reconstruct::runReconstruction minus image IO (Gray-only: column + row codes on UN-rectified images, ray-ray
+ * triangulation), Duke/reconstruct.cpp:230-265.  h_stack = [batch][2][2+2*nbits_col+2*nbits_row][H][W];
+ * h_sum = float [batch][scan_w*scan_h][3], h_cnt = uint8 [batch][scan_w*scan_h], indexed ac(x,y) = x*scan_h + y. */
+SLR_API slr_status slr_run_gray_host(slr_engine *e, const uint8_t *h_stack, int batch, int nbits_col, int nbits_row,
+                                     int black_thr, int white_thr, int scan_w, int scan_h, float *h_sum,
+                                     uint8_t *h_cnt, unsigned long long *h_n_cells);
 SLR_API slr_status slr_host_alloc(void **out, size_t bytes); /* pinned */
 SLR_API slr_status slr_host_free(void *p);
 

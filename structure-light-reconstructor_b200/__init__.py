@@ -59,7 +59,7 @@ EXPORTS = [
     "slr_generate_mf_patterns", "slr_mf_decode", "slr_gray_decode", "slr_match_triangulate_phase",
     "slr_match_triangulate_code", "slr_bucket_triangulate", "slr_run_mf", "slr_run_ge", "slr_run_mf_host",
     "slr_run_ge_host", "slr_host_alloc", "slr_host_free", "slr_synth_mf", "slr_synth_gray",
-    "slr_kernel_launches", "slr_set_rectify_maps", "slr_rectify_stack", "slr_set_host_input_raw",
+    "slr_kernel_launches", "slr_set_rectify_maps", "slr_rectify_stack", "slr_set_host_input_raw", "slr_run_gray_host",
 ]
 
 
@@ -101,6 +101,7 @@ def capi():
     lib.slr_set_rectify_maps.argtypes = [vp, vp, vp]
     lib.slr_rectify_stack.argtypes = [vp, vp, i32, i32, vp]
     lib.slr_set_host_input_raw.argtypes = [vp, i32]
+    lib.slr_run_gray_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, C.POINTER(C.c_ulonglong)]
     lib.slr_kernel_launches.argtypes = [vp]
     lib.slr_kernel_launches.restype = C.c_ulonglong
     _lib = lib

@@ -552,6 +552,61 @@ extern "C" slr_status slr_run_ge_host(slr_engine *e, const uint8_t *h_stack, int
                          });
 }
 
+// Reconstruct::runReconstruction minus image IO (Gray-only, un-rectified): K2 with row codes + K3c, one scan at a
+// time, synchronous staging (this path is latency bound and not on the north-star bench).
+extern "C" slr_status slr_run_gray_host(slr_engine *e, const uint8_t *h_stack, int batch, int nbits_col, int nbits_row,
+                                        int black_thr, int white_thr, int scan_w, int scan_h, float *h_sum,
+                                        uint8_t *h_cnt, unsigned long long *h_n_cells)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(h_stack && h_sum && h_cnt && batch > 0, "slr_run_gray_host: bad argument");
+    SLR_REQUIRE(nbits_col >= 1 && nbits_col <= 16 && nbits_row >= 1 && nbits_row <= 16 && scan_w > 0 && scan_h > 0,
+                "slr_run_gray_host: bad bit counts / scan size");
+    if (!e->calib_set) {
+        slr_set_error("slr_run_gray_host: call slr_set_calib first");
+        return SLR_ERR_STATE;
+    }
+    const size_t P = (size_t)e->W * e->H, ncell = (size_t)scan_w * scan_h;
+    const size_t N = (size_t)(2 + 2 * nbits_col + 2 * nbits_row);
+    uint8_t *d_stack = nullptr, *d_mask = nullptr, *d_cnt = nullptr;
+    int32_t *d_col = nullptr, *d_row = nullptr;
+    float *d_sum = nullptr;
+    slr_status st = SLR_OK;
+    cudaError_t ce = cudaMalloc(&d_stack, 2 * N * P);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_mask, 2 * P);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_col, 2 * P * sizeof(int32_t));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_row, 2 * P * sizeof(int32_t));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_sum, ncell * 3 * sizeof(float));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_cnt, ncell);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream);
+    for (int b = 0; b < batch && ce == cudaSuccess && st == SLR_OK; b++) {
+        ce = cudaMemcpyAsync(d_stack, h_stack + (size_t)b * 2 * N * P, 2 * N * P, cudaMemcpyHostToDevice, e->stream);
+        if (ce != cudaSuccess) break;
+        st = slr_launch_gray_decode(e, d_stack, 2, nbits_col, nbits_row, black_thr, white_thr, scan_w, scan_h, d_col, d_row, d_mask);
+        if (st == SLR_OK) st = slr_launch_bucket_triangulate(e, d_col, d_row, d_mask, 1, scan_w, scan_h, d_sum, d_cnt, e->d_counter);
+        if (st != SLR_OK) break;
+        ce = cudaMemcpyAsync(h_sum + (size_t)b * ncell * 3, d_sum, ncell * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_cnt + (size_t)b * ncell, d_cnt, ncell, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    }
+    if (ce == cudaSuccess && st == SLR_OK) {
+        ce = cudaMemcpyAsync(e->h_counter, e->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        if (ce == cudaSuccess && h_n_cells) *h_n_cells = *e->h_counter;
+    }
+    cudaFree(d_stack);
+    cudaFree(d_mask);
+    cudaFree(d_col);
+    cudaFree(d_row);
+    cudaFree(d_sum);
+    cudaFree(d_cnt);
+    if (ce != cudaSuccess) {
+        slr_set_error("slr_run_gray_host: %s", cudaGetErrorString(ce));
+        return SLR_ERR_CUDA;
+    }
+    return st;
+}
+
 // ------------------------------------------------------------------------------------------------
 // un-fused pipelines (first implementation of the fused entry points; kept as the fallback for
 // shapes the fused kernels do not cover).  Chunked by max_batch through the engine's scratch.

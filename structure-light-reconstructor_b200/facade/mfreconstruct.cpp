@@ -1,0 +1,110 @@
+#include "mfreconstruct.h"
+
+#include <stdio.h>
+
+#include "reconstruct_common.h"
+
+MFReconstruct::MFReconstruct(void *) : points3DProjView(nullptr), imgSuffix(".png"), numberOfImgs(14)
+{
+    cameras = new VirtualCamera[2];
+}
+
+MFReconstruct::~MFReconstruct()
+{
+    delete[] cameras;
+    delete sr;
+    delete points3DProjView;
+}
+
+void MFReconstruct::getParameters(int scansn, int scanw, int scanh, int camw, int camh, int blackt, int whitet,
+                                  const std::string &savePath)
+{
+    scanSN = scansn;
+    scan_w = scanw;
+    scan_h = scanh;
+    cameraWidth = camw;
+    cameraHeight = camh;
+    blackThreshold = blackt;
+    whiteThreshold = whitet;
+    savePath_ = savePath;
+    delete sr;
+    sr = new stereoRect(savePath, duke::Size(camw, camh));
+    sr->getParameters();
+    for (int i = 0; i < 2; i++) {
+        const char *side = i == 0 ? "left" : "right";
+        scanFolder[i] = savePath + "/scan/" + side + "/";
+        imgPrefix[i] = std::to_string(scanSN) + (i == 0 ? "/L" : "/R");
+        calibFolder[i] = savePath + "/calib/" + side + "/";
+    }
+    pathSet = true;
+    camerasLoaded = loadCameras();
+    if (!camerasLoaded) fprintf(stderr, "Get Param: Load Calibration files failed.\n");
+}
+
+bool MFReconstruct::loadCameras()
+{
+    bool loaded = false;
+    for (int i = 0; i < 2; i++) {
+        loaded = cameras[i].loadCameraMatrix(calibFolder[i] + "cam_matrix.txt");
+        if (!loaded) break;
+        cameras[i].loadDistortion(calibFolder[i] + "cam_distortion.txt");
+        cameras[i].loadRotationMatrix(calibFolder[i] + "cam_rotation_matrix.txt");
+        cameras[i].loadTranslationVector(calibFolder[i] + "cam_trans_vectror.txt");
+        cameras[i].loadFundamentalMatrix(savePath_ + "/calib/fundamental_stereo.txt");
+        cameras[i].height = cameraHeight;
+        cameras[i].width = cameraWidth;
+    }
+    return loaded;
+}
+
+bool MFReconstruct::runReconstruction()
+{
+    if (!pathSet || !camerasLoaded || !sr || !sr->loaded()) {
+        fprintf(stderr, "MFReconstruct: calibration is not loaded\n");
+        return false;
+    }
+    const int W = cameraWidth, H = cameraHeight;
+    const size_t P = (size_t)W * H;
+    sr->calParameters();
+
+    slr_engine *eng = nullptr;
+    if (slr_create(&eng, device, W, H, 1) != SLR_OK) {
+        fprintf(stderr, "MFReconstruct: %s\n", slr_last_error());
+        return false;
+    }
+    bool ok = false;
+    void *h_stack = nullptr, *h_xyz = nullptr, *h_valid = nullptr;
+    do {
+        slr_camera cams[2] = {duke::to_slr_camera(cameras[0]), duke::to_slr_camera(cameras[1])};
+        float rigid[12];
+        const float *rg = nullptr;
+        if (scanSN > 0) {  // mfreconstruct.cpp:276-282
+            if (duke::load_rigid(savePath_ + "/scan/transfer_mat" + std::to_string(scanSN) + ".txt", rigid)) rg = rigid;
+        }
+        if (slr_set_calib(eng, cams, sr->Q.v.data(), rg) != SLR_OK) break;
+        if (slr_set_rectify_maps(eng, sr->map1().data(), sr->map2().data()) != SLR_OK) break;
+        if (slr_set_host_input_raw(eng, 1) != SLR_OK) break;
+        if (slr_host_alloc(&h_stack, 2 * (size_t)numberOfImgs * P) != SLR_OK) break;
+        if (slr_host_alloc(&h_xyz, P * 3 * sizeof(float)) != SLR_OK) break;
+        if (slr_host_alloc(&h_valid, P) != SLR_OK) break;
+        bool loaded = true;
+        for (int i = 0; i < 2 && loaded; i++)
+            loaded = duke::load_stack(scanFolder[i], imgPrefix[i], imgSuffix, numberOfImgs, W, H,
+                                      (uint8_t *)h_stack + (size_t)i * numberOfImgs * P);
+        if (!loaded) break;
+        n_points_ = 0;
+        if (slr_run_mf_host(eng, (const uint8_t *)h_stack, 1, 3, 4, blackThreshold, mode, (float *)h_xyz, (uint8_t *)h_valid,
+                            nullptr, &n_points_) != SLR_OK)
+            break;
+        delete points3DProjView;
+        points3DProjView = new PointCloudImage(scan_w, scan_h, false);
+        points3DProjView->addDense((const float *)h_xyz, (const uint8_t *)h_valid, nullptr, W, H);
+        ok = true;
+    } while (false);
+    if (!ok && slr_last_error()[0]) fprintf(stderr, "MFReconstruct: %s\n", slr_last_error());
+    slr_host_free(h_stack);
+    slr_host_free(h_xyz);
+    slr_host_free(h_valid);
+    slr_destroy(eng);
+    return ok;
+}
