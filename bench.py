@@ -185,6 +185,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", action="store_true",
+                    help="N > 1: also time the steps followed by an NCCL all-gather of every rank's cloud (reported "
+                         "under 'with_allgather'; never part of 'value')")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -252,6 +255,21 @@ def main():
     step_ms = [a.elapsed_time(b) for a, b in evs]
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- optional: the same steps followed by an all-gather of the cloud over NVLink (north star's assembly) ----
+    gather = None
+    if args.gather and world > 1:
+        from slr_b200 import parallel
+        n_total = B * world
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for k in range(args.steps):
+            eng.run_mf(stack, F, S, BLACK_THR, slr_b200.MODE_STRICT, out=out)
+            gx, gv = parallel.gather_clouds(out[0], out[1], n_total)
+        g1.record()
+        barrier()
+        gather = {"ms": g0.elapsed_time(g1), "bytes_received_per_rank_per_step": (world - 1) * B * H * W * 13}
+
     # ---- end to end through the host-buffer C-ABI call ----
     e2e = None
     if not args.no_e2e:
@@ -275,11 +293,14 @@ def main():
 
     # ---- reduce over ranks: time = max, points = sum ----
     if world > 1:
-        t = torch.tensor([total_ms, e2e["dt"] if e2e else 0.0], device="cuda", dtype=torch.float64)
+        t = torch.tensor([total_ms, e2e["dt"] if e2e else 0.0, gather["ms"] if gather else 0.0], device="cuda",
+                         dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         p = torch.tensor([points_per_step, e2e["pts"] if e2e else 0], device="cuda", dtype=torch.int64)
         dist.all_reduce(p, op=dist.ReduceOp.SUM)
         total_ms, e_dt_max = float(t[0]), float(t[1])
+        if gather:
+            gather["ms"] = float(t[2])
         points_all, e_pts_all = int(p[0]), int(p[1])
     else:
         e_dt_max = e2e["dt"] if e2e else 0.0
@@ -314,6 +335,11 @@ def main():
                              "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                              "scans_per_step": e2e["batch"], "steps": e2e["steps"],
                              "ms_per_step": e_dt_max / e2e["steps"] * 1e3}
+        if gather:
+            g_ms = gather["ms"] / args.steps
+            result["with_allgather"] = {"value": points_all / (g_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": g_ms,
+                                        "bytes_received_per_rank_per_step": gather["bytes_received_per_rank_per_step"],
+                                        "note": "steps followed by all_gather_into_tensor of xyz+valid (NCCL); not in 'value'"}
         if world == 1 and not args.no_cpu:
             h = h_in[:2]
             v1, sc1, dt1, nt1 = cpu_port_rate(h, cams, Q, 0, 8.0, 40)
