@@ -124,7 +124,8 @@ def cpu_port_rate(stack_np, cams, Q, nthreads, min_seconds, max_scans):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     orc = oracle_lib.load()
-    nthreads = nthreads or orc.max_threads()
+    if not nthreads:
+        nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     pts, scans, t0 = 0, 0, time.perf_counter()
     while True:
         _, _, _, n = orc.run_mf(stack_np[scans % stack_np.shape[0]], cams, Q, F=F, S=S, black_thr=BLACK_THR, mode=0,
@@ -150,7 +151,8 @@ def run_reference(args, rank, world):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     orc = oracle_lib.load()
-    nthreads = orc.max_threads()
+    # all host threads this process may use; torchrun exports OMP_NUM_THREADS=1, so ask the scheduler, not OpenMP
+    nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     per_step = 2     # scans per step (bounded sample of the B-scan workload)
     for _ in range(args.warmup):
         orc.run_mf(stack[0], cams, Q, nthreads=nthreads)
@@ -342,8 +344,8 @@ def main():
                                         "note": "steps followed by all_gather_into_tensor of xyz+valid (NCCL); not in 'value'"}
         if world == 1 and not args.no_cpu:
             h = h_in[:2]
-            v1, sc1, dt1, nt1 = cpu_port_rate(h, cams, Q, 0, 8.0, 40)
-            vs, scs, dts, _ = cpu_port_rate(h, cams, Q, 1, 4.0, 8)
+            v1, sc1, dt1, nt1 = cpu_port_rate(h, cams, Q, 0, 10.0, 2000)
+            vs, scs, dts, _ = cpu_port_rate(h, cams, Q, 1, 5.0, 50)
             result["cpu_baseline"] = {"value": v1, "unit": UNIT, "cores": nt1, "kind": "port",
                                       "sample": f"{sc1} scans of the same workload in {dt1:.1f} s, rows over {nt1} threads",
                                       "single_thread_value": vs,
