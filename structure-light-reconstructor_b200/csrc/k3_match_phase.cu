@@ -12,6 +12,7 @@
 //   4. matched pixels are reprojected with Q in fp64 using the precomputed undistortPoints maps,
 //      the row of XYZ / valid / match_k is staged in smem and leaves by TMA bulk stores.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "slr_device.cuh"
 
@@ -156,10 +157,21 @@ static int next_pow2(int v)
     return p;
 }
 
+slr_status slr_launch_match_phase_fast(slr_engine *e, const float *d_phase, const uint8_t *d_mask, int batch,
+                                       float *d_xyz, uint8_t *d_valid, int32_t *d_match_k,
+                                       unsigned long long *d_n_points, bool *handled);
+
 slr_status slr_launch_match_phase(slr_engine *e, const float *d_phase, const uint8_t *d_mask, int batch,
                                   float *d_xyz, uint8_t *d_valid, int32_t *d_match_k,
                                   unsigned long long *d_n_points)
 {
+    // preferred: the fused kernel's match stage fed with phase rows (value-deduplicating hash, single-chain
+    // probes); this plain kernel remains for shapes that one does not take and as the simple reference form
+    if (!getenv("SLR_K3A_PLAIN")) {
+        bool handled = false;
+        slr_status st = slr_launch_match_phase_fast(e, d_phase, d_mask, batch, d_xyz, d_valid, d_match_k, d_n_points, &handled);
+        if (st != SLR_OK || handled) return st;
+    }
     SLR_REQUIRE(e->W % 16 == 0, "image width must be a multiple of 16 (TMA bulk rows); got %d", e->W);
     SLR_REQUIRE(((uintptr_t)d_phase | (uintptr_t)d_mask | (uintptr_t)d_xyz | (uintptr_t)d_valid |
                  (uintptr_t)d_match_k) % 16 == 0, "device buffers must be 16-byte aligned");

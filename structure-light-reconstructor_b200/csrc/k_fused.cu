@@ -40,9 +40,12 @@ namespace {
 
 constexpr int FUSED_MAX_THREADS = 512;
 constexpr uint32_t KEY_EMPTY = 0xFFFFFFFFu;
+constexpr int MODE_PHASE_INPUT = 2;  // rows of already decoded phase + mask (slr_match_triangulate_phase) instead of images
 
 struct FusedParams {
     const uint8_t *stack;  // [batch][2][N][H][W]
+    const float *phase;    // MODE_PHASE_INPUT: [batch][2][H][W]
+    const uint8_t *mask;   // MODE_PHASE_INPUT: [batch][2][H][W]
     int W, H, batch, F, S, N;
     int T, logT;           // dedupe table / bucket heads size (power of two)
     int black_thr;
@@ -214,7 +217,7 @@ k_fused_mf(const FusedParams p)
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
     int *grp_ctr = reinterpret_cast<int *>(smem + 8);               // dynamic query-group counter
     unsigned char *stage = smem + 16;                               // [2][N][W] u8
-    const size_t stage_bytes = (size_t)2 * N * W;
+    const size_t stage_bytes = (MODE == MODE_PHASE_INPUT) ? (size_t)10 * W : (size_t)2 * N * W;
     // [T] entries {x = distinct right phase (float bits), y = smallest right column carrying it}
     uint2 *ent = reinterpret_cast<uint2 *>(stage + stage_bytes);
     int *head = reinterpret_cast<int *>(ent + T);                   // [HB = 2T] bucket heads
@@ -241,6 +244,14 @@ k_fused_mf(const FusedParams p)
         const int i = (int)(r / (unsigned)p.batch);
         const int b = (int)(r - (unsigned)i * (unsigned)p.batch);
         slr::mbar_expect_tx(bar, (uint32_t)stage_bytes);
+        if (MODE == MODE_PHASE_INPUT) {  // stage = pL f32[W] | pR f32[W] | mL u8[W] | mR u8[W]
+            const size_t offL = ((size_t)(b * 2 + 0) * p.H + i) * W, offR = ((size_t)(b * 2 + 1) * p.H + i) * W;
+            tma_load_1d_hint(stage, p.phase + offL, 4u * W, bar, policy);
+            tma_load_1d_hint(stage + 4 * W, p.phase + offR, 4u * W, bar, policy);
+            tma_load_1d_hint(stage + 8 * W, p.mask + offL, (uint32_t)W, bar, policy);
+            tma_load_1d_hint(stage + 9 * W, p.mask + offR, (uint32_t)W, bar, policy);
+            return;
+        }
         const uint8_t *src = p.stack + ((size_t)b * 2 * N * p.H + i) * W;
         for (int v = 0; v < 2 * N; v++)   // plane v of this scan (cam-major, then image index)
             tma_load_1d_hint(stage + (size_t)v * W, src + (size_t)v * p.H * W, (uint32_t)W, bar, policy);
@@ -282,7 +293,15 @@ k_fused_mf(const FusedParams p)
             bool ok[4];
             if (task < nchunks) {
                 const int c = task;
-                decode_chunk<MODE>(stage + (size_t)N * W, W, c, p, s_ptab, s_mtab, ph, ok);
+                if (MODE == MODE_PHASE_INPUT) {
+                    const float4 v = reinterpret_cast<const float4 *>(stage + 4 * W)[c];
+                    const uint32_t m = reinterpret_cast<const uint32_t *>(stage + 9 * W)[c];
+                    ph[0] = v.x, ph[1] = v.y, ph[2] = v.z, ph[3] = v.w;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) ok[q] = byte_of(m, q) != 0 && ph[q] == ph[q];  // NaN never matches
+                } else {
+                    decode_chunk<MODE>(stage + (size_t)N * W, W, c, p, s_ptab, s_mtab, ph, ok);
+                }
                 // value -> min column, deduplicated.  The four pixels' first probes are issued back to back
                 // (independent atomics in flight); the thread that claims a new value also files it under the
                 // bucket(s) its +-0.1 match window touches.
@@ -314,7 +333,15 @@ k_fused_mf(const FusedParams p)
                 }
             } else {
                 const int c = task - nchunks;
-                decode_chunk<MODE>(stage, W, c, p, s_ptab, s_mtab, ph, ok);
+                if (MODE == MODE_PHASE_INPUT) {
+                    const float4 v = reinterpret_cast<const float4 *>(stage)[c];
+                    const uint32_t m = reinterpret_cast<const uint32_t *>(stage + 8 * W)[c];
+                    ph[0] = v.x, ph[1] = v.y, ph[2] = v.z, ph[3] = v.w;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) ok[q] = byte_of(m, q) != 0;
+                } else {
+                    decode_chunk<MODE>(stage, W, c, p, s_ptab, s_mtab, ph, ok);
+                }
                 reinterpret_cast<float4 *>(s_pl)[c] = make_float4(ok[0] ? ph[0] : slr::qnan(), ok[1] ? ph[1] : slr::qnan(),
                                                                   ok[2] ? ph[2] : slr::qnan(), ok[3] ? ph[3] : slr::qnan());
             }
@@ -425,29 +452,28 @@ slr_status slr_build_strict_tables(slr_engine *e)
     return SLR_OK;
 }
 
-static size_t fused_smem_bytes(int W, int N, int T)
+static size_t fused_smem_bytes(size_t stage_bytes, int W, int T)
 {
-    return 16 + (size_t)2 * N * W + (size_t)24 * T + (size_t)4 * W + 2048 * 8 + 256 * 4;
+    return 16 + stage_bytes + (size_t)24 * T + (size_t)4 * W + 2048 * 8 + 256 * 4;
 }
 
-slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch, int F, int S, int black_thr,
-                               int mode, float *d_xyz, uint8_t *d_valid, int32_t *d_match_k,
-                               unsigned long long *d_n_points)
+// shared launcher: mode = SLR_MODE_STRICT | SLR_MODE_CORRECTED (image stacks) or MODE_PHASE_INPUT (phase + mask rows)
+static slr_status launch_fused(slr_engine *e, int mode, const uint8_t *d_stack, const float *d_phase,
+                               const uint8_t *d_mask, int batch, int F, int S, int black_thr, float *d_xyz,
+                               uint8_t *d_valid, int32_t *d_match_k, unsigned long long *d_n_points, bool *handled)
 {
-    if (mode == SLR_MODE_STRICT)
-        SLR_REQUIRE(F == 3 && S == 4, "strict mode reproduces the reference's hard-coded 3 frequencies x 4 steps "
-                                      "(Duke/mfreconstruct.cpp:237); got F=%d S=%d", F, S);
-    else
-        SLR_REQUIRE(mode == SLR_MODE_CORRECTED && F >= 1 && F <= 8 && S >= 3 && S <= 16,
-                    "corrected mode supports 1<=F<=8, 3<=S<=16; got mode %d F=%d S=%d", mode, F, S);
+    *handled = false;
     const int W = e->W, N = 2 + F * S;
     int T = 64, logT = 6;
     while (T < W || (double)W / T > 0.7) T <<= 1, logT++;
-    const size_t smem = fused_smem_bytes(W, N, T);
+    const size_t stage_bytes = (mode == MODE_PHASE_INPUT) ? (size_t)10 * W : (size_t)2 * N * W;
+    const size_t smem = fused_smem_bytes(stage_bytes, W, T);
     const int nchunks = W / 4;
-    const bool aligned = ((uintptr_t)d_stack | (uintptr_t)d_xyz | (uintptr_t)d_valid | (uintptr_t)d_match_k) % 16 == 0;
+    const bool aligned = ((uintptr_t)d_stack | (uintptr_t)d_phase | (uintptr_t)d_mask | (uintptr_t)d_xyz |
+                          (uintptr_t)d_valid | (uintptr_t)d_match_k) % 16 == 0;
     if (W % 16 != 0 || smem > 227 * 1024 || !aligned || batch > 65535 || (long long)batch * e->H >= (1LL << 31))
-        return slr_unfused_mf(e, d_stack, batch, F, S, black_thr, mode, d_xyz, d_valid, d_match_k, d_n_points);
+        return SLR_OK;  // not handled: the caller falls back to the un-fused kernels
+    *handled = true;
 
     // decode tasks per row = 2*nchunks; a little more than one even share per round measured best (the extra
     // warps help the shared-memory-latency-bound match phase): 1280-wide rows -> 384 threads, two CTAs per SM
@@ -462,6 +488,8 @@ slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch,
     }
     FusedParams p;
     p.stack = d_stack;
+    p.phase = d_phase;
+    p.mask = d_mask;
     p.W = W;
     p.H = e->H;
     p.batch = batch;
@@ -490,17 +518,23 @@ slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch,
     p.calib = e->calib;
 
     void (*kern)(const FusedParams);
-    if (threads <= 320)
-        kern = (mode == SLR_MODE_STRICT) ? k_fused_mf<SLR_MODE_STRICT, 320, 2> : k_fused_mf<SLR_MODE_CORRECTED, 320, 2>;
-    else if (threads <= 384)
-        kern = (mode == SLR_MODE_STRICT) ? k_fused_mf<SLR_MODE_STRICT, 384, 2> : k_fused_mf<SLR_MODE_CORRECTED, 384, 2>;
-    else if (threads <= 448 && 2 * smem + 4096 <= 227 * 1024)
-        kern = (mode == SLR_MODE_STRICT) ? k_fused_mf<SLR_MODE_STRICT, 448, 2> : k_fused_mf<SLR_MODE_CORRECTED, 448, 2>;
-    else if (2 * smem + 4096 <= 227 * 1024)
-        kern = (mode == SLR_MODE_STRICT) ? k_fused_mf<SLR_MODE_STRICT, 512, 2> : k_fused_mf<SLR_MODE_CORRECTED, 512, 2>;
-    else
-        kern = (mode == SLR_MODE_STRICT) ? k_fused_mf<SLR_MODE_STRICT, FUSED_MAX_THREADS, 1>
-                                         : k_fused_mf<SLR_MODE_CORRECTED, FUSED_MAX_THREADS, 1>;
+    const bool two = 2 * smem + 4096 <= 227 * 1024;
+#define SLR_PICK(MAXT, MINB)                                                                                      \
+    kern = (mode == SLR_MODE_STRICT)      ? k_fused_mf<SLR_MODE_STRICT, MAXT, MINB>                                 \
+           : (mode == SLR_MODE_CORRECTED) ? k_fused_mf<SLR_MODE_CORRECTED, MAXT, MINB>                              \
+                                          : k_fused_mf<MODE_PHASE_INPUT, MAXT, MINB>
+    if (threads <= 320) {
+        SLR_PICK(320, 2);
+    } else if (threads <= 384) {
+        SLR_PICK(384, 2);
+    } else if (threads <= 448 && two) {
+        SLR_PICK(448, 2);
+    } else if (two) {
+        SLR_PICK(512, 2);
+    } else {
+        SLR_PICK(FUSED_MAX_THREADS, 1);
+    }
+#undef SLR_PICK
     SLR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     SLR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
@@ -512,6 +546,33 @@ slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch,
     kern<<<(unsigned)grid, threads, smem, e->stream>>>(p);
     SLR_CHECK_LAUNCH(e);
     return SLR_OK;
+}
+
+slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch, int F, int S, int black_thr,
+                               int mode, float *d_xyz, uint8_t *d_valid, int32_t *d_match_k,
+                               unsigned long long *d_n_points)
+{
+    if (mode == SLR_MODE_STRICT)
+        SLR_REQUIRE(F == 3 && S == 4, "strict mode reproduces the reference's hard-coded 3 frequencies x 4 steps "
+                                      "(Duke/mfreconstruct.cpp:237); got F=%d S=%d", F, S);
+    else
+        SLR_REQUIRE(mode == SLR_MODE_CORRECTED && F >= 1 && F <= 8 && S >= 3 && S <= 16,
+                    "corrected mode supports 1<=F<=8, 3<=S<=16; got mode %d F=%d S=%d", mode, F, S);
+    bool handled = false;
+    slr_status st = launch_fused(e, mode, d_stack, nullptr, nullptr, batch, F, S, black_thr, d_xyz, d_valid, d_match_k,
+                                 d_n_points, &handled);
+    if (st != SLR_OK || handled) return st;
+    return slr_unfused_mf(e, d_stack, batch, F, S, black_thr, mode, d_xyz, d_valid, d_match_k, d_n_points);
+}
+
+// K3a through the same kernel: rows of decoded phase + mask in, XYZ out (slr_match_triangulate_phase).
+// Returns handled = false when the shape needs the plain k3a kernel (k3_match_phase.cu).
+slr_status slr_launch_match_phase_fast(slr_engine *e, const float *d_phase, const uint8_t *d_mask, int batch,
+                                       float *d_xyz, uint8_t *d_valid, int32_t *d_match_k,
+                                       unsigned long long *d_n_points, bool *handled)
+{
+    return launch_fused(e, MODE_PHASE_INPUT, nullptr, d_phase, d_mask, batch, 1, 3, 0, d_xyz, d_valid, d_match_k,
+                        d_n_points, handled);
 }
 
 slr_status slr_launch_fused_ge(slr_engine *e, const uint8_t *d_stack, int batch, int nbits_col, int black_thr,

@@ -454,3 +454,17 @@ def test_host_pipeline_with_raw_input_equals_rectify_then_run(cuda_engine_factor
     eng.set_host_input_raw(False)
     assert n_host == int(n.item()) and n_host > 0
     assert (bits(h_xyz) == bits(xyz.cpu().numpy())).all() and (h_k == k.cpu().numpy()).all()
+
+
+def test_wide_rows_take_the_plain_kernels_and_still_match_the_oracle(cuda_engine_factory, oracle):
+    """4096-wide rows (BASELINE config 5's width) exceed the fused kernel's shared-memory stage: slr_run_mf runs
+    K1 + the plain K3a kernel.  Same exactness bar."""
+    W, H = 4096, 3
+    eng = cuda_engine_factory(W, H)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    stack = synth.synth_mf(W, H, seed=77, noise_dn=1.0)[None]
+    xyz, valid, k, n = eng.run_mf(_t(stack))
+    xyz_o, valid_o, k_o, n_o = oracle.run_mf(stack[0], cams, Q, nthreads=oracle.max_threads())
+    assert (k[0].cpu().numpy() == k_o).all() and int(n.item()) == n_o and n_o > 1000
+    assert (bits(xyz[0].cpu().numpy()) == bits(xyz_o)).all()
