@@ -1,60 +1,76 @@
 // k1_mf_decode.cu — K1: shadow mask + multi-frequency phase decode + heterodyne unwrap.
 // Replaces MFReconstruct::computeShadows / decodePatterns / getPhase (Duke/mfreconstruct.cpp:190-269).
 //
-// HBM-bound streaming kernel: each thread owns 16 consecutive pixels of one camera view, issues all
+// Streaming kernel: each thread owns 16 consecutive pixels of one camera view, issues all
 // N = 2 + F*S 128-bit plane loads up front (ld.global.nc, L1 no-allocate), decodes in registers and
 // writes 4 x float4 phase + 1 x uint4 mask.  Algorithmic traffic: N + 4 + 1 bytes per pixel.
+#include <stdlib.h>
+
 #include "slr_device.cuh"
 
 namespace {
 
 constexpr int K1_THREADS = 256;
 
-__device__ __forceinline__ int byte_of(const uint4 &v, int i)
-{
-    const uint32_t w = (i < 4) ? v.x : (i < 8) ? v.y : (i < 12) ? v.z : v.w;
-    return (int)((w >> (8 * (i & 3))) & 0xffu);
-}
-
-// strict mode, F = 3, S = 4, 16 pixels per thread
-__global__ void __launch_bounds__(K1_THREADS)
+// strict mode, F = 3, S = 4, 16 pixels per thread, table-driven exact decode (slr_device.cuh: the integer quotient by
+// reciprocal multiplication, the wrapped phase from the 4x512 table of the reference's float values held as
+// doubles); persistent grid-stride CTAs load the 17 KB of tables into shared memory once
+template <int NW>  // 32-bit words (4 pixels each) per thread per plane: 4 = 128-bit loads, 2 = 64-bit loads
+__global__ void __launch_bounds__(K1_THREADS, NW == 4 ? 2 : 3)
 k1_mf_decode_strict(const uint8_t *__restrict__ stack, size_t P, long long chunks_per_view, long long total_chunks,
-                    int black_thr, const float *__restrict__ g_lut, float *__restrict__ phase,
-                    uint8_t *__restrict__ mask)
+                    int black_thr, const double *__restrict__ g_ptab, const uint32_t *__restrict__ g_mtab,
+                    float *__restrict__ phase, uint8_t *__restrict__ mask)
 {
-    __shared__ float lut[SLR_ATAN_LUT_SIZE + 1];
-    for (int i = threadIdx.x; i < SLR_ATAN_LUT_SIZE; i += K1_THREADS) lut[i] = g_lut[i];
+    __shared__ double s_ptab[2048];
+    __shared__ uint32_t s_mtab[256];
+    for (int i = threadIdx.x; i < 2048; i += K1_THREADS) s_ptab[i] = g_ptab[i];
+    for (int i = threadIdx.x; i < 256; i += K1_THREADS) s_mtab[i] = g_mtab[i];
     __syncthreads();
 
     for (long long chunk = (long long)blockIdx.x * K1_THREADS + threadIdx.x; chunk < total_chunks;
          chunk += (long long)gridDim.x * K1_THREADS) {
         const long long view = chunk / chunks_per_view;
         const long long c = chunk - view * chunks_per_view;
-        const uint8_t *src = stack + (size_t)view * 14 * P + (size_t)c * 16;
-        uint4 img[14];
+        const uint8_t *src = stack + (size_t)view * 14 * P + (size_t)c * (4 * NW);
+        uint32_t img[14][NW];
 #pragma unroll
-        for (int n = 0; n < 14; n++) img[n] = slr::ldg_stream_u4(src + (size_t)n * P);
-
-        float ph[16];
-        uint32_t mk[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            // computeShadows (:199-204): white - black > blackThreshold
-            bool m = (byte_of(img[0], i) - byte_of(img[1], i)) > black_thr;
-            int G[12];
-#pragma unroll
-            for (int n = 0; n < 12; n++) G[n] = byte_of(img[2 + n], i);
-            float p;
-            const bool ok = slr::phase_strict(G, lut, p);
-            m = m && ok;
-            ph[i] = m ? p : slr::qnan();
-            mk[i >> 2] |= (m ? 1u : 0u) << (8 * (i & 3));
+        for (int n = 0; n < 14; n++) {
+            if (NW == 4) {
+                const uint4 v = slr::ldg_stream_u4(src + (size_t)n * P);
+                img[n][0] = v.x, img[n][1] = v.y, img[n][NW - 2] = v.z, img[n][NW - 1] = v.w;
+            } else {
+                const uint2 v = slr::ldg_stream_u2(src + (size_t)n * P);
+                img[n][0] = v.x, img[n][1] = v.y;
+            }
         }
-        const size_t o = (size_t)view * P + (size_t)c * 16;
+
+        const size_t o = (size_t)view * P + (size_t)c * (4 * NW);
+        uint32_t mk[NW];
 #pragma unroll
-        for (int v = 0; v < 4; v++)
-            slr::stg_stream_f4(phase + o + 4 * v, make_float4(ph[4 * v], ph[4 * v + 1], ph[4 * v + 2], ph[4 * v + 3]));
-        slr::stg_stream_u4(mask + o, make_uint4(mk[0], mk[1], mk[2], mk[3]));
+        for (int w = 0; w < NW; w++) {  // one 32-bit word = 4 pixels of every plane
+            auto word = [&](int n) { return img[n][w]; };
+            float ph[4];
+            uint32_t m4 = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                bool ok = (int)slr::byte_of(word(0), i) - (int)slr::byte_of(word(1), i) > black_thr;  // computeShadows (:199-204)
+                double Pw[3];
+#pragma unroll
+                for (int f = 0; f < 3; f++)
+                    Pw[f] = slr::wrapped_strict_tab(slr::byte_of(word(2 + 4 * f), i), slr::byte_of(word(3 + 4 * f), i),
+                                                    slr::byte_of(word(4 + 4 * f), i), slr::byte_of(word(5 + 4 * f), i), s_ptab,
+                                                    s_mtab, ok);
+                const float p = slr::heterodyne_strict_d(Pw[0], Pw[1], Pw[2]);
+                ph[i] = ok ? p : slr::qnan();
+                m4 |= (ok ? 1u : 0u) << (8 * i);
+            }
+            slr::stg_stream_f4(phase + o + 4 * w, make_float4(ph[0], ph[1], ph[2], ph[3]));
+            mk[w] = m4;
+        }
+        if (NW == 4)
+            slr::stg_stream_u4(mask + o, make_uint4(mk[0], mk[1], mk[NW - 2], mk[NW - 1]));
+        else
+            *reinterpret_cast<uint2 *>(mask + o) = make_uint2(mk[0], mk[1]);
     }
 }
 
@@ -173,14 +189,19 @@ slr_status slr_launch_mf_decode(slr_engine *e, const uint8_t *d_stack, int views
                                       "(Duke/mfreconstruct.cpp:237); got F=%d S=%d", F, S);
         const bool vec = (P % 16 == 0) && (((uintptr_t)d_stack | (uintptr_t)d_phase | (uintptr_t)d_mask) % 16 == 0);
         if (vec) {
-            const long long cpv = (long long)(P / 16);
+            const int nw = getenv("SLR_K1_NW2") ? 2 : 4;  // 128-bit loads measured best (0.139 vs 0.148 ms per 8 scans)
+            const long long cpv = (long long)(P / (4 * nw));
             const long long total = cpv * views;
             long long blocks = (total + K1_THREADS - 1) / K1_THREADS;
-            const long long cap = (long long)e->num_sms * 32;
+            const long long cap = (long long)e->num_sms * (nw == 4 ? 2 : 3);   // persistent: tables loaded once per CTA
             if (blocks > cap) blocks = cap;
             if (blocks < 1) blocks = 1;
-            k1_mf_decode_strict<<<(unsigned)blocks, K1_THREADS, 0, e->stream>>>(d_stack, P, cpv, total, black_thr,
-                                                                                e->d_atan_lut, d_phase, d_mask);
+            if (nw == 4)
+                k1_mf_decode_strict<4><<<(unsigned)blocks, K1_THREADS, 0, e->stream>>>(d_stack, P, cpv, total, black_thr,
+                                                                                       e->d_ptab, e->d_mtab, d_phase, d_mask);
+            else
+                k1_mf_decode_strict<2><<<(unsigned)blocks, K1_THREADS, 0, e->stream>>>(d_stack, P, cpv, total, black_thr,
+                                                                                       e->d_ptab, e->d_mtab, d_phase, d_mask);
         } else {
             const long long total = (long long)P * views;
             long long blocks = (total + K1_THREADS - 1) / K1_THREADS;

@@ -77,9 +77,6 @@ __device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gme
         : "memory");
 }
 
-// byte i of a 32-bit word, zero extended: one PRMT
-__device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return __byte_perm(w, 0, 0x4440 + i); }
-
 // Window buckets.  Bucket width 1/4; a right value pR is filed under every bucket that the interval
 // [pR - 0.11, pR + 0.11] touches (one or two), so a left value only probes its own bucket: any pL with
 // fabs(pL - pR) < 0.1 lies inside that interval, and the clamp keeps the mapping monotone for huge values
@@ -87,50 +84,6 @@ __device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return __byte_p
 __device__ __forceinline__ int window_bucket(float p)
 {
     return __float2int_rd(__fmul_rn(fminf(fmaxf(p, -30000.0f), 30000.0f), 4.0f));
-}
-
-// ---- strict decode of one pixel from table lookups (Duke/mfreconstruct.cpp:239-268) ----------------
-// Returns the wrapped phase of one frequency as a double holding the reference's float value.
-// ptab rows (512 doubles each, entry 256 + signed quotient):
-//   0: b > 0, a <= 0 -> atan(q)          1: b < 0 -> atan(q) + PI        2: b > 0, a > 0 -> atan(q) + 2PI
-//   3: b == 0 -> 3PI/2 (a > 0) / PI/2 (a < 0); mtab[0] = 65536 makes the "quotient" there equal to a.
-__device__ __forceinline__ double wrapped_strict_tab(int G1, int G2, int G3, int G4, const double *ptab,
-                                                     const uint32_t *mtab, bool &ok)
-{
-    const int a = G4 - G2, b = G1 - G3;
-    const int ua = abs(a), ub = abs(b);
-    // floor(ua/ub) for 0 <= ua,ub <= 255 via M = floor(65536/ub)+1: the excess ua/65536 < 1/256 <= 1/ub can never
-    // reach the next integer because a non-integer quotient has a fractional part <= 1 - 1/ub.
-    const int q = (int)(((uint32_t)ua * mtab[ub]) >> 16);
-    const int sg = (a ^ b) >> 31;                       // C++ int division truncates toward zero
-    const int qs = (q ^ sg) - sg;
-    int row = (b < 0) ? 512 : ((a > 0) ? 1024 : 0);
-    row = (ub == 0) ? 1536 : row;                       // :250 / :252
-    ok = ok && ((ua | ub) != 0);                        // :254 degenerate
-    return ptab[row + 256 + qs];
-}
-
-__device__ __forceinline__ float heterodyne_strict_d(double P0, double P1, double P2)
-{
-    constexpr float PI_2 = 2.0f * SLR_PI_DEC;
-    constexpr float RPI_2 = 1.0f / PI_2;                // RN(1/(2*PI))
-    const double c = (double)PI_2;
-    double d01 = __dsub_rn(P0, P1);
-    double d12 = __dsub_rn(P1, P2);
-    if (!(P0 > P1)) d01 = __dadd_rn(d01, c);
-    if (!(P1 > P2)) d12 = __dadd_rn(d12, c);
-    const float P12 = __double2float_rn(d01);
-    const float P23 = __double2float_rn(d12);
-    const float d = __fsub_rn(P12, P23);
-    const float P123 = (P12 > P23) ? d : __fadd_rn(d, PI_2);
-    // P123 / (2*PI), correctly rounded, without the generic division routine: with rc = RN(1/c),
-    // q0 = RN(x*rc), rem = x - c*q0 (exact in an FMA), RN(q0 + rem*rc) == RN(x/c).  Verified
-    // exhaustively on the host against IEEE division for every float with 2^-100 <= |x| < 32 and x = +0
-    // (scratch/div_check.c); P123 is +0-free of sign issues and a multiple of 2^-24, so it is in range.
-    const float q0 = __fmul_rn(P123, RPI_2);
-    const float rem = __fmaf_rn(-q0, PI_2, P123);
-    const float quo = __fmaf_rn(rem, RPI_2, q0);
-    return __fmul_rn(quo, 255.0f);
 }
 
 template <int MODE>
@@ -143,7 +96,7 @@ __device__ __forceinline__ void decode_chunk(const uint8_t *__restrict__ rows, i
     const int wstride = W >> 2;
     const uint32_t wv = base[0], bv = base[wstride];
 #pragma unroll
-    for (int i = 0; i < 4; i++) ok[i] = (int)byte_of(wv, i) - (int)byte_of(bv, i) > p.black_thr;  // computeShadows
+    for (int i = 0; i < 4; i++) ok[i] = (int)slr::byte_of(wv, i) - (int)slr::byte_of(bv, i) > p.black_thr;  // computeShadows
     if (MODE == SLR_MODE_STRICT) {
         double P[3][4];
 #pragma unroll
@@ -152,11 +105,35 @@ __device__ __forceinline__ void decode_chunk(const uint8_t *__restrict__ rows, i
             const uint32_t g3 = base[(4 + 4 * f) * wstride], g4 = base[(5 + 4 * f) * wstride];
 #pragma unroll
             for (int i = 0; i < 4; i++)
-                P[f][i] = wrapped_strict_tab(byte_of(g1, i), byte_of(g2, i), byte_of(g3, i), byte_of(g4, i), s_ptab,
+                P[f][i] = slr::wrapped_strict_tab(slr::byte_of(g1, i), slr::byte_of(g2, i), slr::byte_of(g3, i), slr::byte_of(g4, i), s_ptab,
                                              s_mtab, ok[i]);
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) ph[i] = heterodyne_strict_d(P[0][i], P[1][i], P[2][i]);
+        for (int i = 0; i < 4; i++) ph[i] = slr::heterodyne_strict_d(P[0][i], P[1][i], P[2][i]);
+    } else if (p.F == 3 && p.S == 4) {
+        // the reference's 3 frequencies x 4 steps, fully unrolled (same arithmetic as the generic branch below)
+        float l[3][4];
+#pragma unroll
+        for (int f = 0; f < 3; f++) {
+            const uint32_t g1 = base[(2 + 4 * f) * wstride], g2 = base[(3 + 4 * f) * wstride];
+            const uint32_t g3 = base[(4 + 4 * f) * wstride], g4 = base[(5 + 4 * f) * wstride];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int a = (int)slr::byte_of(g4, i) - (int)slr::byte_of(g2, i);
+                const int b = (int)slr::byte_of(g1, i) - (int)slr::byte_of(g3, i);
+                ok[i] = ok[i] && ((a | b) != 0);
+                float ang = atan2f((float)a, (float)b);
+                if (ang < 0.0f) ang = __fadd_rn(ang, SLR_TWO_PI_F);
+                l[f][i] = ang;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float d01 = slr::wrap_2pi(__fsub_rn(l[0][i], l[1][i]));
+            const float d12 = slr::wrap_2pi(__fsub_rn(l[1][i], l[2][i]));
+            const float d = slr::wrap_2pi(__fsub_rn(d01, d12));
+            ph[i] = __fmul_rn(__fdiv_rn(d, SLR_TWO_PI_F), 255.0f);
+        }
     } else {
         float lvl[8][4];
         const int F = p.F, S = p.S;
@@ -167,7 +144,7 @@ __device__ __forceinline__ void decode_chunk(const uint8_t *__restrict__ rows, i
                 const uint32_t v = base[(2 + S * f + s) * wstride];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const int g = (int)byte_of(v, i);
+                    const int g = (int)slr::byte_of(v, i);
                     if (S == 4) {
                         inum[i] += (s == 3) ? g : (s == 1) ? -g : 0;
                         iden[i] += (s == 0) ? g : (s == 2) ? -g : 0;
@@ -298,7 +275,7 @@ k_fused_mf(const FusedParams p)
                     const uint32_t m = reinterpret_cast<const uint32_t *>(stage + 9 * W)[c];
                     ph[0] = v.x, ph[1] = v.y, ph[2] = v.z, ph[3] = v.w;
 #pragma unroll
-                    for (int q = 0; q < 4; q++) ok[q] = byte_of(m, q) != 0 && ph[q] == ph[q];  // NaN never matches
+                    for (int q = 0; q < 4; q++) ok[q] = slr::byte_of(m, q) != 0 && ph[q] == ph[q];  // NaN never matches
                 } else {
                     decode_chunk<MODE>(stage + (size_t)N * W, W, c, p, s_ptab, s_mtab, ph, ok);
                 }
@@ -338,7 +315,7 @@ k_fused_mf(const FusedParams p)
                     const uint32_t m = reinterpret_cast<const uint32_t *>(stage + 8 * W)[c];
                     ph[0] = v.x, ph[1] = v.y, ph[2] = v.z, ph[3] = v.w;
 #pragma unroll
-                    for (int q = 0; q < 4; q++) ok[q] = byte_of(m, q) != 0;
+                    for (int q = 0; q < 4; q++) ok[q] = slr::byte_of(m, q) != 0;
                 } else {
                     decode_chunk<MODE>(stage, W, c, p, s_ptab, s_mtab, ph, ok);
                 }
@@ -385,28 +362,29 @@ k_fused_mf(const FusedParams p)
                     if (slr::phase_match(v1, __uint_as_float(e.x))) best1 = min(best1, (int)e.y);
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int j = u ? j1 : j0;
-                const int best = u ? best1 : best0;
-                if (j < W) {
-                    float X = slr::qnan(), Y = slr::qnan(), Z = slr::qnan();
-                    const bool hit = (best != INT_MAX);
-                    if (hit) {
-                        const float ulx = u ? ulx1 : ulx0;
-                        const float uly = u ? uly1 : uly0;
-                        const float urx = __ldg(rx_row + best);
-                        const float disp = __fsub_rn(ulx, urx);
-                        slr::reproject_q(p.calib, (double)ulx, (double)uly, (double)disp, X, Y, Z);
-                        n_local++;
-                    }
-                    float *dst = xyz_row + 3 * j;
-                    dst[0] = X;
-                    dst[1] = Y;
-                    dst[2] = Z;
-                    valid_row[j] = hit ? 1 : 0;
-                    if (k_row) k_row[j] = hit ? best : -1;
-                }
+            // both pixels are reprojected unconditionally (dummy inputs where there is no match) so that the two
+            // independent fp64 chains interleave; misses are turned into NaN afterwards
+            const bool hit0 = (best0 != INT_MAX), hit1 = (best1 != INT_MAX);
+            const float urx0 = hit0 ? __ldg(rx_row + best0) : 0.0f, urx1 = hit1 ? __ldg(rx_row + best1) : 0.0f;
+            float X0, Y0, Z0, X1, Y1, Z1;
+            slr::reproject_q(p.calib, (double)ulx0, (double)uly0, (double)__fsub_rn(ulx0, urx0), X0, Y0, Z0);
+            slr::reproject_q(p.calib, (double)ulx1, (double)uly1, (double)__fsub_rn(ulx1, urx1), X1, Y1, Z1);
+            n_local += (hit0 ? 1u : 0u) + (hit1 ? 1u : 0u);
+            if (j0 < W) {
+                float *dst = xyz_row + 3 * j0;
+                dst[0] = hit0 ? X0 : slr::qnan();
+                dst[1] = hit0 ? Y0 : slr::qnan();
+                dst[2] = hit0 ? Z0 : slr::qnan();
+                valid_row[j0] = hit0 ? 1 : 0;
+                if (k_row) k_row[j0] = hit0 ? best0 : -1;
+            }
+            if (j1 < W) {
+                float *dst = xyz_row + 3 * j1;
+                dst[0] = hit1 ? X1 : slr::qnan();
+                dst[1] = hit1 ? Y1 : slr::qnan();
+                dst[2] = hit1 ? Z1 : slr::qnan();
+                valid_row[j1] = hit1 ? 1 : 0;
+                if (k_row) k_row[j1] = hit1 ? best1 : -1;
             }
         }
         // the next iteration clears the tables: every warp must be done probing them

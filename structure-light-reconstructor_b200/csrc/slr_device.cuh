@@ -28,6 +28,12 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const void *p)
                  : "l"(p));
     return r;
 }
+__device__ __forceinline__ uint2 ldg_stream_u2(const void *p)
+{
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ uint32_t ldg_stream_u32(const void *p)
 {
     uint32_t r;
@@ -172,6 +178,56 @@ __device__ __forceinline__ bool phase_strict(const int (&G)[12], const float *__
     }
     phase = heterodyne_strict(P[0], P[1], P[2]);
     return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// strict mode, table-driven form used by the kernels (tables built by slr_build_strict_tables, k_fused.cu)
+// ------------------------------------------------------------------------------------------------
+// byte i of a 32-bit word, zero extended: one PRMT
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return __byte_perm(w, 0, 0x4440 + i); }
+
+// ---- strict decode of one pixel from table lookups (Duke/mfreconstruct.cpp:239-268) ----------------
+// Returns the wrapped phase of one frequency as a double holding the reference's float value.
+// ptab rows (512 doubles each, entry 256 + signed quotient):
+//   0: b > 0, a <= 0 -> atan(q)          1: b < 0 -> atan(q) + PI        2: b > 0, a > 0 -> atan(q) + 2PI
+//   3: b == 0 -> 3PI/2 (a > 0) / PI/2 (a < 0); mtab[0] = 65536 makes the "quotient" there equal to a.
+__device__ __forceinline__ double wrapped_strict_tab(int G1, int G2, int G3, int G4, const double *ptab,
+                                                     const uint32_t *mtab, bool &ok)
+{
+    const int a = G4 - G2, b = G1 - G3;
+    const int ua = abs(a), ub = abs(b);
+    // floor(ua/ub) for 0 <= ua,ub <= 255 via M = floor(65536/ub)+1: the excess ua/65536 < 1/256 <= 1/ub can never
+    // reach the next integer because a non-integer quotient has a fractional part <= 1 - 1/ub.
+    const int q = (int)(((uint32_t)ua * mtab[ub]) >> 16);
+    const int sg = (a ^ b) >> 31;                       // C++ int division truncates toward zero
+    const int qs = (q ^ sg) - sg;
+    int row = (b < 0) ? 512 : ((a > 0) ? 1024 : 0);
+    row = (ub == 0) ? 1536 : row;                       // :250 / :252
+    ok = ok && ((ua | ub) != 0);                        // :254 degenerate
+    return ptab[row + 256 + qs];
+}
+
+__device__ __forceinline__ float heterodyne_strict_d(double P0, double P1, double P2)
+{
+    constexpr float PI_2 = 2.0f * SLR_PI_DEC;
+    constexpr float RPI_2 = 1.0f / PI_2;                // RN(1/(2*PI))
+    const double c = (double)PI_2;
+    double d01 = __dsub_rn(P0, P1);
+    double d12 = __dsub_rn(P1, P2);
+    if (!(P0 > P1)) d01 = __dadd_rn(d01, c);
+    if (!(P1 > P2)) d12 = __dadd_rn(d12, c);
+    const float P12 = __double2float_rn(d01);
+    const float P23 = __double2float_rn(d12);
+    const float d = __fsub_rn(P12, P23);
+    const float P123 = (P12 > P23) ? d : __fadd_rn(d, PI_2);
+    // P123 / (2*PI), correctly rounded, without the generic division routine: with rc = RN(1/c),
+    // q0 = RN(x*rc), rem = x - c*q0 (exact in an FMA), RN(q0 + rem*rc) == RN(x/c).  Verified
+    // exhaustively on the host against IEEE division for every float with 2^-100 <= |x| < 32 and x = +0
+    // (scratch/div_check.c); P123 is +0-free of sign issues and a multiple of 2^-24, so it is in range.
+    const float q0 = __fmul_rn(P123, RPI_2);
+    const float rem = __fmaf_rn(-q0, PI_2, P123);
+    const float quo = __fmaf_rn(rem, RPI_2, q0);
+    return __fmul_rn(quo, 255.0f);
 }
 
 // ------------------------------------------------------------------------------------------------

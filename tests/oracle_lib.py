@@ -43,6 +43,7 @@ class Oracle:
         lib.orc_get_phase_strict.argtypes = [vp, vp]
         lib.orc_wrapped_phase_strict.argtypes = [i32, i32, vp]
         lib.orc_mf_decode.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp]
+        lib.orc_mf_decode_mt.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32]
         lib.orc_gray_decode.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]
         lib.orc_undistort_point.argtypes = [C.c_float, C.c_float, C.POINTER(OrcCamera), vp, vp]
         lib.orc_cam2world.argtypes = [C.POINTER(OrcCamera), vp]
@@ -92,14 +93,15 @@ class Oracle:
         ok = self.lib.orc_wrapped_phase_strict(a, b, C.byref(p))
         return bool(ok), np.float32(p.value)
 
-    def mf_decode(self, stack, F=3, S=4, black_thr=40, mode=0):
+    def mf_decode(self, stack, F=3, S=4, black_thr=40, mode=0, nthreads=1):
         """stack: uint8 [N, H, W] (one camera) -> (phase f32 [H,W], mask u8 [H,W])"""
         stack = np.ascontiguousarray(stack, np.uint8)
         N, H, W = stack.shape
         assert N == 2 + F * S
         ph = np.empty((H, W), np.float32)
         mk = np.empty((H, W), np.uint8)
-        rc = self.lib.orc_mf_decode(stack.ctypes.data, W, H, F, S, black_thr, mode, ph.ctypes.data, mk.ctypes.data)
+        rc = self.lib.orc_mf_decode_mt(stack.ctypes.data, W, H, F, S, black_thr, mode, ph.ctypes.data, mk.ctypes.data,
+                                       nthreads)
         assert rc == 0
         return ph, mk
 
