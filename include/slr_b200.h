@@ -159,7 +159,8 @@ SLR_API slr_status slr_bucket_triangulate(slr_engine *e, const int32_t *d_col, c
 SLR_API slr_status slr_run_mf(slr_engine *e, const uint8_t *d_stack, int batch, int F, int S,
                               int black_thr, int mode, float *d_xyz, uint8_t *d_valid,
                               int32_t *d_match_k, unsigned long long *d_n_points);
-/* Reconstruct::runReconstruction_GE minus image IO, Duke/reconstruct.cpp:271-307. */
+/* Reconstruct::runReconstruction_GE minus image IO, Duke/reconstruct.cpp:271-307 (K2 then K3b through engine
+ * scratch; integer codes make the intermediate cheap: 5 bytes per pixel). */
 SLR_API slr_status slr_run_ge(slr_engine *e, const uint8_t *d_stack, int batch, int nbits_col,
                               int black_thr, int white_thr, int scan_w, int have_color,
                               float *d_xyz, uint8_t *d_valid, int32_t *d_match_k, uint8_t *d_color,
