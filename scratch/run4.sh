@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+b() { timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu --no-e2e 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['frac'])"; }
+b
+python scratch/phase_clocks.py strict 2>&1 | tail -9
+python scratch/phase_clocks.py corrected 2>&1 | tail -9

@@ -16,7 +16,8 @@ from dataclasses import dataclass, field
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libslr_b200.so")
+# SLR_B200_LIB: load another build of the same library (the phase-clock debug build of csrc/Makefile PHASE=1)
+LIB_PATH = os.environ.get("SLR_B200_LIB") or os.path.join(_HERE, "libslr_b200.so")
 
 MODE_STRICT = 0
 MODE_CORRECTED = 1

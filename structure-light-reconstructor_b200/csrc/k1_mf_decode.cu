@@ -13,18 +13,18 @@ namespace {
 constexpr int K1_THREADS = 256;
 
 // strict mode, F = 3, S = 4, 16 pixels per thread, table-driven exact decode (slr_device.cuh: the integer quotient by
-// reciprocal multiplication, the wrapped phase from the 4x512 table of the reference's float values held as
-// doubles); persistent grid-stride CTAs load the 17 KB of tables into shared memory once
+// reciprocal multiplication, the wrapped phase from the table of the reference's float values held in exact
+// 2^-24 fixed point); persistent grid-stride CTAs load the 8 KB of tables into shared memory once
 template <int NW>  // 32-bit words (4 pixels each) per thread per plane: 4 = 128-bit loads, 2 = 64-bit loads
 __global__ void __launch_bounds__(K1_THREADS, NW == 4 ? 2 : 3)
 k1_mf_decode_strict(const uint8_t *__restrict__ stack, size_t P, long long chunks_per_view, long long total_chunks,
-                    int black_thr, const double *__restrict__ g_ptab, const uint32_t *__restrict__ g_mtab,
+                    int black_thr, const int *__restrict__ g_ptab, const uint32_t *__restrict__ g_btab,
                     float *__restrict__ phase, uint8_t *__restrict__ mask)
 {
-    __shared__ double s_ptab[2048];
-    __shared__ uint32_t s_mtab[256];
-    for (int i = threadIdx.x; i < 2048; i += K1_THREADS) s_ptab[i] = g_ptab[i];
-    for (int i = threadIdx.x; i < 256; i += K1_THREADS) s_mtab[i] = g_mtab[i];
+    __shared__ int s_ptab[SLR_PTAB_SIZE];
+    __shared__ uint32_t s_btab[SLR_BTAB_SIZE];
+    for (int i = threadIdx.x; i < SLR_PTAB_SIZE; i += K1_THREADS) s_ptab[i] = g_ptab[i];
+    for (int i = threadIdx.x; i < SLR_BTAB_SIZE; i += K1_THREADS) s_btab[i] = g_btab[i];
     __syncthreads();
 
     for (long long chunk = (long long)blockIdx.x * K1_THREADS + threadIdx.x; chunk < total_chunks;
@@ -54,13 +54,13 @@ k1_mf_decode_strict(const uint8_t *__restrict__ stack, size_t P, long long chunk
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 bool ok = (int)slr::byte_of(word(0), i) - (int)slr::byte_of(word(1), i) > black_thr;  // computeShadows (:199-204)
-                double Pw[3];
+                int Pw[3];
 #pragma unroll
-                for (int f = 0; f < 3; f++)
-                    Pw[f] = slr::wrapped_strict_tab(slr::byte_of(word(2 + 4 * f), i), slr::byte_of(word(3 + 4 * f), i),
-                                                    slr::byte_of(word(4 + 4 * f), i), slr::byte_of(word(5 + 4 * f), i), s_ptab,
-                                                    s_mtab, ok);
-                const float p = slr::heterodyne_strict_d(Pw[0], Pw[1], Pw[2]);
+                for (int f = 0; f < 3; f++)   // a = G4 - G2, b = G1 - G3 (:239-242)
+                    Pw[f] = slr::wrapped_strict_fx((int)slr::byte_of(word(5 + 4 * f), i) - (int)slr::byte_of(word(3 + 4 * f), i),
+                                                   (int)slr::byte_of(word(2 + 4 * f), i) - (int)slr::byte_of(word(4 + 4 * f), i),
+                                                   s_ptab, s_btab);
+                const float p = slr::heterodyne_strict_fx(Pw[0], Pw[1], Pw[2], ok);
                 ph[i] = ok ? p : slr::qnan();
                 m4 |= (ok ? 1u : 0u) << (8 * i);
             }
@@ -159,9 +159,7 @@ k1_mf_decode_corrected(const uint8_t *__restrict__ stack, size_t P, long long ch
                 } else if (__fadd_rn(__fmul_rn(nn, nn), __fmul_rn(dd, dd)) < 0.25f) {
                     ok[i] = false;
                 }
-                float ph = atan2f(nn, dd);
-                if (ph < 0.0f) ph = __fadd_rn(ph, SLR_TWO_PI_F);
-                lvl[f][i] = ph;
+                lvl[f][i] = slr::atan2_pos(nn, dd);
             }
         }
         for (int n = F; n > 1; n--)
@@ -171,7 +169,7 @@ k1_mf_decode_corrected(const uint8_t *__restrict__ stack, size_t P, long long ch
         const size_t o = (size_t)view * P + (size_t)c * PX;
 #pragma unroll
         for (int i = 0; i < PX; i++) {
-            const float p = __fmul_rn(__fdiv_rn(lvl[0][i], SLR_TWO_PI_F), 255.0f);
+            const float p = slr::phase_scale_corrected(lvl[0][i]);
             phase[o + i] = ok[i] ? p : slr::qnan();
             mask[o + i] = ok[i] ? 1 : 0;
         }
@@ -198,10 +196,10 @@ slr_status slr_launch_mf_decode(slr_engine *e, const uint8_t *d_stack, int views
             if (blocks < 1) blocks = 1;
             if (nw == 4)
                 k1_mf_decode_strict<4><<<(unsigned)blocks, K1_THREADS, 0, e->stream>>>(d_stack, P, cpv, total, black_thr,
-                                                                                       e->d_ptab, e->d_mtab, d_phase, d_mask);
+                                                                                       e->d_ptab, e->d_btab, d_phase, d_mask);
             else
                 k1_mf_decode_strict<2><<<(unsigned)blocks, K1_THREADS, 0, e->stream>>>(d_stack, P, cpv, total, black_thr,
-                                                                                       e->d_ptab, e->d_mtab, d_phase, d_mask);
+                                                                                       e->d_ptab, e->d_btab, d_phase, d_mask);
         } else {
             const long long total = (long long)P * views;
             long long blocks = (total + K1_THREADS - 1) / K1_THREADS;

@@ -3,28 +3,29 @@
 // Replaces MFReconstruct::runReconstruction minus image IO (Duke/mfreconstruct.cpp:160-334).
 //
 // HBM traffic is the algorithmic minimum: every stack byte is read once (TMA bulk copies into
-// shared memory), every output byte written once (TMA bulk stores); the phase maps never exist in
-// global memory.  One persistent CTA owns one rectified row of one scan at a time:
+// shared memory), every output byte written once; the phase maps never exist in global memory.
+// One persistent CTA owns one rectified row of one scan at a time:
 //
 //   [TMA]   the 2*N image rows (both cameras, all planes) of the NEXT row stream into the stage
-//           buffer while the current row is matched and triangulated;
-//   decode  4 pixels per thread from shared memory, strict mode through two small tables
-//           (exact integer quotient by reciprocal multiplication, and the finite set of wrapped
-//           phase values atan(float(q)) + {0, PI, 2PI} held as doubles), heterodyne in fp64/fp32
-//           exactly as the reference evaluates it;
+//           buffer while the current row is matched and triangulated; the three undistort-map rows
+//           (left x, left y, right x) of image row i are bulk-copied into shared memory once per i
+//           (a CTA walks a contiguous range of (i, scan) pairs, scan fastest);
+//   decode  4 pixels per thread from shared memory in full rounds, the remainder of the row one pixel
+//           per thread so that every thread carries the same load.  Strict mode goes through two
+//           small tables (exact integer quotient by reciprocal multiplication, and the finite set of
+//           wrapped phase values atan(float(q)) + {0, PI, 2PI} held in exact 2^-24 fixed point), the
+//           heterodyne follows the reference's double/float mix exactly (slr_device.cuh);
 //   match   right-row phases go into an open-addressing table keyed by the exact float value
-//           (atomicCAS) holding the minimum column (atomicMin): strict-mode phases repeat heavily
-//           (a few values occupy ~7 % of a row each), and only the smallest k of equal values can be
-//           "the first k".  Each distinct value is then filed under the one or two phase buckets
-//           (width 1/4) its +-0.1 match window touches, so a left pixel walks a single short chain,
-//           applies the exact predicate and keeps the minimum k  ==  the reference's first-k linear
-//           scan, exactly;
-//   emit    warps take 32-pixel groups of the left row from a shared counter (chain lengths vary along
+//           holding the minimum column: strict-mode phases repeat heavily (a few values occupy ~7 %
+//           of a row each), and only the smallest k of equal values can be "the first k".  A plain
+//           64-bit load of the entry settles the common case (value already present with a smaller
+//           column); atomicCAS / atomicMin only run for new values and new minima.  Each distinct
+//           value is then filed under the one or two phase buckets (width 1/4) its +-0.1 match
+//           window touches, so a left pixel walks a single short chain, applies the exact predicate
+//           and keeps the minimum k  ==  the reference's first-k linear scan, exactly;
+//   emit    warps take pixel groups of the left row from a shared counter (chain lengths vary along
 //           a row, so static assignment leaves warps idle at the barrier); Q reprojection in fp64 with
-//           the precomputed undistortPoints maps; XYZ / valid / match_k written straight from registers.
-//
-// Rows are visited row-index-major (all scans' row i back to back) so the undistort-map row stays
-// hot in L2 while the image stacks stream through with an evict-first policy.
+//           the undistortPoints maps from shared memory; XYZ / valid / match_k written from registers.
 #include <limits.h>
 #include <stdlib.h>
 
@@ -47,19 +48,33 @@ struct FusedParams {
     const float *phase;    // MODE_PHASE_INPUT: [batch][2][H][W]
     const uint8_t *mask;   // MODE_PHASE_INPUT: [batch][2][H][W]
     int W, H, batch, F, S, N;
-    int T, logT;           // dedupe table / bucket heads size (power of two)
+    int T, logT;           // dedupe table size (power of two); 2T bucket heads
     int black_thr;
-    int stagger_ns, num_sms;
     const float *lx, *ly, *rx;
-    const double *ptab;    // strict: [4][512] wrapped-phase values; see build_strict_tables()
-    const uint32_t *mtab;  // strict: [256] reciprocal multipliers
+    const int *ptab;       // strict: [SLR_PTAB_SIZE] wrapped-phase values, 2^-24 fixed point (slr_device.cuh)
+    const uint32_t *btab;  // strict: [SLR_BTAB_SIZE] reciprocal multipliers + row bases
     float cs[16], sn[16];  // corrected: cos/sin(2 pi s / S)
     float *xyz;
     uint8_t *valid;
     int32_t *match_k;
     unsigned long long *n_points;
     slr_calib_dev calib;
+#ifdef SLR_PHASE_CLOCKS
+    long long *dbg;        // [grid][DBG_ROWS][16 warps][DBG_PTS] clock64 stamps (debug builds only)
+#endif
 };
+
+#ifdef SLR_PHASE_CLOCKS
+constexpr int DBG_ROWS = 8, DBG_PTS = 7, DBG_SKIP = 4;
+#define SLR_STAMP(pt)                                                                                          \
+    do {                                                                                                       \
+        __syncwarp();                                                                                          \
+        if (lane == 0 && it >= DBG_SKIP && it < DBG_SKIP + DBG_ROWS)                                            \
+            p.dbg[(((size_t)blockIdx.x * DBG_ROWS + (it - DBG_SKIP)) * 16 + (tid >> 5)) * DBG_PTS + (pt)] = clock64(); \
+    } while (0)
+#else
+#define SLR_STAMP(pt) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint64_t make_evict_first_policy()
 {
@@ -81,69 +96,84 @@ __device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gme
 // [pR - 0.11, pR + 0.11] touches (one or two), so a left value only probes its own bucket: any pL with
 // fabs(pL - pR) < 0.1 lies inside that interval, and the clamp keeps the mapping monotone for huge values
 // (where float spacing exceeds the margin every such value shares the end bucket).
+template <bool CLAMP>
 __device__ __forceinline__ int window_bucket(float p)
 {
-    return __float2int_rd(__fmul_rn(fminf(fmaxf(p, -30000.0f), 30000.0f), 4.0f));
+    // decoded phases are bounded (|p| < 1000); caller-supplied phase maps (MODE_PHASE_INPUT) are arbitrary floats
+    if (CLAMP) p = fminf(fmaxf(p, -30000.0f), 30000.0f);
+    return __float2int_rd(__fmul_rn(p, 4.0f));
 }
 
-template <int MODE>
-__device__ __forceinline__ void decode_chunk(const uint8_t *__restrict__ rows, int W, int c, const FusedParams &p,
-                                             const double *s_ptab, const uint32_t *s_mtab, float (&ph)[4],
-                                             bool (&ok)[4])
+// Slot of a phase value.  Two multiply rounds: a single multiplicative hash maps the arithmetic progressions that
+// smooth (corrected-mode) phase ramps form in float-bit space onto a handful of slots for unlucky strides, and
+// probing then degenerates into scans of hundreds of entries.
+__device__ __forceinline__ uint32_t slot_of(uint32_t key, int logT)
 {
-    // rows = [N][W] u8 for one camera in shared memory; c = 4-pixel chunk index
-    const uint32_t *base = reinterpret_cast<const uint32_t *>(rows) + c;
-    const int wstride = W >> 2;
-    const uint32_t wv = base[0], bv = base[wstride];
+    uint32_t h = key * 0x9E3779B1u;
+    h ^= h >> 15;
+    h *= 0x85EBCA77u;
+    return h >> (32 - logT);
+}
+
+// PX consecutive pixels (4 / 2 / 1: one 32- / 16- / 8-bit load per plane) of one camera row held in shared
+// memory as rows = [N][W] u8; x0 = first pixel (a multiple of PX).
+template <int MODE, int PX>
+__device__ __forceinline__ void decode_px(const uint8_t *__restrict__ rows, int W, int x0, const FusedParams &p,
+                                          const int *s_ptab, const uint32_t *s_btab, float (&ph)[PX], bool (&ok)[PX])
+{
+    auto plane = [&](int n) -> uint32_t {
+        if (PX == 4) return *reinterpret_cast<const uint32_t *>(rows + (size_t)n * W + x0);
+        if (PX == 2) return *reinterpret_cast<const uint16_t *>(rows + (size_t)n * W + x0);
+        return rows[(size_t)n * W + x0];
+    };
+    const uint32_t wv = plane(0), bv = plane(1);
 #pragma unroll
-    for (int i = 0; i < 4; i++) ok[i] = (int)slr::byte_of(wv, i) - (int)slr::byte_of(bv, i) > p.black_thr;  // computeShadows
+    for (int i = 0; i < PX; i++) ok[i] = (int)slr::byte_of(wv, i) - (int)slr::byte_of(bv, i) > p.black_thr;  // computeShadows
     if (MODE == SLR_MODE_STRICT) {
-        double P[3][4];
+        int P[3][PX];
 #pragma unroll
         for (int f = 0; f < 3; f++) {
-            const uint32_t g1 = base[(2 + 4 * f) * wstride], g2 = base[(3 + 4 * f) * wstride];
-            const uint32_t g3 = base[(4 + 4 * f) * wstride], g4 = base[(5 + 4 * f) * wstride];
+            const uint32_t g1 = plane(2 + 4 * f), g2 = plane(3 + 4 * f), g3 = plane(4 + 4 * f), g4 = plane(5 + 4 * f);
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                P[f][i] = slr::wrapped_strict_tab(slr::byte_of(g1, i), slr::byte_of(g2, i), slr::byte_of(g3, i), slr::byte_of(g4, i), s_ptab,
-                                             s_mtab, ok[i]);
+            for (int i = 0; i < PX; i++)
+                P[f][i] = slr::wrapped_strict_fx((int)slr::byte_of(g4, i) - (int)slr::byte_of(g2, i),
+                                                 (int)slr::byte_of(g1, i) - (int)slr::byte_of(g3, i), s_ptab, s_btab);
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) ph[i] = slr::heterodyne_strict_d(P[0][i], P[1][i], P[2][i]);
+        for (int i = 0; i < PX; i++) ph[i] = slr::heterodyne_strict_fx(P[0][i], P[1][i], P[2][i], ok[i]);
     } else if (p.F == 3 && p.S == 4) {
         // the reference's 3 frequencies x 4 steps, fully unrolled (same arithmetic as the generic branch below)
-        float l[3][4];
+        float l[3][PX];
 #pragma unroll
         for (int f = 0; f < 3; f++) {
-            const uint32_t g1 = base[(2 + 4 * f) * wstride], g2 = base[(3 + 4 * f) * wstride];
-            const uint32_t g3 = base[(4 + 4 * f) * wstride], g4 = base[(5 + 4 * f) * wstride];
+            const uint32_t g1 = plane(2 + 4 * f), g2 = plane(3 + 4 * f), g3 = plane(4 + 4 * f), g4 = plane(5 + 4 * f);
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
+            for (int i = 0; i < PX; i++) {
                 const int a = (int)slr::byte_of(g4, i) - (int)slr::byte_of(g2, i);
                 const int b = (int)slr::byte_of(g1, i) - (int)slr::byte_of(g3, i);
                 ok[i] = ok[i] && ((a | b) != 0);
-                float ang = atan2f((float)a, (float)b);
-                if (ang < 0.0f) ang = __fadd_rn(ang, SLR_TWO_PI_F);
-                l[f][i] = ang;
+                l[f][i] = slr::atan2_pos((float)a, (float)b);
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < PX; i++) {
             const float d01 = slr::wrap_2pi(__fsub_rn(l[0][i], l[1][i]));
             const float d12 = slr::wrap_2pi(__fsub_rn(l[1][i], l[2][i]));
             const float d = slr::wrap_2pi(__fsub_rn(d01, d12));
-            ph[i] = __fmul_rn(__fdiv_rn(d, SLR_TWO_PI_F), 255.0f);
+            ph[i] = slr::phase_scale_corrected(d);
         }
     } else {
-        float lvl[8][4];
+        float lvl[8][PX];
         const int F = p.F, S = p.S;
         for (int f = 0; f < F; f++) {
-            float num[4] = {0, 0, 0, 0}, den[4] = {0, 0, 0, 0};
-            int inum[4] = {0, 0, 0, 0}, iden[4] = {0, 0, 0, 0};
-            for (int s = 0; s < S; s++) {
-                const uint32_t v = base[(2 + S * f + s) * wstride];
+            float num[PX], den[PX];
+            int inum[PX], iden[PX];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
+            for (int i = 0; i < PX; i++) num[i] = den[i] = 0.0f, inum[i] = iden[i] = 0;
+            for (int s = 0; s < S; s++) {
+                const uint32_t v = plane(2 + S * f + s);
+#pragma unroll
+                for (int i = 0; i < PX; i++) {
                     const int g = (int)slr::byte_of(v, i);
                     if (S == 4) {
                         inum[i] += (s == 3) ? g : (s == 1) ? -g : 0;
@@ -155,7 +185,7 @@ __device__ __forceinline__ void decode_chunk(const uint8_t *__restrict__ rows, i
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
+            for (int i = 0; i < PX; i++) {
                 float nn = num[i], dd = den[i];
                 if (S == 4) {
                     nn = (float)inum[i];
@@ -164,95 +194,215 @@ __device__ __forceinline__ void decode_chunk(const uint8_t *__restrict__ rows, i
                 } else if (__fadd_rn(__fmul_rn(nn, nn), __fmul_rn(dd, dd)) < 0.25f) {
                     ok[i] = false;
                 }
-                float a = atan2f(nn, dd);
-                if (a < 0.0f) a = __fadd_rn(a, SLR_TWO_PI_F);
-                lvl[f][i] = a;
+                lvl[f][i] = slr::atan2_pos(nn, dd);
             }
         }
         for (int n = F; n > 1; n--)
             for (int j = 0; j + 1 < n; j++)
 #pragma unroll
-                for (int i = 0; i < 4; i++) lvl[j][i] = slr::wrap_2pi(__fsub_rn(lvl[j][i], lvl[j + 1][i]));
+                for (int i = 0; i < PX; i++) lvl[j][i] = slr::wrap_2pi(__fsub_rn(lvl[j][i], lvl[j + 1][i]));
 #pragma unroll
-        for (int i = 0; i < 4; i++) ph[i] = __fmul_rn(__fdiv_rn(lvl[0][i], SLR_TWO_PI_F), 255.0f);
+        for (int i = 0; i < PX; i++) ph[i] = slr::phase_scale_corrected(lvl[0][i]);
     }
 }
 
-// MAXT/MINB: launch bounds.  Rows up to 1280 wide run 320-thread CTAs, two per SM (<= 102 registers);
-// wider rows run up to 512 threads, one CTA per SM.
-template <int MODE, int MAXT, int MINB>
+// phases of PX pixels of the right or left row, from the staged image rows (or the staged phase + mask rows)
+template <int MODE, int PX>
+__device__ __forceinline__ void load_phases(const unsigned char *stage, int W, int N, int x0, bool right,
+                                            const FusedParams &p, const int *s_ptab, const uint32_t *s_btab,
+                                            float (&ph)[PX], bool (&ok)[PX])
+{
+    if (MODE == MODE_PHASE_INPUT) {  // stage = pL f32[W] | pR f32[W] | mL u8[W] | mR u8[W]
+        const float *src = reinterpret_cast<const float *>(stage + (right ? 4 * W : 0)) + x0;
+        const unsigned char *m = stage + (right ? 9 * W : 8 * W) + x0;
+#pragma unroll
+        for (int q = 0; q < PX; q++) {
+            ph[q] = src[q];
+            ok[q] = m[q] != 0 && (!right || ph[q] == ph[q]);  // a NaN on the right never matches
+        }
+    } else {
+        decode_px<MODE, PX>(stage + (right ? (size_t)N * W : 0), W, x0, p, s_ptab, s_btab, ph, ok);
+    }
+}
+
+// Shared-memory tables of one row.
+struct RowTables {
+    uint2 *ent;   // [T]  {x = distinct right phase (float bits), y = smallest right column carrying it}
+    int *head;    // [2T] bucket heads (-1 = empty)
+    int *nxt;     // [2T] node n = entry + T*(0|1)
+    int T, logT;
+};
+
+// value -> min column, deduplicated, for PX right pixels of columns col0 .. col0+PX-1.  The pixels advance in lock
+// step (all first probes, then all claims, then all minima, then all bucket links) so that their shared-memory
+// round trips overlap.  The thread that claims a new value also files it under the bucket(s) its +-0.1 match
+// window touches.
+template <int PX, bool CLAMP>
+__device__ __forceinline__ void insert_right(const RowTables &t, const float (&ph)[PX], const bool (&ok)[PX], int col0)
+{
+    const int T = t.T, HB = 2 * t.T;
+    uint32_t key[PX], h[PX], cur[PX];
+    int mk[PX];
+    bool need[PX], claimed[PX];
+#pragma unroll
+    for (int q = 0; q < PX; q++) {
+        key[q] = __float_as_uint(__fadd_rn(ph[q], 0.0f));  // -0 -> +0
+        h[q] = slot_of(key[q], t.logT);
+        // the same value one column to the left is already filed with a smaller column
+        need[q] = ok[q] && !(q > 0 && ok[q > 0 ? q - 1 : 0] && key[q] == key[q > 0 ? q - 1 : 0]);
+    }
+#pragma unroll
+    for (int q = 0; q < PX; q++) {
+        const uint2 e = need[q] ? t.ent[h[q]] : make_uint2(key[q], 0u);
+        cur[q] = e.x;
+        mk[q] = (int)e.y;
+    }
+#pragma unroll
+    for (int q = 0; q < PX; q++) {
+        claimed[q] = false;
+        if (need[q] && cur[q] == KEY_EMPTY) {
+            cur[q] = atomicCAS(&t.ent[h[q]].x, KEY_EMPTY, key[q]);
+            mk[q] = INT_MAX;
+            claimed[q] = cur[q] == KEY_EMPTY;
+            if (claimed[q]) cur[q] = key[q];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PX; q++) {
+        // collision (need[q] is set here): double hashing, odd stride.  Linear probing's longest run at the 0.6 load
+        // of a row of all-distinct phases is ~75 slots, and one such lane stalls its warp for thousands of cycles.
+        const uint32_t stride = ((key[q] * 0x7FEB352Du) >> 9) | 1u;
+        while (cur[q] != key[q]) {
+            h[q] = (h[q] + stride) & (T - 1);
+            const uint2 n = t.ent[h[q]];
+            cur[q] = n.x;
+            mk[q] = (int)n.y;
+            if (cur[q] == KEY_EMPTY) {
+                cur[q] = atomicCAS(&t.ent[h[q]].x, KEY_EMPTY, key[q]);
+                mk[q] = INT_MAX;
+                claimed[q] = cur[q] == KEY_EMPTY;
+                if (claimed[q]) cur[q] = key[q];
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PX; q++)
+        if (need[q] && col0 + q < mk[q]) atomicMin(reinterpret_cast<int *>(&t.ent[h[q]].y), col0 + q);
+#pragma unroll
+    for (int q = 0; q < PX; q++) {
+        if (claimed[q]) {
+            const float v = __uint_as_float(key[q]);
+            const int lo = window_bucket<CLAMP>(__fsub_rn(v, 0.11f)), hi = window_bucket<CLAMP>(__fadd_rn(v, 0.11f));
+            t.nxt[h[q]] = atomicExch(&t.head[lo & (HB - 1)], (int)h[q]);
+            if (hi != lo) t.nxt[h[q] + T] = atomicExch(&t.head[hi & (HB - 1)], (int)h[q] + T);
+        }
+    }
+}
+
+// smallest right column whose phase matches v (INT_MAX = none): walk the chain of v's bucket
+template <bool CLAMP>
+__device__ __forceinline__ int first_match(const RowTables &t, float v)
+{
+    int best = INT_MAX;
+    int n = t.head[window_bucket<CLAMP>(v) & (2 * t.T - 1)];
+    while (n >= 0) {
+        const uint2 e = t.ent[n & (t.T - 1)];
+        n = t.nxt[n];
+        if (slr::phase_match(v, __uint_as_float(e.x))) best = min(best, (int)e.y);
+    }
+    return best;
+}
+
+// MAXT/MINB: launch bounds.  QPX: left pixels per lane in one query group (group = 32*QPX pixels).
+template <int MODE, int MAXT, int MINB, int QPX>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_fused_mf(const FusedParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr bool CLAMP = MODE == MODE_PHASE_INPUT;
     const int W = p.W, N = p.N, T = p.T;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+
+    // this CTA's contiguous range of rows r = i * batch + b (scan index b fastest, so consecutive rows share the
+    // undistort-map row i)
     const long long rows = (long long)p.batch * p.H;
-    if ((long long)blockIdx.x >= rows) return;
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const long long r_begin = rows * blockIdx.x / gridDim.x, r_end = rows * (blockIdx.x + 1) / gridDim.x;
+    if (r_begin >= r_end) return;
 
     // ---- shared memory carve-up ----
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
-    int *grp_ctr = reinterpret_cast<int *>(smem + 8);               // dynamic query-group counter
-    unsigned char *stage = smem + 16;                               // [2][N][W] u8
+    uint64_t *bar_stage = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *bar_maps = reinterpret_cast<uint64_t *>(smem + 8);
+    int *grp_ctr = reinterpret_cast<int *>(smem + 16);              // dynamic query-group counter
+    unsigned char *stage = smem + 32;                               // [2][N][W] u8
     const size_t stage_bytes = (MODE == MODE_PHASE_INPUT) ? (size_t)10 * W : (size_t)2 * N * W;
-    // [T] entries {x = distinct right phase (float bits), y = smallest right column carrying it}
-    uint2 *ent = reinterpret_cast<uint2 *>(stage + stage_bytes);
-    int *head = reinterpret_cast<int *>(ent + T);                   // [HB = 2T] bucket heads
-    const int HB = 2 * T;
-    int *nxt = head + HB;                                           // [2T]  node n = entry + T*(0|1)
-    float *s_pl = reinterpret_cast<float *>(nxt + 2 * T);           // [W]   left phases (NaN = none)
-    double *s_ptab = reinterpret_cast<double *>(s_pl + W);          // [2048] (strict)
-    uint32_t *s_mtab = reinterpret_cast<uint32_t *>(s_ptab + 2048); // [256]  (strict)
+    RowTables tab;
+    tab.T = T;
+    tab.logT = p.logT;
+    tab.ent = reinterpret_cast<uint2 *>(stage + stage_bytes);
+    tab.head = reinterpret_cast<int *>(tab.ent + T);
+    tab.nxt = tab.head + 2 * T;
+    float *s_pl = reinterpret_cast<float *>(tab.nxt + 2 * T);       // [W]   left phases (NaN = none)
+    float *s_lx = s_pl + W, *s_ly = s_lx + W, *s_rx = s_ly + W;     // [W]   undistort-map rows of image row i
+    int *s_ptab = reinterpret_cast<int *>(s_rx + W);                // [SLR_PTAB_SIZE] (strict)
+    uint32_t *s_btab = reinterpret_cast<uint32_t *>(s_ptab + SLR_PTAB_SIZE);  // [SLR_BTAB_SIZE] (strict)
 
     if (MODE == SLR_MODE_STRICT) {
-        for (int i = tid; i < 2048; i += nthr) s_ptab[i] = p.ptab[i];
-        for (int i = tid; i < 256; i += nthr) s_mtab[i] = p.mtab[i];
+        for (int k = tid; k < SLR_PTAB_SIZE; k += nthr) s_ptab[k] = p.ptab[k];
+        for (int k = tid; k < SLR_BTAB_SIZE; k += nthr) s_btab[k] = p.btab[k];
     }
     uint64_t policy = 0;
     if (tid == 0) {
-        slr::mbar_init(bar, 1);
+        slr::mbar_init(bar_stage, 1);
+        slr::mbar_init(bar_maps, 1);
         slr::mbar_fence_init();
         policy = make_evict_first_policy();
     }
     __syncthreads();
 
-    // row-index-major visiting order: r -> (i = r / batch, b = r % batch)
-    auto issue_row = [&](unsigned r) {
-        const int i = (int)(r / (unsigned)p.batch);
-        const int b = (int)(r - (unsigned)i * (unsigned)p.batch);
-        slr::mbar_expect_tx(bar, (uint32_t)stage_bytes);
+    auto issue_row = [&](int i, int b) {
+        slr::mbar_expect_tx(bar_stage, (uint32_t)stage_bytes);
         if (MODE == MODE_PHASE_INPUT) {  // stage = pL f32[W] | pR f32[W] | mL u8[W] | mR u8[W]
             const size_t offL = ((size_t)(b * 2 + 0) * p.H + i) * W, offR = ((size_t)(b * 2 + 1) * p.H + i) * W;
-            tma_load_1d_hint(stage, p.phase + offL, 4u * W, bar, policy);
-            tma_load_1d_hint(stage + 4 * W, p.phase + offR, 4u * W, bar, policy);
-            tma_load_1d_hint(stage + 8 * W, p.mask + offL, (uint32_t)W, bar, policy);
-            tma_load_1d_hint(stage + 9 * W, p.mask + offR, (uint32_t)W, bar, policy);
+            tma_load_1d_hint(stage, p.phase + offL, 4u * W, bar_stage, policy);
+            tma_load_1d_hint(stage + 4 * W, p.phase + offR, 4u * W, bar_stage, policy);
+            tma_load_1d_hint(stage + 8 * W, p.mask + offL, (uint32_t)W, bar_stage, policy);
+            tma_load_1d_hint(stage + 9 * W, p.mask + offR, (uint32_t)W, bar_stage, policy);
             return;
         }
         const uint8_t *src = p.stack + ((size_t)b * 2 * N * p.H + i) * W;
         for (int v = 0; v < 2 * N; v++)   // plane v of this scan (cam-major, then image index)
-            tma_load_1d_hint(stage + (size_t)v * W, src + (size_t)v * p.H * W, (uint32_t)W, bar, policy);
+            tma_load_1d_hint(stage + (size_t)v * W, src + (size_t)v * p.H * W, (uint32_t)W, bar_stage, policy);
     };
-    if (tid == 0) issue_row(blockIdx.x);
-    // CTAs that share an SM would otherwise march in lock step (identical rows): the ALU-bound decode phases and
-    // the shared-memory-bound match phases of both would coincide.  Delay the second wave by part of a row.
-    if (p.stagger_ns > 0 && blockIdx.x >= (unsigned)p.num_sms) {
-        for (int w = 0; w < p.stagger_ns; w += 500) __nanosleep(500);
-    }
+    auto issue_maps = [&](int i) {  // L2-resident (15 MB for all rows), default policy
+        slr::mbar_expect_tx(bar_maps, 12u * W);
+        slr::tma_load_1d(s_lx, p.lx + (size_t)i * W, 4u * W, bar_maps);
+        slr::tma_load_1d(s_ly, p.ly + (size_t)i * W, 4u * W, bar_maps);
+        slr::tma_load_1d(s_rx, p.rx + (size_t)i * W, 4u * W, bar_maps);
+    };
 
-    const int nchunks = W >> 2;
-    const int ngroups = (W + 63) >> 6;
-    const int lane = tid & 31;
+    int i = (int)(r_begin / p.batch), b = (int)(r_begin - (long long)i * p.batch);
+    size_t orow = ((size_t)b * p.H + i) * W;            // first output pixel of row (b, i)
+    const size_t scan_px = (size_t)p.H * W;
+    if (tid == 0) {
+        issue_row(i, b);
+        issue_maps(i);
+    }
+    bool maps_pending = true;
+    uint32_t maps_parity = 0;
+
+    const int ntasks = W >> 1;                          // 4-pixel chunks, right and left interleaved
+    const int full_tasks = (ntasks / nthr) * nthr;      // done in full rounds; the rest goes pixel by pixel
+    const int rem_x0 = 2 * full_tasks;                  // first column left over (per camera)
+    const int rem_px = W - rem_x0, rem_pad = (rem_px + 15) & ~15;
+    constexpr int GPX = 32 * QPX;
+    const int ngroups = (W + GPX - 1) / GPX;
     unsigned n_local = 0;
     int it = 0;
-    for (unsigned r = blockIdx.x; r < (unsigned)rows; r += gridDim.x, ++it) {
-        const int i = (int)(r / (unsigned)p.batch);
-        const int b = (int)(r - (unsigned)i * (unsigned)p.batch);
-
+    for (long long r = r_begin; r < r_end; ++r, ++it) {
         // ---- clear the tables while the stage fills: keys = EMPTY, mink = INT_MAX, heads = -1 ----
         {
-            uint4 *e4p = reinterpret_cast<uint4 *>(ent);   // two entries per vector
-            uint4 *h4 = reinterpret_cast<uint4 *>(head);
+            uint4 *e4p = reinterpret_cast<uint4 *>(tab.ent);   // two entries per vector
+            uint4 *h4 = reinterpret_cast<uint4 *>(tab.head);
             const uint4 e4 = make_uint4(KEY_EMPTY, 0x7fffffffu, KEY_EMPTY, 0x7fffffffu);
             const uint4 m4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
             for (int t = tid; t < (T >> 1); t += nthr) {
@@ -261,76 +411,68 @@ k_fused_mf(const FusedParams p)
             }
             if (tid == 0) *grp_ctr = 0;
         }
-        slr::mbar_wait(bar, it & 1);
+        SLR_STAMP(0);
+#ifdef SLR_PHASE_CLOCKS
+        if (tid == 0 && it == DBG_SKIP) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            p.dbg[(((size_t)blockIdx.x * DBG_ROWS) * 16) * DBG_PTS + 6] = smid;
+        }
+#endif
+        slr::mbar_wait(bar_stage, it & 1);
         __syncthreads();  // tables cleared, stage landed
+        SLR_STAMP(1);
 
-        // ---- decode: tasks [0, nchunks) = right 4-pixel chunks, [nchunks, 2 nchunks) = left chunks ----
-        for (int task = tid; task < 2 * nchunks; task += nthr) {
+        // ---- decode: 4-pixel chunks, right and left chunk of the same columns on neighbouring lanes.  The right
+        //      lane hands its upper two phases to the left lane, so every lane decodes 4 pixels and files 2 right
+        //      pixels in the tables: all lanes, hence all warps, carry the same load ----
+        for (int task = tid; task < full_tasks; task += nthr) {
             float ph[4];
             bool ok[4];
-            if (task < nchunks) {
-                const int c = task;
-                if (MODE == MODE_PHASE_INPUT) {
-                    const float4 v = reinterpret_cast<const float4 *>(stage + 4 * W)[c];
-                    const uint32_t m = reinterpret_cast<const uint32_t *>(stage + 9 * W)[c];
-                    ph[0] = v.x, ph[1] = v.y, ph[2] = v.z, ph[3] = v.w;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) ok[q] = slr::byte_of(m, q) != 0 && ph[q] == ph[q];  // NaN never matches
-                } else {
-                    decode_chunk<MODE>(stage + (size_t)N * W, W, c, p, s_ptab, s_mtab, ph, ok);
-                }
-                // value -> min column, deduplicated.  The four pixels' first probes are issued back to back
-                // (independent atomics in flight); the thread that claims a new value also files it under the
-                // bucket(s) its +-0.1 match window touches.
-                uint32_t key[4], h[4], old[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    key[q] = __float_as_uint(__fadd_rn(ph[q], 0.0f));  // -0 -> +0
-                    h[q] = (key[q] * 2654435761u) >> (32 - p.logT);
-                    old[q] = ok[q] ? atomicCAS(&ent[h[q]].x, KEY_EMPTY, key[q]) : key[q];
-                }
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    while (old[q] != KEY_EMPTY && old[q] != key[q]) {  // collision: linear probing
-                        h[q] = (h[q] + 1) & (T - 1);
-                        old[q] = atomicCAS(&ent[h[q]].x, KEY_EMPTY, key[q]);
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (ok[q]) atomicMin(reinterpret_cast<int *>(&ent[h[q]].y), 4 * c + q);
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if (ok[q] && old[q] == KEY_EMPTY) {
-                        const float v = __uint_as_float(key[q]);
-                        const int lo = window_bucket(__fsub_rn(v, 0.11f)), hi = window_bucket(__fadd_rn(v, 0.11f));
-                        nxt[h[q]] = atomicExch(&head[lo & (HB - 1)], (int)h[q]);
-                        if (hi != lo) nxt[h[q] + T] = atomicExch(&head[hi & (HB - 1)], (int)h[q] + T);
-                    }
-                }
-            } else {
-                const int c = task - nchunks;
-                if (MODE == MODE_PHASE_INPUT) {
-                    const float4 v = reinterpret_cast<const float4 *>(stage)[c];
-                    const uint32_t m = reinterpret_cast<const uint32_t *>(stage + 8 * W)[c];
-                    ph[0] = v.x, ph[1] = v.y, ph[2] = v.z, ph[3] = v.w;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) ok[q] = slr::byte_of(m, q) != 0;
-                } else {
-                    decode_chunk<MODE>(stage, W, c, p, s_ptab, s_mtab, ph, ok);
-                }
-                reinterpret_cast<float4 *>(s_pl)[c] = make_float4(ok[0] ? ph[0] : slr::qnan(), ok[1] ? ph[1] : slr::qnan(),
-                                                                  ok[2] ? ph[2] : slr::qnan(), ok[3] ? ph[3] : slr::qnan());
-            }
+            const int x0 = 4 * (task >> 1);
+            const bool right = (task & 1) == 0;
+            load_phases<MODE, 4>(stage, W, N, x0, right, p, s_ptab, s_btab, ph, ok);
+            const float n2 = __shfl_xor_sync(0xffffffffu, ph[2], 1), n3 = __shfl_xor_sync(0xffffffffu, ph[3], 1);
+            const unsigned okb = __shfl_xor_sync(0xffffffffu, (ok[2] ? 1u : 0u) | (ok[3] ? 2u : 0u), 1);
+            float ip[2] = {right ? ph[0] : n2, right ? ph[1] : n3};
+            bool io[2] = {right ? ok[0] : (okb & 1u) != 0, right ? ok[1] : (okb & 2u) != 0};
+            insert_right<2, CLAMP>(tab, ip, io, right ? x0 : x0 + 2);
+            if (!right)
+                reinterpret_cast<float4 *>(s_pl)[x0 >> 2] = make_float4(ok[0] ? ph[0] : slr::qnan(), ok[1] ? ph[1] : slr::qnan(),
+                                                                        ok[2] ? ph[2] : slr::qnan(), ok[3] ? ph[3] : slr::qnan());
         }
+        // ---- the remaining columns one pixel per thread: lanes 0-15 of a warp take right pixels, lanes 16-31 the
+        //      left pixels of the same columns ----
+        for (int s = tid; s < 2 * rem_pad; s += nthr) {
+            float ph[1];
+            bool ok[1];
+            const bool right = (s & 16) == 0;
+            const int xi = ((s >> 5) << 4) | (s & 15);
+            const bool live = xi < rem_px;
+            const int x = rem_x0 + (live ? xi : 0);
+            load_phases<MODE, 1>(stage, W, N, x, right, p, s_ptab, s_btab, ph, ok);
+            ok[0] = ok[0] && live;
+            if (right)
+                insert_right<1, CLAMP>(tab, ph, ok, x);
+            else if (live)
+                s_pl[x] = ok[0] ? ph[0] : slr::qnan();
+        }
+        SLR_STAMP(2);
         __syncthreads();  // stage consumed, table + chains + left phases complete
+        SLR_STAMP(3);
 
-        if (tid == 0 && r + gridDim.x < (unsigned)rows) issue_row(r + gridDim.x);  // prefetch the next row
+        // next row of this CTA; its image rows stream in while this row is matched
+        int ni = i, nb = b + 1;
+        if (nb == p.batch) nb = 0, ni = i + 1;
+        const bool more = r + 1 < r_end;
+        if (tid == 0 && more) issue_row(ni, nb);
+        if (maps_pending) {
+            slr::mbar_wait(bar_maps, maps_parity);
+            maps_parity ^= 1u;
+            maps_pending = false;
+        }
 
-        // ---- query + emit: warps take 64-pixel groups dynamically (chain lengths vary along the row);
-        //      each lane owns two pixels of the group ----
-        const float *lx_row = p.lx + (size_t)i * W, *ly_row = p.ly + (size_t)i * W, *rx_row = p.rx + (size_t)i * W;
-        const size_t orow = ((size_t)b * p.H + i) * W;
+        // ---- query + emit: warps take pixel groups dynamically (chain lengths vary along the row) ----
         float *xyz_row = p.xyz + orow * 3;
         uint8_t *valid_row = p.valid + orow;
         int32_t *k_row = p.match_k ? p.match_k + orow : nullptr;
@@ -339,100 +481,102 @@ k_fused_mf(const FusedParams p)
             if (lane == 0) g = atomicAdd(grp_ctr, 1);
             g = __shfl_sync(0xffffffffu, g, 0);
             if (g >= ngroups) break;
-            const int j0 = (g << 6) + lane, j1 = j0 + 32;
-            const float v0 = (j0 < W) ? s_pl[j0] : slr::qnan();
-            const float v1 = (j1 < W) ? s_pl[j1] : slr::qnan();
-            // the undistort-map values of both pixels are requested now so that their L2 latency overlaps the walk
-            const float ulx0 = (v0 == v0) ? __ldg(lx_row + j0) : 0.0f, uly0 = (v0 == v0) ? __ldg(ly_row + j0) : 0.0f;
-            const float ulx1 = (v1 == v1) ? __ldg(lx_row + j1) : 0.0f, uly1 = (v1 == v1) ? __ldg(ly_row + j1) : 0.0f;
-            int best0 = INT_MAX, best1 = INT_MAX;
-            if (v0 == v0) {
-                int t = head[window_bucket(v0) & (HB - 1)];
-                while (t >= 0) {
-                    const uint2 e = ent[t & (T - 1)];
-                    t = nxt[t];
-                    if (slr::phase_match(v0, __uint_as_float(e.x))) best0 = min(best0, (int)e.y);
+            int j[QPX], best[QPX];
+            float v[QPX];
+#pragma unroll
+            for (int u = 0; u < QPX; u++) {
+                j[u] = g * GPX + 32 * u + lane;
+                v[u] = (j[u] < W) ? s_pl[j[u]] : slr::qnan();
+            }
+#pragma unroll
+            for (int u = 0; u < QPX; u++) best[u] = (v[u] == v[u]) ? first_match<CLAMP>(tab, v[u]) : INT_MAX;
+            // every pixel is reprojected unconditionally (dummy inputs where there is no match) so that independent
+            // fp64 chains interleave; misses are turned into NaN afterwards
+            float X[QPX], Y[QPX], Z[QPX];
+#pragma unroll
+            for (int u = 0; u < QPX; u++) {
+                const bool hit = best[u] != INT_MAX;
+                const float ulx = hit ? s_lx[j[u]] : 0.0f, uly = hit ? s_ly[j[u]] : 0.0f, urx = hit ? s_rx[best[u]] : 0.0f;
+                slr::reproject_q(p.calib, (double)ulx, (double)uly, (double)__fsub_rn(ulx, urx), X[u], Y[u], Z[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < QPX; u++) {
+                const bool hit = best[u] != INT_MAX;
+                n_local += hit ? 1u : 0u;
+                if (j[u] < W) {
+                    float *dst = xyz_row + 3 * j[u];
+                    dst[0] = hit ? X[u] : slr::qnan();
+                    dst[1] = hit ? Y[u] : slr::qnan();
+                    dst[2] = hit ? Z[u] : slr::qnan();
+                    valid_row[j[u]] = hit ? 1 : 0;
+                    if (k_row) k_row[j[u]] = hit ? best[u] : -1;
                 }
-            }
-            if (v1 == v1) {
-                int t = head[window_bucket(v1) & (HB - 1)];
-                while (t >= 0) {
-                    const uint2 e = ent[t & (T - 1)];
-                    t = nxt[t];
-                    if (slr::phase_match(v1, __uint_as_float(e.x))) best1 = min(best1, (int)e.y);
-                }
-            }
-            // both pixels are reprojected unconditionally (dummy inputs where there is no match) so that the two
-            // independent fp64 chains interleave; misses are turned into NaN afterwards
-            const bool hit0 = (best0 != INT_MAX), hit1 = (best1 != INT_MAX);
-            const float urx0 = hit0 ? __ldg(rx_row + best0) : 0.0f, urx1 = hit1 ? __ldg(rx_row + best1) : 0.0f;
-            float X0, Y0, Z0, X1, Y1, Z1;
-            slr::reproject_q(p.calib, (double)ulx0, (double)uly0, (double)__fsub_rn(ulx0, urx0), X0, Y0, Z0);
-            slr::reproject_q(p.calib, (double)ulx1, (double)uly1, (double)__fsub_rn(ulx1, urx1), X1, Y1, Z1);
-            n_local += (hit0 ? 1u : 0u) + (hit1 ? 1u : 0u);
-            if (j0 < W) {
-                float *dst = xyz_row + 3 * j0;
-                dst[0] = hit0 ? X0 : slr::qnan();
-                dst[1] = hit0 ? Y0 : slr::qnan();
-                dst[2] = hit0 ? Z0 : slr::qnan();
-                valid_row[j0] = hit0 ? 1 : 0;
-                if (k_row) k_row[j0] = hit0 ? best0 : -1;
-            }
-            if (j1 < W) {
-                float *dst = xyz_row + 3 * j1;
-                dst[0] = hit1 ? X1 : slr::qnan();
-                dst[1] = hit1 ? Y1 : slr::qnan();
-                dst[2] = hit1 ? Z1 : slr::qnan();
-                valid_row[j1] = hit1 ? 1 : 0;
-                if (k_row) k_row[j1] = hit1 ? best1 : -1;
             }
         }
         // the next iteration clears the tables: every warp must be done probing them
+        SLR_STAMP(4);
         __syncthreads();
+        SLR_STAMP(5);
+        if (more && ni != i) {  // nobody reads the old map rows any more
+            if (tid == 0) issue_maps(ni);
+            maps_pending = true;
+        }
+        orow = (ni == i) ? orow + scan_px : orow - (size_t)(p.batch - 1) * scan_px + W;
+        i = ni;
+        b = nb;
     }
     if (p.n_points) {
         const unsigned long long s = slr::warp_sum_u32(n_local);
-        if ((tid & 31) == 0 && s) atomicAdd(p.n_points, s);
+        if (lane == 0 && s) atomicAdd(p.n_points, s);
     }
 }
 
 }  // namespace
 
-// strict-mode tables, built once per engine on the host with the host libm:
-//   ptab[cs*512 + 256 + q]  (double holding the reference's float wrapped phase)
-//      cs = 0: b > 0, a <= 0   atan(float(q))            (Duke/mfreconstruct.cpp:261, and :246 via q = 0)
-//      cs = 1: b < 0           atan(float(q)) + PI       (:257, and :248 via q = 0)
-//      cs = 2: b > 0, a > 0    atan(float(q)) + 2*PI     (:259)
-//      cs = 3: b == 0          256 + a: PI/2 (a < 0, :252), 3*PI/2 (a > 0, :250)
-//   mtab[ub] = floor(65536/ub) + 1  (mtab[0] = 65536)
+// strict-mode tables (layout: slr_device.cuh), built once per engine on the host with the host libm
 slr_status slr_build_strict_tables(slr_engine *e)
 {
-    static double ptab[2048];
-    static uint32_t mtab[256];
+    static int32_t ptab[SLR_PTAB_SIZE];
+    static uint32_t btab[SLR_BTAB_SIZE];
     const float PI = SLR_PI_DEC;
-    for (int i = 0; i < 2048; i++) ptab[i] = 0.0;
-    for (int q = -255; q <= 255; q++) {
-        const float at = atanf((float)q);
-        ptab[0 * 512 + 256 + q] = (double)at;
-        ptab[1 * 512 + 256 + q] = (double)(at + PI);
-        ptab[2 * 512 + 256 + q] = (double)(at + 2.0f * PI);
+    bool exact = true;
+    auto fx = [&](float v) -> int32_t {  // v in units of 2^-24; exact for every value the reference can produce
+        const double s = (double)v * 16777216.0;
+        const int32_t r = (int32_t)s;
+        if ((double)r != s) exact = false;
+        return r;
+    };
+    for (int q = 0; q <= 255; q++) {
+        const float atp = atanf((float)q), atn = atanf((float)(-q));
+        ptab[0 * 256 + q] = fx(atn);                       // b > 0, a <= 0 (:261 / :246)
+        ptab[1 * 256 + q] = fx(atp + 2 * PI);              // b > 0, a > 0  (:259)
+        ptab[2 * 256 + q] = fx(atp + PI);                  // b < 0, a <= 0 (:257 / :248)
+        ptab[3 * 256 + q] = fx(atn + PI);                  // b < 0, a > 0  (:257)
+        ptab[4 * 256 + q] = fx(PI / 2);                    // b == 0, a < 0 (:252)
+        ptab[5 * 256 + q] = fx(3 * PI / 2);                // b == 0, a > 0 (:250)
     }
-    for (int q = 1; q <= 255; q++) {
-        ptab[1536 + 256 + q] = (double)(3.0f * PI / 2.0f);   // b == 0, a > 0 (:250)
-        ptab[1536 + 256 - q] = (double)(PI / 2.0f);          // b == 0, a < 0 (:252)
+    ptab[4 * 256 + 0] = SLR_PTAB_DEGENERATE;               // a == 0 and b == 0 (:254)
+    if (!exact) {
+        slr_set_error("strict tables: a wrapped phase is not a multiple of 2^-24 (host libm atanf out of spec?)");
+        return SLR_ERR_INVALID;
     }
-    mtab[0] = 65536u;   // b == 0: the "quotient" is |a| itself (selects within row 3)
-    for (int ub = 1; ub < 256; ub++) mtab[ub] = 65536u / (uint32_t)ub + 1u;
+    for (int b = -255; b <= 255; b++) {
+        const uint32_t ub = (uint32_t)abs(b);
+        const uint32_t M = ub ? 65536u / ub + 1u : 65536u;  // b == 0: q = |a| selects within rows 4/5
+        const uint32_t row = (b > 0) ? 0u : (b < 0) ? 2u : 4u;
+        btab[b + 256] = M | ((row * 256u) << 17);
+    }
+    btab[0] = 0;
     if (!e->d_ptab) SLR_CHECK_CUDA(cudaMalloc(&e->d_ptab, sizeof(ptab)));
-    if (!e->d_mtab) SLR_CHECK_CUDA(cudaMalloc(&e->d_mtab, sizeof(mtab)));
+    if (!e->d_btab) SLR_CHECK_CUDA(cudaMalloc(&e->d_btab, sizeof(btab)));
     SLR_CHECK_CUDA(cudaMemcpy(e->d_ptab, ptab, sizeof(ptab), cudaMemcpyHostToDevice));
-    SLR_CHECK_CUDA(cudaMemcpy(e->d_mtab, mtab, sizeof(mtab), cudaMemcpyHostToDevice));
+    SLR_CHECK_CUDA(cudaMemcpy(e->d_btab, btab, sizeof(btab), cudaMemcpyHostToDevice));
     return SLR_OK;
 }
 
 static size_t fused_smem_bytes(size_t stage_bytes, int W, int T)
 {
-    return 16 + stage_bytes + (size_t)24 * T + (size_t)4 * W + 2048 * 8 + 256 * 4;
+    return 32 + stage_bytes + (size_t)24 * T + (size_t)16 * W + SLR_PTAB_SIZE * 4 + SLR_BTAB_SIZE * 4;
 }
 
 // shared launcher: mode = SLR_MODE_STRICT | SLR_MODE_CORRECTED (image stacks) or MODE_PHASE_INPUT (phase + mask rows)
@@ -446,24 +590,24 @@ static slr_status launch_fused(slr_engine *e, int mode, const uint8_t *d_stack, 
     while (T < W || (double)W / T > 0.7) T <<= 1, logT++;
     const size_t stage_bytes = (mode == MODE_PHASE_INPUT) ? (size_t)10 * W : (size_t)2 * N * W;
     const size_t smem = fused_smem_bytes(stage_bytes, W, T);
-    const int nchunks = W / 4;
     const bool aligned = ((uintptr_t)d_stack | (uintptr_t)d_phase | (uintptr_t)d_mask | (uintptr_t)d_xyz |
                           (uintptr_t)d_valid | (uintptr_t)d_match_k) % 16 == 0;
     if (W % 16 != 0 || smem > 227 * 1024 || !aligned || batch > 65535 || (long long)batch * e->H >= (1LL << 31))
         return SLR_OK;  // not handled: the caller falls back to the un-fused kernels
     *handled = true;
 
-    // decode tasks per row = 2*nchunks; a little more than one even share per round measured best (the extra
-    // warps help the shared-memory-latency-bound match phase): 1280-wide rows -> 384 threads, two CTAs per SM
-    const int tasks = 2 * nchunks;
-    const int rounds = (tasks + FUSED_MAX_THREADS - 1) / FUSED_MAX_THREADS;
-    int threads = ((tasks + rounds - 1) / rounds + 31) / 32 * 32 + 64;
+    // 512 threads, two CTAs per SM (64 registers) when two row contexts fit in shared memory: 32 warps per SM hide
+    // the shared-memory and fp64 latencies of the match phase; narrow rows get one thread per 4-pixel chunk.
+    const bool two = 2 * (smem + 1024) <= 228 * 1024;
+    int threads = (W / 2 + 31) / 32 * 32;   // one 4-pixel decode task per thread, or the widest CTA
     if (threads > FUSED_MAX_THREADS) threads = FUSED_MAX_THREADS;
     if (threads < 64) threads = 64;
     if (const char *ev = getenv("SLR_FUSED_THREADS")) {  // tuning knob (bench experiments)
         const int t = atoi(ev);
         if (t >= 64 && t <= FUSED_MAX_THREADS && t % 32 == 0) threads = t;
     }
+    int qpx = (W + 63) / 64 >= 3 * (threads / 32) ? 2 : 1;  // 64-pixel groups only when every warp still gets >= 3
+    if (const char *ev = getenv("SLR_FUSED_QPX")) qpx = atoi(ev) == 2 ? 2 : 1;
     FusedParams p;
     p.stack = d_stack;
     p.phase = d_phase;
@@ -477,14 +621,11 @@ static slr_status launch_fused(slr_engine *e, int mode, const uint8_t *d_stack, 
     p.T = T;
     p.logT = logT;
     p.black_thr = black_thr;
-    p.num_sms = e->num_sms;
-    p.stagger_ns = 0;
-    if (const char *ev = getenv("SLR_FUSED_STAGGER_NS")) p.stagger_ns = atoi(ev);
     p.lx = e->d_undist_lx;
     p.ly = e->d_undist_ly;
     p.rx = e->d_undist_rx;
     p.ptab = e->d_ptab;
-    p.mtab = e->d_mtab;
+    p.btab = e->d_btab;
     for (int s = 0; s < 16; s++) {
         p.cs[s] = (s < S) ? (float)cos(2.0 * 3.14159265358979323846 * s / S) : 0.0f;
         p.sn[s] = (s < S) ? (float)sin(2.0 * 3.14159265358979323846 * s / S) : 0.0f;
@@ -496,23 +637,25 @@ static slr_status launch_fused(slr_engine *e, int mode, const uint8_t *d_stack, 
     p.calib = e->calib;
 
     void (*kern)(const FusedParams);
-    const bool two = 2 * smem + 4096 <= 227 * 1024;
-#define SLR_PICK(MAXT, MINB)                                                                                      \
-    kern = (mode == SLR_MODE_STRICT)      ? k_fused_mf<SLR_MODE_STRICT, MAXT, MINB>                                 \
-           : (mode == SLR_MODE_CORRECTED) ? k_fused_mf<SLR_MODE_CORRECTED, MAXT, MINB>                              \
-                                          : k_fused_mf<MODE_PHASE_INPUT, MAXT, MINB>
-    if (threads <= 320) {
-        SLR_PICK(320, 2);
-    } else if (threads <= 384) {
-        SLR_PICK(384, 2);
-    } else if (threads <= 448 && two) {
-        SLR_PICK(448, 2);
+#define SLR_PICK_Q(MAXT, MINB, Q)                                                                                 \
+    kern = (mode == SLR_MODE_STRICT)      ? k_fused_mf<SLR_MODE_STRICT, MAXT, MINB, Q>                           \
+           : (mode == SLR_MODE_CORRECTED) ? k_fused_mf<SLR_MODE_CORRECTED, MAXT, MINB, Q>                        \
+                                          : k_fused_mf<MODE_PHASE_INPUT, MAXT, MINB, Q>
+#define SLR_PICK(MAXT, MINB)          \
+    if (qpx == 2) {                   \
+        SLR_PICK_Q(MAXT, MINB, 2);    \
+    } else {                          \
+        SLR_PICK_Q(MAXT, MINB, 1);    \
+    }
+    if (threads <= 384 && two) {
+        SLR_PICK(384, 2)
     } else if (two) {
-        SLR_PICK(512, 2);
+        SLR_PICK(512, 2)
     } else {
-        SLR_PICK(FUSED_MAX_THREADS, 1);
+        SLR_PICK(FUSED_MAX_THREADS, 1)
     }
 #undef SLR_PICK
+#undef SLR_PICK_Q
     SLR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     SLR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
@@ -521,8 +664,28 @@ static slr_status launch_fused(slr_engine *e, int mode, const uint8_t *d_stack, 
     const long long rows = (long long)batch * e->H;
     if (grid > rows) grid = rows;
     if (grid < 1) return SLR_OK;
+#ifdef SLR_PHASE_CLOCKS
+    const size_t dbg_n = (size_t)grid * DBG_ROWS * 16 * DBG_PTS;
+    SLR_CHECK_CUDA(cudaMalloc(&p.dbg, dbg_n * sizeof(long long)));
+    SLR_CHECK_CUDA(cudaMemsetAsync(p.dbg, 0, dbg_n * sizeof(long long), e->stream));
+#endif
     kern<<<(unsigned)grid, threads, smem, e->stream>>>(p);
     SLR_CHECK_LAUNCH(e);
+#ifdef SLR_PHASE_CLOCKS
+    if (const char *path = getenv("SLR_PHASE_CLOCKS_OUT")) {
+        long long *h = (long long *)malloc(dbg_n * sizeof(long long));
+        SLR_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+        SLR_CHECK_CUDA(cudaMemcpy(h, p.dbg, dbg_n * sizeof(long long), cudaMemcpyDeviceToHost));
+        if (FILE *f = fopen(path, "wb")) {
+            int hdr[4] = {(int)grid, DBG_ROWS, 16, DBG_PTS};
+            fwrite(hdr, sizeof(hdr), 1, f);
+            fwrite(h, sizeof(long long), dbg_n, f);
+            fclose(f);
+        }
+        free(h);
+    }
+    cudaFree(p.dbg);
+#endif
     return SLR_OK;
 }
 

@@ -9,6 +9,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 
 #include "slr_internal.h"
@@ -181,52 +182,65 @@ __device__ __forceinline__ bool phase_strict(const int (&G)[12], const float *__
 }
 
 // ------------------------------------------------------------------------------------------------
-// strict mode, table-driven form used by the kernels (tables built by slr_build_strict_tables, k_fused.cu)
+// strict mode, table-driven integer form used by the kernels (tables built by slr_build_strict_tables, k_fused.cu)
 // ------------------------------------------------------------------------------------------------
 // byte i of a 32-bit word, zero extended: one PRMT
 __device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return __byte_perm(w, 0, 0x4440 + i); }
 
-// ---- strict decode of one pixel from table lookups (Duke/mfreconstruct.cpp:239-268) ----------------
-// Returns the wrapped phase of one frequency as a double holding the reference's float value.
-// ptab rows (512 doubles each, entry 256 + signed quotient):
-//   0: b > 0, a <= 0 -> atan(q)          1: b < 0 -> atan(q) + PI        2: b > 0, a > 0 -> atan(q) + 2PI
-//   3: b == 0 -> 3PI/2 (a > 0) / PI/2 (a < 0); mtab[0] = 65536 makes the "quotient" there equal to a.
-__device__ __forceinline__ double wrapped_strict_tab(int G1, int G2, int G3, int G4, const double *ptab,
-                                                     const uint32_t *mtab, bool &ok)
+// Every wrapped phase the reference can produce (Duke/mfreconstruct.cpp:246-261) is one of a few hundred floats in
+// [-1.6, 7.9], each zero or >= 0.78 in magnitude, i.e. an integer multiple of 2^-24.  The tables hold them as
+// int32 in units of 2^-24 ("fixed point", exact), so that the double-precision steps of :265-266 become exact
+// integer arithmetic followed by ONE rounding (I2F), which is what narrowing the exact double to float does.
+//
+//   btab[b + 256], b = G1-G3 in [-255, 255]:  bits 0..16  M = floor(65536/|b|) + 1   (b == 0: 65536)
+//                                             bits 17..   first ptab row of this sign of b, times 256
+//   q = (|a| * M) >> 16 == floor(|a| / |b|) for 0 <= |a|, |b| <= 255 (b == 0: q = |a|): the excess |a|/65536 < 1/256
+//       <= 1/|b| can never reach the next integer because a non-integer quotient has a fractional part <= 1 - 1/|b|.
+//   ptab rows (256 entries, index q; C++ int division truncates toward zero, so the signed quotient is +-q):
+//     0: b > 0, a <= 0   atan(float(-q))            (:261, and :246 via q = 0)
+//     1: b > 0, a >  0   atan(float( q)) + 2*PI     (:259)
+//     2: b < 0, a <= 0   atan(float( q)) + PI       (:257, and :248 via q = 0)
+//     3: b < 0, a >  0   atan(float(-q)) + PI       (:257)
+//     4: b == 0, a <= 0  PI/2 (:252); entry 0 (a == 0: the degenerate branch :254) = SLR_PTAB_DEGENERATE
+//     5: b == 0, a >  0  3*PI/2 (:250)
+#define SLR_PTAB_ROWS 6
+#define SLR_PTAB_SIZE (SLR_PTAB_ROWS * 256)
+#define SLR_BTAB_SIZE 512
+#define SLR_PTAB_DEGENERATE INT_MIN
+
+__device__ __forceinline__ int wrapped_strict_fx(int a, int b, const int *__restrict__ ptab,
+                                                 const uint32_t *__restrict__ btab)
 {
-    const int a = G4 - G2, b = G1 - G3;
-    const int ua = abs(a), ub = abs(b);
-    // floor(ua/ub) for 0 <= ua,ub <= 255 via M = floor(65536/ub)+1: the excess ua/65536 < 1/256 <= 1/ub can never
-    // reach the next integer because a non-integer quotient has a fractional part <= 1 - 1/ub.
-    const int q = (int)(((uint32_t)ua * mtab[ub]) >> 16);
-    const int sg = (a ^ b) >> 31;                       // C++ int division truncates toward zero
-    const int qs = (q ^ sg) - sg;
-    int row = (b < 0) ? 512 : ((a > 0) ? 1024 : 0);
-    row = (ub == 0) ? 1536 : row;                       // :250 / :252
-    ok = ok && ((ua | ub) != 0);                        // :254 degenerate
-    return ptab[row + 256 + qs];
+    const uint32_t t = btab[b + 256];
+    const uint32_t q = ((uint32_t)abs(a) * (t & 0x1FFFFu)) >> 16;
+    return ptab[(t >> 17) + q + ((a > 0) ? 256u : 0u)];
 }
 
-__device__ __forceinline__ float heterodyne_strict_d(double P0, double P1, double P2)
+// Heterodyne of :265-268 on fixed-point wrapped phases.  I0 - I1 (+ 2*PI) is exact in int32 (|I| < 2^27), and
+// (float)D * 2^-24 == float(double result of the reference) because scaling by a power of two commutes with
+// rounding.  P123 and the division stay in fp32 as in the reference, carried in units of 2^-24 throughout (every
+// operation below is exactly the reference's operation on scaled operands; no overflow, no subnormals).
+// P123 / (2*PI), correctly rounded, without the generic division routine: with rc = RN(1/c), q0 = RN(x*rc),
+// rem = x - c*q0 (exact in an FMA), RN(q0 + rem*rc) == RN(x/c).  Verified exhaustively on the host against IEEE
+// division for every float with 2^-100 <= |x| < 32 and x = +0 (scratch/div_check.c).
+__device__ __forceinline__ float heterodyne_strict_fx(int I0, int I1, int I2, bool &ok)
 {
     constexpr float PI_2 = 2.0f * SLR_PI_DEC;
-    constexpr float RPI_2 = 1.0f / PI_2;                // RN(1/(2*PI))
-    const double c = (double)PI_2;
-    double d01 = __dsub_rn(P0, P1);
-    double d12 = __dsub_rn(P1, P2);
-    if (!(P0 > P1)) d01 = __dadd_rn(d01, c);
-    if (!(P1 > P2)) d12 = __dadd_rn(d12, c);
-    const float P12 = __double2float_rn(d01);
-    const float P23 = __double2float_rn(d12);
+    constexpr float SC = 16777216.0f;                   // 2^24
+    constexpr float C_S = PI_2 * SC;                    // exact
+    constexpr float RC_S = (1.0f / PI_2) / SC;          // RN(1/(2*PI)) * 2^-24, exact scaling
+    const int C_I = (int)C_S;                           // 2*PI in units of 2^-24 (a multiple of 8)
+    ok = ok && (min(I0, min(I1, I2)) != SLR_PTAB_DEGENERATE);
+    // (unsigned arithmetic: a degenerate entry would overflow int; its pixel is dropped anyway)
+    const int d01 = (int)((unsigned)I0 - (unsigned)I1 + ((I0 > I1) ? 0u : (unsigned)C_I));
+    const int d12 = (int)((unsigned)I1 - (unsigned)I2 + ((I1 > I2) ? 0u : (unsigned)C_I));
+    const float P12 = __int2float_rn(d01);              // = P12 * 2^24
+    const float P23 = __int2float_rn(d12);
     const float d = __fsub_rn(P12, P23);
-    const float P123 = (P12 > P23) ? d : __fadd_rn(d, PI_2);
-    // P123 / (2*PI), correctly rounded, without the generic division routine: with rc = RN(1/c),
-    // q0 = RN(x*rc), rem = x - c*q0 (exact in an FMA), RN(q0 + rem*rc) == RN(x/c).  Verified
-    // exhaustively on the host against IEEE division for every float with 2^-100 <= |x| < 32 and x = +0
-    // (scratch/div_check.c); P123 is +0-free of sign issues and a multiple of 2^-24, so it is in range.
-    const float q0 = __fmul_rn(P123, RPI_2);
-    const float rem = __fmaf_rn(-q0, PI_2, P123);
-    const float quo = __fmaf_rn(rem, RPI_2, q0);
+    const float P123 = (P12 > P23) ? d : __fadd_rn(d, C_S);
+    const float q0 = __fmul_rn(P123, RC_S);
+    const float rem = __fmaf_rn(-q0, C_S, P123);
+    const float quo = __fmaf_rn(rem, RC_S, q0);
     return __fmul_rn(quo, 255.0f);
 }
 
@@ -236,6 +250,34 @@ __device__ __forceinline__ float heterodyne_strict_d(double P0, double P1, doubl
 #define SLR_TWO_PI_F 6.28318530717958647692f
 
 __device__ __forceinline__ float wrap_2pi(float d) { return (d < 0.0f) ? __fadd_rn(d, SLR_TWO_PI_F) : d; }
+
+// corrected-mode scale of the unwrapped phase to 0..255 (one multiply; the oracle's d / 2pi * 255 differs by <= 1 ulp)
+__device__ __forceinline__ float phase_scale_corrected(float d) { return __fmul_rn(d, 255.0f / SLR_TWO_PI_F); }
+
+// atan2(a, b) mapped to [0, 2*pi]: octant reduction, one approximate reciprocal (MUFU.RCP) and a degree-6 minimax
+// polynomial in t^2 (max error 3.4e-7 rad on [0, 1], about one float ulp of the result) instead of libdevice's
+// atan2f (a full-precision division with its slow path, plus special-case branches): ~20 instructions, no
+// branches.  Corrected mode has no reference counterpart and is checked against the oracle's libm atan2f within the
+// north star's 1e-4.  a == b == 0 gives NaN; those pixels are dropped by the caller.
+__device__ __forceinline__ float atan2_pos(float a, float b)
+{
+    const float ax = fabsf(a), bx = fabsf(b);
+    const float mx = fmaxf(ax, bx), mn = fminf(ax, bx);
+    const float t = __fdividef(mn, mx);
+    const float u = t * t;
+    float q = 0.006811774335801601f;
+    q = fmaf(q, u, -0.033604156225919724f);
+    q = fmaf(q, u, 0.07962359488010406f);
+    q = fmaf(q, u, -0.13233336806297302f);
+    q = fmaf(q, u, 0.19807814061641693f);
+    q = fmaf(q, u, -0.3331736922264099f);
+    q = fmaf(q, u, 0.9999961256980896f);
+    float r = q * t;
+    if (ax > bx) r = 1.57079632679489661923f - r;
+    if (b < 0.0f) r = 3.14159265358979323846f - r;
+    if (a < 0.0f) r = SLR_TWO_PI_F - r;
+    return r;
+}
 
 // ------------------------------------------------------------------------------------------------
 // match predicate: Duke/mfreconstruct.cpp:295  fabs(pL - pR) < 0.1  (float difference, float fabs,

@@ -37,7 +37,7 @@ static void free_engine(slr_engine *e)
     cudaFree(e->d_undist_rx);
     cudaFree(e->d_atan_lut);
     cudaFree(e->d_ptab);
-    cudaFree(e->d_mtab);
+    cudaFree(e->d_btab);
     cudaFree(e->d_phase);
     cudaFree(e->d_code);
     cudaFree(e->d_mask);

@@ -38,8 +38,8 @@ struct slr_engine {
     // atan(float(q)) for q in [-255, 255] (index q+255), built on the host with the host libm.
     float *d_atan_lut = nullptr;
     // strict-mode tables of the fused kernel (k_fused.cu: slr_build_strict_tables)
-    double *d_ptab = nullptr;
-    uint32_t *d_mtab = nullptr;
+    int32_t *d_ptab = nullptr;      // [SLR_PTAB_SIZE] wrapped phases in units of 2^-24
+    uint32_t *d_btab = nullptr;     // [SLR_BTAB_SIZE] reciprocal multiplier + row base per b = G1-G3
 
     // scratch for the un-fused pipelines / host entry points
     float *d_phase = nullptr;      // [max_batch][2][H][W]
