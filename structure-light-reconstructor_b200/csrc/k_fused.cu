@@ -62,6 +62,9 @@ struct FusedParams {
 #ifdef SLR_PHASE_CLOCKS
     long long *dbg;        // [grid][DBG_ROWS][16 warps][DBG_PTS] clock64 stamps (debug builds only)
 #endif
+#ifdef SLR_ABLATION
+    int ablate;            // SLR_ABLATE bit mask: skip 1 reprojection, 2 chain walk, 4 insert, 8 decode math, 16 stores
+#endif
 };
 
 #ifdef SLR_PHASE_CLOCKS
@@ -74,6 +77,11 @@ constexpr int DBG_ROWS = 8, DBG_PTS = 7, DBG_SKIP = 4;
     } while (0)
 #else
 #define SLR_STAMP(pt) do { } while (0)
+#endif
+#ifdef SLR_ABLATION   // cost-attribution builds (csrc/Makefile ABLATE=1): results are wrong by construction
+#define SLR_ABLATE(bit) ((p.ablate & (bit)) != 0)
+#else
+#define SLR_ABLATE(bit) false
 #endif
 
 __device__ __forceinline__ uint64_t make_evict_first_policy()
@@ -220,6 +228,10 @@ __device__ __forceinline__ void load_phases(const unsigned char *stage, int W, i
             ph[q] = src[q];
             ok[q] = m[q] != 0 && (!right || ph[q] == ph[q]);  // a NaN on the right never matches
         }
+    } else if (SLR_ABLATE(8)) {
+        const unsigned char *r0 = stage + (right ? (size_t)N * W : 0) + x0;
+#pragma unroll
+        for (int q = 0; q < PX; q++) ph[q] = (float)r0[2 * W + q] + 0.01f * (float)r0[6 * W + q], ok[q] = r0[q] > r0[W + q];
     } else {
         decode_px<MODE, PX>(stage + (right ? (size_t)N * W : 0), W, x0, p, s_ptab, s_btab, ph, ok);
     }
@@ -436,7 +448,7 @@ k_fused_mf(const FusedParams p)
             const unsigned okb = __shfl_xor_sync(0xffffffffu, (ok[2] ? 1u : 0u) | (ok[3] ? 2u : 0u), 1);
             float ip[2] = {right ? ph[0] : n2, right ? ph[1] : n3};
             bool io[2] = {right ? ok[0] : (okb & 1u) != 0, right ? ok[1] : (okb & 2u) != 0};
-            insert_right<2, CLAMP>(tab, ip, io, right ? x0 : x0 + 2);
+            if (!SLR_ABLATE(4)) insert_right<2, CLAMP>(tab, ip, io, right ? x0 : x0 + 2);
             if (!right)
                 reinterpret_cast<float4 *>(s_pl)[x0 >> 2] = make_float4(ok[0] ? ph[0] : slr::qnan(), ok[1] ? ph[1] : slr::qnan(),
                                                                         ok[2] ? ph[2] : slr::qnan(), ok[3] ? ph[3] : slr::qnan());
@@ -452,7 +464,9 @@ k_fused_mf(const FusedParams p)
             const int x = rem_x0 + (live ? xi : 0);
             load_phases<MODE, 1>(stage, W, N, x, right, p, s_ptab, s_btab, ph, ok);
             ok[0] = ok[0] && live;
-            if (right)
+            if (right && SLR_ABLATE(4))
+                ;
+            else if (right)
                 insert_right<1, CLAMP>(tab, ph, ok, x);
             else if (live)
                 s_pl[x] = ok[0] ? ph[0] : slr::qnan();
@@ -489,7 +503,8 @@ k_fused_mf(const FusedParams p)
                 v[u] = (j[u] < W) ? s_pl[j[u]] : slr::qnan();
             }
 #pragma unroll
-            for (int u = 0; u < QPX; u++) best[u] = (v[u] == v[u]) ? first_match<CLAMP>(tab, v[u]) : INT_MAX;
+            for (int u = 0; u < QPX; u++)
+                best[u] = (v[u] != v[u]) ? INT_MAX : SLR_ABLATE(2) ? max(j[u] - 7, 0) : first_match<CLAMP>(tab, v[u]);
             // every pixel is reprojected unconditionally (dummy inputs where there is no match) so that independent
             // fp64 chains interleave; misses are turned into NaN afterwards
             float X[QPX], Y[QPX], Z[QPX];
@@ -497,13 +512,16 @@ k_fused_mf(const FusedParams p)
             for (int u = 0; u < QPX; u++) {
                 const bool hit = best[u] != INT_MAX;
                 const float ulx = hit ? s_lx[j[u]] : 0.0f, uly = hit ? s_ly[j[u]] : 0.0f, urx = hit ? s_rx[best[u]] : 0.0f;
-                slr::reproject_q(p.calib, (double)ulx, (double)uly, (double)__fsub_rn(ulx, urx), X[u], Y[u], Z[u]);
+                if (SLR_ABLATE(1))
+                    X[u] = ulx, Y[u] = uly, Z[u] = urx;
+                else
+                    slr::reproject_q(p.calib, (double)ulx, (double)uly, (double)__fsub_rn(ulx, urx), X[u], Y[u], Z[u]);
             }
 #pragma unroll
             for (int u = 0; u < QPX; u++) {
                 const bool hit = best[u] != INT_MAX;
                 n_local += hit ? 1u : 0u;
-                if (j[u] < W) {
+                if (j[u] < W && !(SLR_ABLATE(16) && X[u] != 12345.0f)) {
                     float *dst = xyz_row + 3 * j[u];
                     dst[0] = hit ? X[u] : slr::qnan();
                     dst[1] = hit ? Y[u] : slr::qnan();
@@ -664,6 +682,9 @@ static slr_status launch_fused(slr_engine *e, int mode, const uint8_t *d_stack, 
     const long long rows = (long long)batch * e->H;
     if (grid > rows) grid = rows;
     if (grid < 1) return SLR_OK;
+#ifdef SLR_ABLATION
+    p.ablate = getenv("SLR_ABLATE") ? atoi(getenv("SLR_ABLATE")) : 0;
+#endif
 #ifdef SLR_PHASE_CLOCKS
     const size_t dbg_n = (size_t)grid * DBG_ROWS * 16 * DBG_PTS;
     SLR_CHECK_CUDA(cudaMalloc(&p.dbg, dbg_n * sizeof(long long)));
