@@ -35,3 +35,61 @@ def gather_clouds(xyz_local, valid_local, n_scans: int, group=None):
     dist.all_gather_into_tensor(vg, vl, group=group)
     keep = torch.cat([torch.arange(r * bmax, r * bmax + (hi - lo)) for r, (lo, hi) in enumerate(sizes)]).to(xg.device)
     return xg.index_select(0, keep), vg.index_select(0, keep)
+
+
+class CloudAssembly:
+    """The assembled cloud of all ranks, allocated ONCE: [world * b_local, H, W, 3] xyz + [world * b_local, H, W] valid.
+
+    Every rank's kernels write straight into its own block (`local_views()` are views of the assembled tensors), and
+    `gather()` is an in-place all-gather (send buffer = this rank's block of the receive buffer), so assembling the
+    cloud costs no copy besides the NVLink transfer itself.  With `slots=2` the gather of step k runs on a side
+    stream while step k+1 computes into the other slot (events order producer and consumer both ways).
+    Equal shards only (b_local scans on every rank); ragged batches go through `gather_clouds`."""
+
+    def __init__(self, b_local: int, H: int, W: int, device, slots: int = 2, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.b = b_local
+        n = self.world * b_local
+        self.xyz = [torch.empty((n, H, W, 3), dtype=torch.float32, device=device) for _ in range(slots)]
+        self.valid = [torch.empty((n, H, W), dtype=torch.uint8, device=device) for _ in range(slots)]
+        self.cuda = torch.device(device).type == "cuda"
+        if self.cuda:
+            self.comm = torch.cuda.Stream(device=device)
+            self.filled = [torch.cuda.Event() for _ in range(slots)]    # compute -> comm
+            self.gathered = [torch.cuda.Event() for _ in range(slots)]  # comm -> compute (slot may be overwritten)
+            self.used = [False] * slots
+
+    def local_views(self, slot: int):
+        lo = self.rank * self.b
+        return self.xyz[slot][lo:lo + self.b], self.valid[slot][lo:lo + self.b]
+
+    def before_compute(self, slot: int):
+        """Call before launching kernels that write slot: waits until the previous gather of that slot is done."""
+        if self.cuda and self.used[slot]:
+            self.torch.cuda.current_stream().wait_event(self.gathered[slot])
+
+    def gather(self, slot: int):
+        """In-place all-gather of slot (asynchronous on GPUs: ordered after the kernels already launched on the
+        current stream, executed on the communication stream)."""
+        xl, vl = self.local_views(slot)
+        if not self.cuda:
+            self.dist.all_gather_into_tensor(self.xyz[slot], xl, group=self.group)
+            self.dist.all_gather_into_tensor(self.valid[slot], vl, group=self.group)
+            return self.xyz[slot], self.valid[slot]
+        torch = self.torch
+        self.filled[slot].record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.filled[slot])
+            self.dist.all_gather_into_tensor(self.xyz[slot], xl, group=self.group)
+            self.dist.all_gather_into_tensor(self.valid[slot], vl, group=self.group)
+            self.gathered[slot].record(self.comm)
+        self.used[slot] = True
+        return self.xyz[slot], self.valid[slot]
+
+    def wait(self):
+        """Make the current stream wait for every gather issued so far."""
+        if self.cuda:
+            self.torch.cuda.current_stream().wait_stream(self.comm)

@@ -49,6 +49,16 @@ def _worker(rank, world, port, n_scans, H, W, out_dir):
         p = torch.tensor([int(full_valid[lo:hi].sum())], dtype=torch.int64)
         dist.all_reduce(p, op=dist.ReduceOp.SUM)
         ok = ok and float(t) == float(world) and int(p) == int(full_valid.sum())
+        if n_scans % world == 0:   # equal shards: the pre-allocated in-place assembly bench.py --gather uses
+            b = n_scans // world
+            asm = parallel.CloudAssembly(b, H, W, "cpu", slots=2)
+            for slot in range(2):
+                xl, vl = asm.local_views(slot)
+                xl.copy_(full_xyz[lo:hi])
+                vl.copy_(full_valid[lo:hi])
+                gx, gv = asm.gather(slot)
+                ok = ok and torch.equal(gx, full_xyz) and torch.equal(gv, full_valid)
+            asm.wait()
         open(os.path.join(out_dir, f"rank{rank}.ok" if ok else f"rank{rank}.bad"), "w").close()
     finally:
         dist.destroy_process_group()
