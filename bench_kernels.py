@@ -109,6 +109,18 @@ def main():
     ms = timed(lambda: eng.rectify_stack(mf))
     c = cpu_time(lambda: [orc.remap_linear(h_mf[0, cam, n], m1s[cam], m2s[cam]) for cam in range(2) for n in range(14)]) if orc else None
     report("k0_rectify (14 planes)", "stereoRect::doStereoRectify (cv::remap)", ms, B * 2 * P * (14 * 2 + 6), c, B * 2 * 14 * P, "pixels")
+    # ---------------- K5: mesh indexing of one full-frame cloud (N3) ----------------
+    import oracle_lib as _ol
+    _o = orc if orc else _ol.load()
+    sums_h, cnt_h = _o.pointcloud_from_dense(out[0][0].cpu().numpy(), out[1][0].cpu().numpy(), W, H)   # F7 drop rule applied
+    sums_d, cnt_d = torch.from_numpy(sums_h).cuda(), torch.from_numpy(cnt_h).cuda()
+    vert, src, faces = eng.mesh_index(sums_d, cnt_d, 0)
+    nv, nf = vert.shape[0], faces.shape[0]
+    ms = timed(lambda: eng.mesh_index(sums_d, cnt_d, 0))
+    c = cpu_time(lambda: orc.mesh_index(sums_h, cnt_h, W, H, 0)) if orc else None
+    rows_before = len(rows)
+    report("k5 mesh index (1 cloud, 1280x1024)", "MeshCreator::exportPlyMesh index passes", ms, P * 13 + nv * 16 + nf * 12, c, P, "pixels")
+    rows[rows_before]["speedup_vs_cpu_port"] = (c / (ms * 1e-3)) if c else None
     del mf, ph, mk, out
 
     # ---------------- 1280x1024 Gray EPI ----------------

@@ -184,6 +184,24 @@ SLR_API slr_status slr_run_ge_host(slr_engine *e, const uint8_t *h_stack, int ba
 SLR_API slr_status slr_run_gray_host(slr_engine *e, const uint8_t *h_stack, int batch, int nbits_col, int nbits_row,
                                      int black_thr, int white_thr, int scan_w, int scan_h, float *h_sum,
                                      uint8_t *h_cnt, unsigned long long *h_n_cells);
+/* ---- mesh indexing ---------------------------------------------------------- */
+/* The index passes of MeshCreator::exportPlyMesh / exportObjMesh, Duke/meshcreator.cpp:16-65, 67-166, on a
+ * PointCloudImage stored as the reference stores it (Duke/pointcloudimage.cpp:3-13): d_sum = float [h][w][3]
+ * coordinate sums, d_count = uint8 [h][w] points per pixel; w, h = PointCloudImage width / height.
+ * Traversal order i in [0,w) outer, j in [0,h) inner.  first_vertex = 0 reproduces the PLY numbering (whose first
+ * vertex reads as "absent" when faces are formed, meshcreator.cpp:79,100), 1 the OBJ numbering.
+ *   d_vertices   float [w*h][3]   getPoint(i,j) of every pixel that has one, in traversal order
+ *   d_vertex_src int32 [w*h]      storage element j*w+i each vertex came from (for per-vertex colour); may be NULL
+ *   d_faces      int32 [2*w*h][3] vertex numbers of every face, in the reference's output order and orientation
+ *   d_counts     uint64 [2]       number of vertices, number of faces */
+SLR_API slr_status slr_mesh_index(slr_engine *e, const float *d_sum, const uint8_t *d_count, int w, int h,
+                                  int first_vertex, float *d_vertices, int32_t *d_vertex_src, int32_t *d_faces,
+                                  unsigned long long *d_counts);
+/* Same with HOST buffers (what the facade's MeshCreator calls): h_vertices / h_vertex_src / h_faces must hold the
+ * worst case (w*h vertices, 2*w*h faces); h_counts[2] receives the actual numbers. */
+SLR_API slr_status slr_mesh_index_host(slr_engine *e, const float *h_sum, const uint8_t *h_count, int w, int h,
+                                       int first_vertex, float *h_vertices, int32_t *h_vertex_src, int32_t *h_faces,
+                                       unsigned long long *h_counts);
 SLR_API slr_status slr_host_alloc(void **out, size_t bytes); /* pinned */
 SLR_API slr_status slr_host_free(void *p);
 

@@ -14,6 +14,7 @@
 #include "mfreconstruct.h"
 #include "multifrequency.h"
 #include "pointcloudimage.h"
+#include "meshcreator.h"
 #include "reconstruct.h"
 #include "utilities.h"
 
@@ -358,6 +359,26 @@ void ref_pointcloud_add(int w, int h, const int32_t *iw, const int32_t *jh, cons
     PointCloudImage pc(w, h, false);
     for (int k = 0; k < n; k++) pc.addPoint(iw[k], jh[k], cv::Point3f(pts[3 * k], pts[3 * k + 1], pts[3 * k + 2]));
     dump_cloud(&pc, w, h, points, count);
+}
+
+// MeshCreator::exportPlyMesh / exportObjMesh (meshcreator.cpp:16-166) on a PointCloudImage filled from
+// sums [h][w][3] + counts [h][w] (+ optional colour sums u8 [h][w][3]).
+int ref_export_mesh(const float *points, const uint8_t *count, const uint8_t *color, int w, int h, int obj, const char *path)
+{
+    PointCloudImage pc(w, h, color != nullptr);
+    for (int r = 0; r < h; r++)
+        for (int c = 0; c < w; c++) {
+            const size_t q = (size_t)r * w + c;
+            pc.numOfPointsForPixel.at<uchar>(r, c) = count[q];
+            pc.points.at<cv::Vec3f>(r, c) = cv::Vec3f(points[q * 3], points[q * 3 + 1], points[q * 3 + 2]);
+            if (color) pc.color.at<cv::Vec3b>(r, c) = cv::Vec3b(color[q * 3], color[q * 3 + 1], color[q * 3 + 2]);
+        }
+    MeshCreator mc(&pc);
+    if (obj)
+        mc.exportObjMesh(QString(path));
+    else
+        mc.exportPlyMesh(QString(path));
+    return 0;
 }
 
 }  // extern "C"

@@ -9,6 +9,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
@@ -751,6 +752,120 @@ void orc_pointcloud_from_dense(const float *xyz, const uint8_t *valid, int W, in
                 count[q] = (uint8_t)(count[q] + 1);
             }
         }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* N3: MeshCreator — vertex numbering, grid-neighbour faces, PLY / OBJ text                      */
+/* ------------------------------------------------------------------------------------------ */
+
+/* PointCloudImage::getPoint, pointcloudimage.cpp:56-67: Vec3d(points) / (float)num == points * (1.f/num)
+ * evaluated in double (OpenCV 2.4 Vec operator/), narrowed to Point3f. */
+static int orc_get_point(const float *points, const uint8_t *count, int w, int h, int i_w, int j_h, float out[3])
+{
+    if (i_w >= w || j_h >= h)
+        return 0;
+    size_t q = (size_t)j_h * w + i_w;
+    uint8_t num = count[q];
+    if (num == 0)
+        return 0;
+    float inv = 1.f / (float)num;
+    for (int c = 0; c < 3; c++)
+        out[c] = (float)((double)points[q * 3 + c] * inv);
+    return 1;
+}
+
+/* The index passes of exportPlyMesh (meshcreator.cpp:75-110, first_vertex = 0) and exportObjMesh (:25-63,
+ * first_vertex = 1).  vertices [w*h][3], vertex_src [w*h] (storage element j*w+i), faces [2*w*h][3];
+ * returns the counts through nv / nf.  pixel_num is caller scratch [w*h]. */
+void orc_mesh_index(const float *points, const uint8_t *count, int w, int h, int first_vertex, int *pixel_num,
+                    float *vertices, int32_t *vertex_src, int32_t *faces, int64_t *nv, int64_t *nf)
+{
+    int vertex = first_vertex;
+    int64_t n = 0;
+    for (int i = 0; i < w; i++)
+        for (int j = 0; j < h; j++) {
+            float pt[3];
+            if (orc_get_point(points, count, w, h, i, j, pt)) {
+                pixel_num[i * h + j] = vertex++;          /* access(i,j) = i*h + j, meshcreator.cpp:168-171 */
+                vertices[n * 3 + 0] = pt[0];
+                vertices[n * 3 + 1] = pt[1];
+                vertices[n * 3 + 2] = pt[2];
+                if (vertex_src)
+                    vertex_src[n] = (int32_t)((size_t)j * w + i);
+                n++;
+            } else {
+                pixel_num[i * h + j] = 0;
+            }
+        }
+    *nv = n;
+    int64_t f = 0;
+    for (int i = 0; i < w; i++)
+        for (int j = 0; j < h; j++) {
+            int v1 = pixel_num[i * h + j], v2, v3;
+            v2 = (i < w - 1) ? pixel_num[(i + 1) * h + j] : 0;
+            v3 = (j < h - 1) ? pixel_num[i * h + j + 1] : 0;
+            if (v1 != 0 && v2 != 0 && v3 != 0) {          /* "3 v1 v2 v3", :151-152 */
+                faces[f * 3 + 0] = v1, faces[f * 3 + 1] = v2, faces[f * 3 + 2] = v3;
+                f++;
+            }
+            v3 = (j > 0 && i < w - 1) ? pixel_num[(i + 1) * h + j - 1] : 0;
+            if (v1 != 0 && v2 != 0 && v3 != 0) {          /* "3 v1 v3 v2", :159-160 */
+                faces[f * 3 + 0] = v1, faces[f * 3 + 1] = v3, faces[f * 3 + 2] = v2;
+                f++;
+            }
+        }
+    *nf = f;
+}
+
+/* exportPlyMesh (:67-166) / exportObjMesh (:16-65) text.  `ostream << float` is printf("%g") (precision 6).
+ * colour: sums int [h][w][3] or NULL; without a colour plane getPoint yields (100, 0, 0) — the reference's
+ * `(cv::Point3i)(100,100,100)` is a comma expression (pointcloudimage.cpp:50) — printed as "0 0 100". */
+int orc_export_mesh(const float *points, const uint8_t *count, const int32_t *color, int w, int h, int obj,
+                    const char *path)
+{
+    size_t px = (size_t)w * h;
+    int *pn = (int *)malloc(px * sizeof(int));
+    float *vert = (float *)malloc(px * 3 * sizeof(float));
+    int32_t *src = (int32_t *)malloc(px * sizeof(int32_t));
+    int32_t *faces = (int32_t *)malloc(px * 6 * sizeof(int32_t));
+    int64_t nv = 0, nf = 0;
+    FILE *fp = fopen(path, "w");
+    if (!pn || !vert || !src || !faces || !fp) {
+        free(pn), free(vert), free(src), free(faces);
+        if (fp)
+            fclose(fp);
+        return -1;
+    }
+    orc_mesh_index(points, count, w, h, obj ? 1 : 0, pn, vert, src, faces, &nv, &nf);
+    if (!obj) {
+        fprintf(fp, "ply\nformat ascii 1.0\nelement vertex %lld\n", (long long)nv);
+        fprintf(fp, "property float x\nproperty float y\nproperty float z\n");
+        fprintf(fp, "property uchar red\nproperty uchar green\nproperty uchar blue\n");
+        fprintf(fp, "element face %lld\nproperty list uchar int vertex_indices\nend_header\n", (long long)nf);
+    }
+    for (int64_t v = 0; v < nv; v++) {
+        if (obj) {
+            fprintf(fp, "v %g %g %g\n", vert[v * 3], vert[v * 3 + 1], vert[v * 3 + 2]);
+        } else {
+            int c[3] = {100, 0, 0};
+            if (color) {
+                float inv = 1.f / (float)count[src[v]];   /* Vec3i / float: saturate_cast<int>(v * (1.f/num)) = cvRound */
+                for (int k = 0; k < 3; k++)
+                    c[k] = (int)lrint((double)color[(size_t)src[v] * 3 + k] * inv);
+            }
+            fprintf(fp, "%g %g %g %d %d %d\n", vert[v * 3], vert[v * 3 + 1], vert[v * 3 + 2], c[2], c[1], c[0]);
+        }
+    }
+    for (int64_t f = 0; f < nf; f++) {
+        const int32_t *t = faces + f * 3;
+        if (obj)
+            fprintf(fp, "f %d/%d %d/%d %d/%d\n", t[0], t[0], t[1], t[1], t[2], t[2]);
+        else
+            fprintf(fp, "3 %d %d %d\n", t[0], t[1], t[2]);
+    }
+    fclose(fp);
+    free(pn), free(vert), free(src), free(faces);
+    return 0;
 }
 
 /* PointCloudImage::addPoint applied to a sequence of (i_w, j_h, point) calls: pointcloudimage.cpp:86-97 with

@@ -138,6 +138,13 @@ int64_t orc_run_mf(const uint8_t *stacks, int W, int H, int F, int S, int black_
 
 int orc_max_threads(void);
 
+/* N3: MeshCreator index passes + text export (Duke/meshcreator.cpp:16-166) on a PointCloudImage stored as
+ * points float [h][w][3] / count u8 [h][w]; see slr_oracle.c. */
+void orc_mesh_index(const float *points, const uint8_t *count, int w, int h, int first_vertex, int *pixel_num,
+                    float *vertices, int32_t *vertex_src, int32_t *faces, int64_t *nv, int64_t *nf);
+int orc_export_mesh(const float *points, const uint8_t *count, const int32_t *color, int w, int h, int obj,
+                    const char *path);
+
 #ifdef __cplusplus
 }
 #endif

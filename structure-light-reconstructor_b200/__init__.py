@@ -60,7 +60,7 @@ EXPORTS = [
     "slr_generate_mf_patterns", "slr_mf_decode", "slr_gray_decode", "slr_match_triangulate_phase",
     "slr_match_triangulate_code", "slr_bucket_triangulate", "slr_run_mf", "slr_run_ge", "slr_run_mf_host",
     "slr_run_ge_host", "slr_host_alloc", "slr_host_free", "slr_synth_mf", "slr_synth_gray",
-    "slr_kernel_launches", "slr_set_rectify_maps", "slr_rectify_stack", "slr_set_host_input_raw", "slr_run_gray_host",
+    "slr_kernel_launches", "slr_mesh_index", "slr_mesh_index_host", "slr_set_rectify_maps", "slr_rectify_stack", "slr_set_host_input_raw", "slr_run_gray_host",
 ]
 
 
@@ -103,6 +103,8 @@ def capi():
     lib.slr_rectify_stack.argtypes = [vp, vp, i32, i32, vp]
     lib.slr_set_host_input_raw.argtypes = [vp, i32]
     lib.slr_run_gray_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, C.POINTER(C.c_ulonglong)]
+    lib.slr_mesh_index.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.slr_mesh_index_host.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
     lib.slr_kernel_launches.argtypes = [vp]
     lib.slr_kernel_launches.restype = C.c_ulonglong
     _lib = lib
@@ -336,6 +338,22 @@ class Engine:
         return int(n.value)
 
     # -- synthetic inputs ---------------------------------------------------------------------
+    def mesh_index(self, sums, counts, first_vertex=0):
+        """slr_mesh_index on device tensors sums [h,w,3] f32 / counts [h,w] u8 -> (vertices [nv,3], vertex_src [nv],
+        faces [nf,3]) device tensors (MeshCreator's vertex numbering + faces, Duke/meshcreator.cpp:16-166)."""
+        t = self._torch
+        h, w = counts.shape
+        px = w * h
+        vert = self._empty((px, 3), t.float32)
+        src = self._empty((px,), t.int32)
+        faces = self._empty((2 * px, 3), t.int32)
+        cnts = t.zeros(2, dtype=t.int64, device=vert.device)
+        self._bind_stream()
+        _check(self.lib.slr_mesh_index(self.h, self._p(sums), self._p(counts), w, h, first_vertex, self._p(vert),
+                                       self._p(src), self._p(faces), self._p(cnts)), "slr_mesh_index")
+        nv, nf = (int(v) for v in cnts.tolist())
+        return vert[:nv], src[:nv], faces[:nf]
+
     def synth_mf(self, batch, proj_w=None, seed=0, integer_disparity=True, noise_dn=0.0):
         t = self._torch
         stack = self._empty((batch, 2, 14, self.H, self.W), t.uint8)

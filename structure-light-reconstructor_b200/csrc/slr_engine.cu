@@ -38,6 +38,14 @@ static void free_engine(slr_engine *e)
     cudaFree(e->d_atan_lut);
     cudaFree(e->d_ptab);
     cudaFree(e->d_btab);
+    cudaFree(e->d_mesh_pn);
+    cudaFree(e->d_mesh_tiles);
+    cudaFree(e->d_mesh_sum);
+    cudaFree(e->d_mesh_count);
+    cudaFree(e->d_mesh_vertices);
+    cudaFree(e->d_mesh_src);
+    cudaFree(e->d_mesh_faces);
+    cudaFree(e->d_mesh_counts);
     cudaFree(e->d_phase);
     cudaFree(e->d_code);
     cudaFree(e->d_mask);
@@ -358,6 +366,84 @@ extern "C" slr_status slr_run_ge(slr_engine *e, const uint8_t *d_stack, int batc
     }
     return slr_launch_fused_ge(e, d_stack, batch, nbits_col, black_thr, white_thr, scan_w, have_color, d_xyz,
                                d_valid, d_match_k, d_color, d_n_points);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: mesh indexing (MeshCreator's vertex numbering + faces)
+// ------------------------------------------------------------------------------------------------
+static slr_status ensure_mesh_scratch(slr_engine *e, size_t px, bool host_staging)
+{
+    if (e->mesh_px < px) {
+        cudaFree(e->d_mesh_pn);
+        cudaFree(e->d_mesh_tiles);
+        e->d_mesh_pn = e->d_mesh_tiles = nullptr;
+        e->mesh_px = 0;
+        SLR_CHECK_CUDA(cudaMalloc(&e->d_mesh_pn, px * sizeof(int)));
+        SLR_CHECK_CUDA(cudaMalloc(&e->d_mesh_tiles, (px / 1024 + 2) * sizeof(int)));
+        e->mesh_px = px;
+    }
+    if (host_staging && e->mesh_host_px < px) {
+        cudaFree(e->d_mesh_sum);
+        cudaFree(e->d_mesh_count);
+        cudaFree(e->d_mesh_vertices);
+        cudaFree(e->d_mesh_src);
+        cudaFree(e->d_mesh_faces);
+        cudaFree(e->d_mesh_counts);
+        e->d_mesh_sum = e->d_mesh_vertices = nullptr;
+        e->d_mesh_count = nullptr;
+        e->d_mesh_src = e->d_mesh_faces = nullptr;
+        e->d_mesh_counts = nullptr;
+        e->mesh_host_px = 0;
+        SLR_CHECK_CUDA(cudaMalloc(&e->d_mesh_sum, px * 3 * sizeof(float)));
+        SLR_CHECK_CUDA(cudaMalloc(&e->d_mesh_count, px));
+        SLR_CHECK_CUDA(cudaMalloc(&e->d_mesh_vertices, px * 3 * sizeof(float)));
+        SLR_CHECK_CUDA(cudaMalloc(&e->d_mesh_src, px * sizeof(int32_t)));
+        SLR_CHECK_CUDA(cudaMalloc(&e->d_mesh_faces, px * 6 * sizeof(int32_t)));
+        SLR_CHECK_CUDA(cudaMalloc(&e->d_mesh_counts, 2 * sizeof(unsigned long long)));
+        e->mesh_host_px = px;
+    }
+    return SLR_OK;
+}
+
+extern "C" slr_status slr_mesh_index(slr_engine *e, const float *d_sum, const uint8_t *d_count, int w, int h,
+                                     int first_vertex, float *d_vertices, int32_t *d_vertex_src, int32_t *d_faces,
+                                     unsigned long long *d_counts)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(d_sum && d_count && d_vertices && d_faces && d_counts && w > 0 && h > 0 &&
+                (long long)w * h < (1LL << 30) && (first_vertex == 0 || first_vertex == 1), "slr_mesh_index: bad argument");
+    slr_status st = ensure_mesh_scratch(e, (size_t)w * h, false);
+    if (st != SLR_OK) return st;
+    return slr_launch_mesh_index(e, d_sum, d_count, w, h, first_vertex, e->d_mesh_pn, e->d_mesh_tiles, d_vertices,
+                                 d_vertex_src, d_faces, d_counts);
+}
+
+extern "C" slr_status slr_mesh_index_host(slr_engine *e, const float *h_sum, const uint8_t *h_count, int w, int h,
+                                          int first_vertex, float *h_vertices, int32_t *h_vertex_src, int32_t *h_faces,
+                                          unsigned long long *h_counts)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(h_sum && h_count && h_vertices && h_faces && h_counts && w > 0 && h > 0 &&
+                (long long)w * h < (1LL << 30) && (first_vertex == 0 || first_vertex == 1),
+                "slr_mesh_index_host: bad argument");
+    const size_t px = (size_t)w * h;
+    slr_status st = ensure_mesh_scratch(e, px, true);
+    if (st != SLR_OK) return st;
+    SLR_CHECK_CUDA(cudaMemcpyAsync(e->d_mesh_sum, h_sum, px * 3 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    SLR_CHECK_CUDA(cudaMemcpyAsync(e->d_mesh_count, h_count, px, cudaMemcpyHostToDevice, e->stream));
+    st = slr_launch_mesh_index(e, e->d_mesh_sum, e->d_mesh_count, w, h, first_vertex, e->d_mesh_pn, e->d_mesh_tiles,
+                               e->d_mesh_vertices, e->d_mesh_src, e->d_mesh_faces, e->d_mesh_counts);
+    if (st != SLR_OK) return st;
+    SLR_CHECK_CUDA(cudaMemcpyAsync(h_counts, e->d_mesh_counts, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                   e->stream));
+    SLR_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    const size_t nv = (size_t)h_counts[0], nf = (size_t)h_counts[1];
+    if (nv) SLR_CHECK_CUDA(cudaMemcpyAsync(h_vertices, e->d_mesh_vertices, nv * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    if (nv && h_vertex_src)
+        SLR_CHECK_CUDA(cudaMemcpyAsync(h_vertex_src, e->d_mesh_src, nv * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (nf) SLR_CHECK_CUDA(cudaMemcpyAsync(h_faces, e->d_mesh_faces, nf * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    SLR_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+    return SLR_OK;
 }
 
 extern "C" slr_status slr_synth_mf(slr_engine *e, uint8_t *d_stack, int batch, int proj_w, unsigned seed,

@@ -63,6 +63,15 @@ struct slr_engine {
     uint8_t *d_stage_rect[2] = {nullptr, nullptr};
     size_t stage_rect_bytes = 0;
 
+    // K5 mesh index scratch: vertex numbers + tile sums, and the staging of the host entry point
+    int *d_mesh_pn = nullptr, *d_mesh_tiles = nullptr;
+    size_t mesh_px = 0;
+    float *d_mesh_sum = nullptr, *d_mesh_vertices = nullptr;
+    uint8_t *d_mesh_count = nullptr;
+    int32_t *d_mesh_src = nullptr, *d_mesh_faces = nullptr;
+    unsigned long long *d_mesh_counts = nullptr;
+    size_t mesh_host_px = 0;
+
     void *d_bucket_scratch = nullptr;  // K3c counting-sort scratch (one scan)
     size_t bucket_scratch_bytes = 0;
 
@@ -120,6 +129,10 @@ slr_status slr_launch_fused_ge(slr_engine *e, const uint8_t *d_stack, int batch,
 slr_status slr_launch_undistort_maps(slr_engine *e);
 slr_status slr_launch_rectify(slr_engine *e, const uint8_t *d_raw, int batch, int N, uint8_t *d_out);
 slr_status slr_build_strict_tables(slr_engine *e);
+slr_status slr_launch_mesh_index(slr_engine *e, const float *d_sum, const uint8_t *d_count, int w, int h,
+                                 int first_vertex, int *d_pn, int *d_tiles, float *d_vertices, int32_t *d_vertex_src,
+                                 int32_t *d_faces, unsigned long long *d_counts);
+int slr_mesh_tiles(int w, int h);
 slr_status slr_launch_synth_mf(slr_engine *e, uint8_t *d_stack, int batch, int proj_w, unsigned seed,
                                int integer_disparity, float noise_dn);
 slr_status slr_launch_synth_gray(slr_engine *e, uint8_t *d_stack, int batch, int scan_w, unsigned seed,

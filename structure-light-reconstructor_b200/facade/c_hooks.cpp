@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "imageio.h"
+#include "meshcreator.h"
 #include "rectify.h"
 #include "stereorect.h"
 #include "virtualcamera.h"
@@ -85,4 +86,31 @@ int duke_load_camera_matrix(const char *path, float *fc_cc)
     return 1;
 }
 
+
+// MeshCreator on a cloud given as sums [h][w][3] + counts [h][w] (+ colour values int [h][w][3] or NULL):
+// fills a PointCloudImage the way the reconstructors do and exports <path> (needs a GPU).
+int duke_export_mesh(const float *sums, const uint8_t *counts, const int *color, int w, int h, int obj, const char *path,
+                     unsigned long long *nv, unsigned long long *nf)
+{
+    PointCloudImage pc(w, h, color != nullptr);
+    for (int j = 0; j < h; j++)
+        for (int i = 0; i < w; i++) {
+            const size_t q = (size_t)j * w + i;
+            for (int k = 0; k < counts[q]; k++) {   // first call sets, later calls add (pointcloudimage.cpp:86-97)
+                const duke::Point3f p(k == 0 ? sums[q * 3] : -0.f, k == 0 ? sums[q * 3 + 1] : -0.f, k == 0 ? sums[q * 3 + 2] : -0.f);  // x + (-0) == x, signed zeros included
+                if (color)
+                    pc.addPoint(i, j, p, k == 0 ? duke::Vec3i(color[q * 3], color[q * 3 + 1], color[q * 3 + 2]) : duke::Vec3i(0, 0, 0));
+                else
+                    pc.addPoint(i, j, p);
+            }
+        }
+    MeshCreator mc(&pc);
+    if (obj)
+        mc.exportObjMesh(path);
+    else
+        mc.exportPlyMesh(path);
+    if (nv) *nv = mc.vertexCount();
+    if (nf) *nf = mc.faceCount();
+    return mc.ok() ? 0 : -1;
+}
 }  // extern "C"

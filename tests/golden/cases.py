@@ -56,3 +56,15 @@ def gray_only_rig(W, H):
 def helper_points(n=64, seed=5):
     rng = np.random.default_rng(seed)
     return rng.uniform(0, 1280, (n, 2)).astype(np.float32), rng.normal(0, 1, (n, 4, 3)).astype(np.float32)
+
+
+def mesh_cloud(w=29, h=17, seed=51, color=True):
+    """A PointCloudImage with holes, multi-hit pixels, awkward magnitudes: sums [h,w,3], counts [h,w], colour u8."""
+    rng = np.random.default_rng(seed)
+    count = ((rng.random((h, w)) > 0.3) * rng.integers(1, 4, (h, w))).astype(np.uint8)
+    count[0, 0] = 1                                # PLY vertex 0 exists: faces treat it as absent (meshcreator.cpp:79,100)
+    pts = (rng.normal(0, 300, (h, w, 3)) * count[..., None]).astype(np.float32)
+    pts[0, 0] = [1e-7, 123456789.0, -0.000123456]
+    pts[1, 1] = [0.0, -0.0, 1e10]
+    col = rng.integers(0, 256, (h, w, 3)).astype(np.uint8) if color else None
+    return pts, count, col

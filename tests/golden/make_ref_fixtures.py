@@ -85,6 +85,18 @@ def main():
     out["helpers"] = dict(px=px, vecs=vecs, undistort=und, ll_ok=np.array([o for o, _ in ll]), ll_p=np.array([p for _, p in ll]),
                           cam2world=c2w, normalize=nrm, pc_iw=iw, pc_jh=jh, pc_pts=pp, pc_sum=pcs, pc_cnt=pcc)
 
+    # N3: MeshCreator text export
+    import tempfile
+    mesh = {}
+    for tag, color in (("c", True), ("n", False)):
+        pts, cnt, col = cases.mesh_cloud(color=color)
+        h, w = cnt.shape
+        for obj in (False, True):
+            with tempfile.NamedTemporaryFile(suffix=".txt") as f:
+                r.export_mesh(pts, cnt, w, h, f.name, obj, col)
+                mesh[f"{tag}_{'obj' if obj else 'ply'}"] = np.frombuffer(open(f.name, "rb").read(), np.uint8)
+    out["mesh"] = mesh
+
     for name, arrs in out.items():
         np.savez_compressed(os.path.join(HERE, f"ref_{name}.npz"), **arrs)
         print(f"ref_{name}.npz", {k: v.shape for k, v in arrs.items()})

@@ -60,6 +60,8 @@ class Oracle:
         lib.orc_pointcloud_from_dense.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
         lib.orc_run_mf.argtypes = [vp, i32, i32, i32, i32, i32, i32, C.POINTER(OrcCamera), vp, vp, vp, vp, vp, i32]
         lib.orc_run_mf.restype = C.c_int64
+        lib.orc_mesh_index.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+        lib.orc_export_mesh.argtypes = [vp, vp, vp, i32, i32, i32, C.c_char_p]
         lib.orc_max_threads.restype = i32
 
     # ---- patterns ----
@@ -218,8 +220,33 @@ class Oracle:
     def max_threads(self):
         return self.lib.orc_max_threads()
 
+    # ---- N3: mesh ----
+    def mesh_index(self, points, count, w, h, first_vertex):
+        """-> (vertices [nv,3] f32, vertex_src [nv] i32, faces [nf,3] i32)"""
+        points = np.ascontiguousarray(points, np.float32)
+        count = np.ascontiguousarray(count, np.uint8)
+        px = w * h
+        pn = np.empty(px, np.int32)
+        vert = np.empty((px, 3), np.float32)
+        src = np.empty(px, np.int32)
+        faces = np.empty((2 * px, 3), np.int32)
+        nv, nf = np.zeros(1, np.int64), np.zeros(1, np.int64)
+        self.lib.orc_mesh_index(points.ctypes.data, count.ctypes.data, w, h, first_vertex, pn.ctypes.data,
+                                vert.ctypes.data, src.ctypes.data, faces.ctypes.data, nv.ctypes.data, nf.ctypes.data)
+        return vert[:nv[0]].copy(), src[:nv[0]].copy(), faces[:nf[0]].copy()
+
+    def export_mesh(self, points, count, w, h, path, obj=False, color=None):
+        points = np.ascontiguousarray(points, np.float32)
+        count = np.ascontiguousarray(count, np.uint8)
+        cptr = None
+        if color is not None:
+            color = np.ascontiguousarray(color, np.int32)
+            cptr = color.ctypes.data
+        rc = self.lib.orc_export_mesh(points.ctypes.data, count.ctypes.data, cptr, w, h, int(obj), str(path).encode())
+        assert rc == 0
 
 _oracle = None
+
 
 
 def load() -> Oracle:

@@ -156,6 +156,18 @@ class Ref:
         return out, cnt
 
 
+    def export_mesh(self, points, count, w, h, path, obj=False, color=None):
+        """MeshCreator::exportPlyMesh / exportObjMesh on a cloud given as sums [h,w,3] + counts [h,w]."""
+        points = np.ascontiguousarray(points, np.float32)
+        count = np.ascontiguousarray(count, np.uint8)
+        cptr = None
+        if color is not None:
+            color = np.ascontiguousarray(color, np.uint8)
+            cptr = C.c_void_p(color.ctypes.data)
+        self.lib.ref_export_mesh(C.c_void_p(points.ctypes.data), C.c_void_p(count.ctypes.data), cptr, int(w), int(h),
+                                 int(obj), str(path).encode())
+
+
 _ref = None
 
 

@@ -156,3 +156,42 @@ def test_reconstruct_gray_only_facade_end_to_end(tmp_path, oracle):
     s_img = s_o.reshape(W, H, 3).transpose(1, 0, 2)
     assert (cnt == c_img).all()
     assert (bits(sums[cnt > 0]) == bits(s_img[c_img > 0])).all()
+
+
+@pytest.mark.parametrize("color", [True, False])
+@pytest.mark.parametrize("obj", [False, True])
+def test_meshcreator_facade_writes_the_reference_file(tmp_path, oracle, color, obj):
+    """MeshCreator (facade, GPU index passes + threaded text) writes byte for byte what the reference's
+    exportPlyMesh / exportObjMesh write (Duke/meshcreator.cpp:16-166): golden fixture + the oracle on a larger cloud."""
+    import ctypes as C
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import cases
+    duke = C.CDLL(os.path.join(ROOT, "structure-light-reconstructor_b200", "libduke_b200.so"))
+    golden = dict(np.load(os.path.join(ROOT, "tests", "golden", "ref_mesh.npz")))
+
+    def export(pts, cnt, col, path):
+        h, w = cnt.shape
+        ci = None if col is None else np.ascontiguousarray(col, np.int32)
+        nv, nf = C.c_ulonglong(0), C.c_ulonglong(0)
+        rc = duke.duke_export_mesh(C.c_void_p(pts.ctypes.data), C.c_void_p(cnt.ctypes.data),
+                                   C.c_void_p(ci.ctypes.data) if ci is not None else None, w, h, int(obj),
+                                   str(path).encode(), C.byref(nv), C.byref(nf))
+        assert rc == 0
+        return nv.value, nf.value
+
+    pts, cnt, col = cases.mesh_cloud(color=color)
+    # the hook re-adds points one by one (count[q] addPoint calls): make the sums what that produces
+    export(pts, cnt, col, tmp_path / "a.txt")
+    want = golden[f"{'c' if color else 'n'}_{'obj' if obj else 'ply'}"].tobytes()
+    assert open(tmp_path / "a.txt", "rb").read() == want
+
+    rng = np.random.default_rng(77)
+    h, w = 300, 417
+    cnt = ((rng.random((h, w)) < 0.8) * 1).astype(np.uint8)
+    pts = (rng.normal(0, 500, (h, w, 3)) * cnt[..., None]).astype(np.float32)
+    col = rng.integers(0, 256, (h, w, 3)).astype(np.uint8) if color else None
+    nv, nf = export(pts, cnt, col, tmp_path / "b.txt")
+    oracle.export_mesh(pts, cnt, w, h, tmp_path / "o.txt", obj, None if col is None else col.astype(np.int32))
+    assert open(tmp_path / "b.txt", "rb").read() == open(tmp_path / "o.txt", "rb").read()
+    assert nv == int(cnt.sum()) and nf > 0

@@ -468,3 +468,50 @@ def test_wide_rows_take_the_plain_kernels_and_still_match_the_oracle(cuda_engine
     xyz_o, valid_o, k_o, n_o = oracle.run_mf(stack[0], cams, Q, nthreads=oracle.max_threads())
     assert (k[0].cpu().numpy() == k_o).all() and int(n.item()) == n_o and n_o > 1000
     assert (bits(xyz[0].cpu().numpy()) == bits(xyz_o)).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# K5: mesh indexing (MeshCreator's vertex numbering + faces, Duke/meshcreator.cpp:16-166)
+# ------------------------------------------------------------------------------------------------
+def _random_cloud(w, h, seed, fill=0.7):
+    rng = np.random.default_rng(seed)
+    count = ((rng.random((h, w)) < fill) * rng.integers(1, 4, (h, w))).astype(np.uint8)
+    pts = (rng.normal(0, 300, (h, w, 3)) * count[..., None]).astype(np.float32)
+    return pts, count
+
+
+@pytest.mark.parametrize("w,h,fill", [(29, 17, 0.7), (1, 1, 1.0), (5, 1, 1.0), (1, 7, 0.5), (64, 48, 0.0), (333, 257, 0.9),
+                                      (2048, 3, 0.6)])
+@pytest.mark.parametrize("first_vertex", [0, 1])
+def test_k5_mesh_index_vs_oracle(cuda_engine_factory, oracle, w, h, fill, first_vertex):
+    eng = cuda_engine_factory(64, 16)
+    pts, count = _random_cloud(w, h, 7 * w + h, fill)
+    if w * h > 1:
+        count[0, 0] = 1   # PLY numbering: vertex 0 exists and must read as "absent" when faces are formed
+    vert, src, faces = eng.mesh_index(_t(pts), _t(count), first_vertex)
+    vo, so, fo = oracle.mesh_index(pts, count, w, h, first_vertex)
+    assert vert.shape[0] == len(vo) and faces.shape[0] == len(fo)
+    assert (bits(vert.cpu().numpy()) == bits(vo)).all()
+    assert (src.cpu().numpy() == so).all()
+    assert (faces.cpu().numpy() == fo).all()
+
+
+def test_k5_mesh_index_full_frame_cloud(cuda_engine_factory, oracle):
+    """The mesh of a real 1280x1024 MF cloud: PointCloudImage(1280, 1024) filled as MFReconstruct does (F7 drop rule)."""
+    W, H = 1280, 1024
+    eng = cuda_engine_factory(W, H, 1)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    stack = eng.synth_mf(1, seed=5, integer_disparity=True, noise_dn=0.0)
+    xyz, valid, k, n = eng.run_mf(stack, black_thr=40)
+    sums, count = oracle.pointcloud_from_dense(xyz[0].cpu().numpy(), valid[0].cpu().numpy(), W, H)
+    for first_vertex in (0, 1):
+        vert, src, faces = eng.mesh_index(_t(sums), _t(count), first_vertex)
+        vo, so, fo = oracle.mesh_index(sums, count, W, H, first_vertex)
+        assert len(vo) > 0.5 * 1024 * 1024 and len(fo) > len(vo)
+        assert (bits(vert.cpu().numpy()) == bits(vo)).all() and (src.cpu().numpy() == so).all()
+        assert (faces.cpu().numpy() == fo).all()
+    # size-independent properties: vertex numbers are 0/1-based ranks, every face references existing vertices,
+    # face count never exceeds two per pixel
+    f = faces.cpu().numpy()
+    assert f.min() >= 1 and f.max() <= len(vo) and len(f) <= 2 * W * H

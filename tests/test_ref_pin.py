@@ -161,6 +161,31 @@ def test_geometry_helpers_match_reference(oracle):
     assert g["pc_cnt"][3, 2] == (300 + int(((g["pc_iw"][300:] == 2) & (g["pc_jh"][300:] == 3)).sum())) % 256
 
 
+@pytest.mark.parametrize("tag,color", [("c", True), ("n", False)])
+@pytest.mark.parametrize("obj", [False, True])
+def test_mesh_export_matches_reference(oracle, tmp_path, tag, color, obj):
+    """MeshCreator::exportPlyMesh / exportObjMesh (Duke/meshcreator.cpp:16-166): the oracle writes the same bytes."""
+    g = golden("mesh")
+    pts, cnt, col = cases.mesh_cloud(color=color)
+    h, w = cnt.shape
+    path = tmp_path / "m.txt"
+    oracle.export_mesh(pts, cnt, w, h, path, obj, None if col is None else col.astype(np.int32))
+    want = g[f"{tag}_{'obj' if obj else 'ply'}"].tobytes()
+    assert open(path, "rb").read() == want
+    if ref_lib.available():                       # live: the reference's own MeshCreator, now
+        rp = tmp_path / "r.txt"
+        ref_lib.load().export_mesh(pts, cnt, w, h, rp, obj, col)
+        assert open(rp, "rb").read() == want
+    # the index arrays agree with the text (vertex count in the header / number of "v" lines)
+    vert, src, faces = oracle.mesh_index(pts, cnt, w, h, 1 if obj else 0)
+    text = want.decode()
+    if obj:
+        assert text.count("\nv ") + text.startswith("v ") == len(vert) and text.count("\nf ") == len(faces)
+    else:
+        assert f"element vertex {len(vert)}\n" in text and f"element face {len(faces)}\n" in text
+    assert len(vert) == int((cnt > 0).sum())
+
+
 @pytest.mark.skipif(not ref_lib.available(), reason="oracle/_ref/libref.so only exists where /root/reference is mounted")
 def test_fixtures_are_what_the_reference_computes_now():
     """Re-run the reference's code and require the committed fixtures to be current."""
