@@ -141,6 +141,33 @@ def main():
     del g, col, gm
     eng.close()
 
+    # ---------------- BASELINE configs 4 and 5: larger frames through slr_run_mf ----------------
+    for (Wc, Hc, Fc, Sc, Bc, mode, label) in [(2048, 1536, 3, 4, 4, slr_b200.MODE_STRICT, "config 4: 2048x1536, 3x4, strict, one CTA per SM"),
+                                               (4096, 3000, 4, 8, 2, slr_b200.MODE_CORRECTED, "config 5: 4096x3000, 4x8, corrected, K1 + plain K3a")]:
+        ec = slr_b200.Engine(Wc, Hc, max_batch=Bc)
+        camsc, Qc = slr_b200.synthetic_rig(Wc, Hc)
+        ec.set_calib(camsc, Qc)
+        Nc = 2 + Fc * Sc
+        if Fc == 3 and Sc == 4:
+            stc = ec.synth_mf(Bc, seed=3, integer_disparity=True, noise_dn=0.0)
+        else:   # no reference pattern set exists for 4x8: smooth synthetic fringes generated on the device
+            xs_ = torch.arange(Wc, device="cuda", dtype=torch.float32)[None, None, :] / Wc
+            stc = torch.empty((Bc, 2, Nc, Hc, Wc), dtype=torch.uint8, device="cuda")
+            stc[:, :, 0] = 220
+            stc[:, :, 1] = 10
+            for f_, fr in enumerate([70, 64, 59, 56][:Fc]):   # differences 6,5,3 -> 1,2 -> one beat period over the row
+                for s_ in range(Sc):
+                    for cam in range(2):
+                        v = 128 + 90 * torch.cos(2 * np.pi * fr * (xs_ + 0.013 - 0.01 * cam) + 2 * np.pi * s_ / Sc)
+                        stc[:, cam, 2 + Sc * f_ + s_] = v.to(torch.uint8)
+        outc = ec._outputs(Bc, want_k=False)
+        ms = timed(lambda: ec.run_mf(stc, F=Fc, S=Sc, mode=mode, out=outc))
+        rows_before = len(rows)
+        report(f"slr_run_mf ({label}, {Bc} scans)", "MFReconstruct::runReconstruction - IO", ms,
+               Bc * (2 * Wc * Hc * Nc + Wc * Hc * 13), None, Bc * Wc * Hc, "pixels")
+        del stc, outc
+        ec.close()
+
     # ---------------- config 1: 640x480 Gray decode only ----------------
     W1, H1 = 640, 480
     e1 = slr_b200.Engine(W1, H1, max_batch=B)

@@ -1,0 +1,3 @@
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python scratch/cfg5.py 2>&1 | tail -5
+timeout 300 python bench_kernels.py --no-cpu 2>/dev/null | grep -E "corrected|config"

@@ -6,7 +6,8 @@
 // scans k linearly (O(W^2) per row).  Here each persistent CTA owns one row at a time:
 //   1. the L/R phase + mask rows arrive in shared memory by TMA bulk copies (cp.async.bulk +
 //      mbarrier), double buffered so the next row streams in while this one is matched;
-//   2. the right row is hashed by phase bucket (width 1/8 > 0.1) into chained lists in smem;
+//   2. the right row is hashed by phase bucket (width 1/8 > 0.1) into chained lists in smem, pushed in
+//      descending column blocks so that chains are ordered by block and walks can stop early;
 //   3. each left pixel probes the three buckets that can hold a match, applies the exact
 //      predicate and keeps the minimum k  ==  the reference's "first k" (exact, not approximate);
 //   4. matched pixels are reprojected with Q in fp64 using the precomputed undistortPoints maps,
@@ -87,12 +88,17 @@ k3a_phase_match(const K3aParams p)
         const uint8_t *mR = st + 9 * W;
         __syncthreads();
 
-        // hash the right row: chained lists keyed by phase bucket
-        for (int k = tid; k < W; k += K3_THREADS) {
-            if (mR[k]) {
+        // hash the right row: chained lists keyed by phase bucket.  Columns are pushed in descending blocks of
+        // K3_THREADS (one barrier per block), so every chain lists block 0's columns first, then block 1's, ...:
+        // a walk can stop at the first entry of a later block than its best match (rows whose phases repeat
+        // hundreds of times would otherwise cost a full chain per left pixel)
+        for (int kb = (W - 1) / K3_THREADS; kb >= 0; kb--) {
+            const int k = kb * K3_THREADS + tid;
+            if (k < W && mR[k]) {
                 const int slot = slr::phase_bucket(pR[k]) & (HB - 1);
                 next[k] = atomicExch(&head[slot], k);
             }
+            __syncthreads();
         }
         if (tid == 0) slr::tma_store_wait_read<0>();  // previous row's staged outputs have left smem
         __syncthreads();
@@ -109,6 +115,7 @@ k3a_phase_match(const K3aParams p)
                 for (int db = -1; db <= 1; db++) {
                     int k = head[(b0 + db) & (HB - 1)];
                     while (k >= 0) {
+                        if (best != INT_MAX && k / K3_THREADS > best / K3_THREADS) break;  // only later blocks follow
                         if (slr::phase_match(pl, pR[k])) best = min(best, k);
                         k = next[k];
                     }
