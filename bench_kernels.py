@@ -97,6 +97,13 @@ def main():
     c = cpu_time(lambda: orc.run_mf(h_mf[0], cams, Q, nthreads=nthreads)) if orc else None
     report("k_fused_mf (strict)", "MFReconstruct::runReconstruction - IO", ms, B * (2 * P * 14 + P * 13), c, B * P, "pixels")
 
+    out1 = eng._outputs(1, want_k=False)
+    mf1 = mf[:1].contiguous()
+    ms1 = timed(lambda: eng.run_mf(mf1, out=out1))
+    rows_before = len(rows)
+    report("k_fused_mf (strict), ONE scan: latency", "same, single scan (launch + 7 rows per CTA)", ms1, 2 * P * 14 + P * 13, c, P, "pixels")
+    rows[rows_before]["speedup_vs_cpu_port"] = (c / (ms1 * 1e-3)) if c else None
+
     ms = timed(lambda: eng.run_mf(mf, mode=slr_b200.MODE_CORRECTED, out=out))
     c = cpu_time(lambda: orc.run_mf(h_mf[0], cams, Q, mode=1, nthreads=nthreads)) if orc else None
     report("k_fused_mf (corrected)", "(no reference counterpart)", ms, B * (2 * P * 14 + P * 13), c, B * P, "pixels")

@@ -39,7 +39,7 @@ slr_status slr_unfused_ge(slr_engine *e, const uint8_t *d_stack, int batch, int 
 
 namespace {
 
-constexpr int FUSED_MAX_THREADS = 512;
+constexpr int FUSED_MAX_THREADS = 1024;   // one CTA per SM (rows too wide for two row contexts): 64 registers as well
 constexpr uint32_t KEY_EMPTY = 0xFFFFFFFFu;
 constexpr int MODE_PHASE_INPUT = 2;  // rows of already decoded phase + mask (slr_match_triangulate_phase) instead of images
 
@@ -72,7 +72,7 @@ constexpr int DBG_ROWS = 8, DBG_PTS = 7, DBG_SKIP = 4;
 #define SLR_STAMP(pt)                                                                                          \
     do {                                                                                                       \
         __syncwarp();                                                                                          \
-        if (lane == 0 && it >= DBG_SKIP && it < DBG_SKIP + DBG_ROWS)                                            \
+        if (lane == 0 && tid < 512 && it >= DBG_SKIP && it < DBG_SKIP + DBG_ROWS)                                          \
             p.dbg[(((size_t)blockIdx.x * DBG_ROWS + (it - DBG_SKIP)) * 16 + (tid >> 5)) * DBG_PTS + (pt)] = clock64(); \
     } while (0)
 #else
@@ -618,7 +618,7 @@ static slr_status launch_fused(slr_engine *e, int mode, const uint8_t *d_stack, 
     // the shared-memory and fp64 latencies of the match phase; narrow rows get one thread per 4-pixel chunk.
     const bool two = 2 * (smem + 1024) <= 228 * 1024;
     int threads = (W / 2 + 31) / 32 * 32;   // one 4-pixel decode task per thread, or the widest CTA
-    if (threads > FUSED_MAX_THREADS) threads = FUSED_MAX_THREADS;
+    if (threads > (two ? 512 : FUSED_MAX_THREADS)) threads = two ? 512 : FUSED_MAX_THREADS;
     if (threads < 64) threads = 64;
     if (const char *ev = getenv("SLR_FUSED_THREADS")) {  // tuning knob (bench experiments)
         const int t = atoi(ev);
@@ -669,8 +669,10 @@ static slr_status launch_fused(slr_engine *e, int mode, const uint8_t *d_stack, 
         SLR_PICK(384, 2)
     } else if (two) {
         SLR_PICK(512, 2)
+    } else if (threads <= 512) {
+        SLR_PICK(512, 1)
     } else {
-        SLR_PICK(FUSED_MAX_THREADS, 1)
+        SLR_PICK(1024, 1)
     }
 #undef SLR_PICK
 #undef SLR_PICK_Q
