@@ -8,6 +8,9 @@
 
 #include <string>
 
+#include <chrono>
+
+#include "meshcreator.h"
 #include "mfreconstruct.h"
 #include "reconstruct.h"
 
@@ -37,6 +40,24 @@ static void dump(const char *path, PointCloudImage *pc, stereoRect *sr)
     fclose(f);
 }
 
+static double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// MainWindow::startreconstruct's export step (mainwindow.cpp:637-646): <project>/reconstruction/<sn>.ply when the
+// environment variable DUKE_EXPORT_PLY names a file
+static void maybe_export(PointCloudImage *pc)
+{
+    const char *path = getenv("DUKE_EXPORT_PLY");
+    if (!path) return;
+    const double t0 = now_ms();
+    MeshCreator mc(pc);
+    mc.exportPlyMesh(path);
+    fprintf(stderr, "[facade_demo] exportPlyMesh: %llu vertices, %llu faces, %.1f ms\n", mc.vertexCount(), mc.faceCount(),
+            now_ms() - t0);
+}
+
 int main(int argc, char **argv)
 {
     if (argc != 12) {
@@ -49,7 +70,14 @@ int main(int argc, char **argv)
     if (kind == "mf") {
         MFReconstruct *mfr = new MFReconstruct();
         mfr->getParameters(sn, scanw, scanh, camw, camh, black, white, project);
-        if (!mfr->runReconstruction()) return 1;
+        const int repeat = getenv("DUKE_REPEAT") ? atoi(getenv("DUKE_REPEAT")) : 1;   // later calls reuse context + engine
+        for (int rep = 0; rep < repeat; rep++) {
+            const double t0 = now_ms();
+            if (!mfr->runReconstruction()) return 1;
+            fprintf(stderr, "[facade_demo] MFReconstruct::runReconstruction #%d (image files -> PointCloudImage): %.1f ms\n", rep,
+                    now_ms() - t0);
+        }
+        maybe_export(mfr->points3DProjView);
         dump(argv[11], mfr->points3DProjView, mfr->rectifier());
         printf("mf: %llu points\n", mfr->pointCount());
         delete mfr;
@@ -63,8 +91,12 @@ int main(int argc, char **argv)
         r->setBlackThreshold(black);
         r->setWhiteThreshold(white);
         r->disableRaySampling();
+        const double t0 = now_ms();
         const bool ok = (kind == "ge") ? r->runReconstruction_GE() : r->runReconstruction();
         if (!ok) return 1;
+        fprintf(stderr, "[facade_demo] Reconstruct::runReconstruction%s (image files -> PointCloudImage): %.1f ms\n",
+                kind == "ge" ? "_GE" : "", now_ms() - t0);
+        maybe_export(r->points3DProjView);
         dump(argv[11], r->points3DProjView, kind == "ge" ? r->rectifier() : nullptr);
         delete r;
     }

@@ -7,6 +7,7 @@
 #include <thread>
 #include <vector>
 
+#include "reconstruct_common.h"
 #include "slr_b200.h"
 
 MeshCreator::MeshCreator(PointCloudImage *in) : cloud(in), w(in->getWidth()), h(in->getHeight()) {}
@@ -62,15 +63,14 @@ bool MeshCreator::exportMesh(const std::string &path, bool obj)
     std::vector<int32_t> src(px), faces(px * 6);
     unsigned long long counts[2] = {0, 0};
 
-    slr_engine *eng = nullptr;
-    if (slr_create(&eng, 0, w, h, 1) != SLR_OK) {
+    slr_engine *eng = duke::shared_engine(0, w, h);
+    if (!eng) {
         fprintf(stderr, "MeshCreator: %s\n", slr_last_error());
         return false;
     }
     const slr_status st = slr_mesh_index_host(eng, cloud->sums().data(), cloud->counts().data(), w, h, obj ? 1 : 0,
                                               vert.data(), src.data(), faces.data(), counts);
     if (st != SLR_OK) fprintf(stderr, "MeshCreator: %s\n", slr_last_error());
-    slr_destroy(eng);
     if (st != SLR_OK) return false;
     const size_t nv = (size_t)counts[0], nf = (size_t)counts[1];
 

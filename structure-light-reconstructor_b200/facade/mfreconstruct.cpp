@@ -1,5 +1,7 @@
 #include "mfreconstruct.h"
 
+#include <chrono>
+
 #include <stdio.h>
 
 #include "reconstruct_common.h"
@@ -65,10 +67,20 @@ bool MFReconstruct::runReconstruction()
     }
     const int W = cameraWidth, H = cameraHeight;
     const size_t P = (size_t)W * H;
+    // DUKE_TIMING=1: where the wall time of a drop-in call goes (stderr)
+    const bool timing = getenv("DUKE_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_prev = now();
+    auto lap = [&](const char *what) {
+        const double t = now();
+        if (timing) fprintf(stderr, "[MFReconstruct] %-34s %8.1f ms\n", what, t - t_prev);
+        t_prev = t;
+    };
     sr->calParameters();
+    lap("stereoRect::calParameters (host)");
 
-    slr_engine *eng = nullptr;
-    if (slr_create(&eng, device, W, H, 1) != SLR_OK) {
+    slr_engine *eng = duke::shared_engine(device, W, H);
+    if (!eng) {
         fprintf(stderr, "MFReconstruct: %s\n", slr_last_error());
         return false;
     }
@@ -84,27 +96,27 @@ bool MFReconstruct::runReconstruction()
         if (slr_set_calib(eng, cams, sr->Q.v.data(), rg) != SLR_OK) break;
         if (slr_set_rectify_maps(eng, sr->map1().data(), sr->map2().data()) != SLR_OK) break;
         if (slr_set_host_input_raw(eng, 1) != SLR_OK) break;
-        if (slr_host_alloc(&h_stack, 2 * (size_t)numberOfImgs * P) != SLR_OK) break;
-        if (slr_host_alloc(&h_xyz, P * 3 * sizeof(float)) != SLR_OK) break;
-        if (slr_host_alloc(&h_valid, P) != SLR_OK) break;
+        if (!(h_stack = duke::pinned_scratch(0, 2 * (size_t)numberOfImgs * P))) break;
+        if (!(h_xyz = duke::pinned_scratch(1, P * 3 * sizeof(float)))) break;
+        if (!(h_valid = duke::pinned_scratch(2, P))) break;
+        lap("CUDA context + engine + calib + pinned");
         bool loaded = true;
         for (int i = 0; i < 2 && loaded; i++)
             loaded = duke::load_stack(scanFolder[i], imgPrefix[i], imgSuffix, numberOfImgs, W, H,
                                       (uint8_t *)h_stack + (size_t)i * numberOfImgs * P);
         if (!loaded) break;
+        lap("image files -> pinned stack");
         n_points_ = 0;
         if (slr_run_mf_host(eng, (const uint8_t *)h_stack, 1, 3, 4, blackThreshold, mode, (float *)h_xyz, (uint8_t *)h_valid,
                             nullptr, &n_points_) != SLR_OK)
             break;
+        lap("slr_run_mf_host (H2D, K0, fused, D2H)");
         delete points3DProjView;
         points3DProjView = new PointCloudImage(scan_w, scan_h, false);
         points3DProjView->addDense((const float *)h_xyz, (const uint8_t *)h_valid, nullptr, W, H);
+        lap("PointCloudImage::addDense");
         ok = true;
     } while (false);
     if (!ok && slr_last_error()[0]) fprintf(stderr, "MFReconstruct: %s\n", slr_last_error());
-    slr_host_free(h_stack);
-    slr_host_free(h_xyz);
-    slr_host_free(h_valid);
-    slr_destroy(eng);
-    return ok;
+    return ok;   // engine and pinned buffers stay with the process (reconstruct_common.h)
 }

@@ -3,6 +3,7 @@
 #include <math.h>
 
 #include <fstream>
+#include <thread>
 
 PointCloudImage::PointCloudImage(int imageW, int imageH, bool colorFlag)
     : w(imageW), h(imageH), has_color_(colorFlag), points_((size_t)imageW * imageH * 3, 0.0f), num_((size_t)imageW * imageH, 0)
@@ -91,16 +92,28 @@ bool PointCloudImage::addPoint(int i_w, int j_h, duke::Point3f point)
 
 void PointCloudImage::addDense(const float *xyz, const uint8_t *valid, const uint8_t *gray, int W, int H)
 {
-    for (int i = 0; i < H; i++)
-        for (int j = 0; j < W; j++) {
-            const size_t p = (size_t)i * W + j;
-            if (!valid[p]) continue;
-            const duke::Point3f pt(xyz[p * 3], xyz[p * 3 + 1], xyz[p * 3 + 2]);
-            if (gray && has_color_)
-                addPoint(i, j, pt, duke::Vec3i(gray[p], gray[p], gray[p]));
-            else
-                addPoint(i, j, pt);
-        }
+    // addPoint(i, j, p) lands in cell (i_w = i, j_h = j): image rows map to distinct cells, so bands of rows can be
+    // filled by different host threads and every cell still sees its additions in the reference's order
+    auto band = [&](int i0, int i1) {
+        for (int i = i0; i < i1; i++)
+            for (int j = 0; j < W; j++) {
+                const size_t p = (size_t)i * W + j;
+                if (!valid[p]) continue;
+                const duke::Point3f pt(xyz[p * 3], xyz[p * 3 + 1], xyz[p * 3 + 2]);
+                if (gray && has_color_)
+                    addPoint(i, j, pt, duke::Vec3i(gray[p], gray[p], gray[p]));
+                else
+                    addPoint(i, j, pt);
+            }
+    };
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    if (nt > 16) nt = 16;
+    if ((size_t)W * H < 65536) nt = 1;
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nt; t++) pool.emplace_back(band, (int)((long long)H * t / nt), (int)((long long)H * (t + 1) / nt));
+    band(0, (int)((long long)H / nt));
+    for (auto &t : pool) t.join();
 }
 
 void PointCloudImage::exportXYZ(const char *path, bool exportOffPixels, bool colorFlag)

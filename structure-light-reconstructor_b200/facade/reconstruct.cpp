@@ -109,8 +109,8 @@ bool Reconstruct::runReconstruction_GE()
         cameras[i].height = H;
     }
     sr->calParameters();
-    slr_engine *eng = nullptr;
-    if (slr_create(&eng, device, W, H, 1) != SLR_OK) {
+    slr_engine *eng = duke::shared_engine(device, W, H);
+    if (!eng) {
         fprintf(stderr, "Reconstruct: %s\n", slr_last_error());
         return false;
     }
@@ -124,10 +124,10 @@ bool Reconstruct::runReconstruction_GE()
         if (slr_set_calib(eng, cams, sr->Q.v.data(), rg) != SLR_OK) break;
         if (slr_set_rectify_maps(eng, sr->map1().data(), sr->map2().data()) != SLR_OK) break;
         if (slr_set_host_input_raw(eng, 1) != SLR_OK) break;
-        if (slr_host_alloc(&h_stack, 2 * (size_t)nimg * P) != SLR_OK) break;
-        if (slr_host_alloc(&h_xyz, P * 3 * sizeof(float)) != SLR_OK) break;
-        if (slr_host_alloc(&h_valid, P) != SLR_OK) break;
-        if (haveColor && slr_host_alloc(&h_color, P) != SLR_OK) break;
+        if (!(h_stack = duke::pinned_scratch(0, 2 * (size_t)nimg * P))) break;
+        if (!(h_xyz = duke::pinned_scratch(1, P * 3 * sizeof(float)))) break;
+        if (!(h_valid = duke::pinned_scratch(2, P))) break;
+        if (haveColor && !(h_color = duke::pinned_scratch(3, P))) break;
         bool loaded = true;
         for (int i = 0; i < 2 && loaded; i++)
             loaded = duke::load_stack(scanFolder[i], imgPrefix[i], imgSuffix, nimg, W, H, (uint8_t *)h_stack + (size_t)i * nimg * P);
@@ -142,12 +142,7 @@ bool Reconstruct::runReconstruction_GE()
         ok = true;
     } while (false);
     if (!ok && slr_last_error()[0]) fprintf(stderr, "Reconstruct: %s\n", slr_last_error());
-    slr_host_free(h_stack);
-    slr_host_free(h_xyz);
-    slr_host_free(h_valid);
-    slr_host_free(h_color);
-    slr_destroy(eng);
-    return ok;
+    return ok;   // engine and pinned buffers stay with the process (reconstruct_common.h)
 }
 
 bool Reconstruct::runReconstruction()
@@ -166,8 +161,8 @@ bool Reconstruct::runReconstruction()
         cameras[i].width = W;
         cameras[i].height = H;
     }
-    slr_engine *eng = nullptr;
-    if (slr_create(&eng, device, W, H, 1) != SLR_OK) {
+    slr_engine *eng = duke::shared_engine(device, W, H);
+    if (!eng) {
         fprintf(stderr, "Reconstruct: %s\n", slr_last_error());
         return false;
     }
@@ -182,6 +177,7 @@ bool Reconstruct::runReconstruction()
         const float *rg = nullptr;
         if (scanSN > 0 && duke::load_rigid(savePath_ + "/scan/transfer_mat" + std::to_string(scanSN) + ".txt", rigid)) rg = rigid;
         if (slr_set_calib(eng, cams, Qid, rg) != SLR_OK) break;
+        if (slr_set_host_input_raw(eng, 0) != SLR_OK) break;   // the shared engine may have rectified for a GE / MF scan
         bool loaded = true;
         for (int i = 0; i < 2 && loaded; i++)
             loaded = duke::load_stack(scanFolder[i], imgPrefix[i], imgSuffix, nimg, W, H, stack.data() + (size_t)i * nimg * P);
@@ -204,6 +200,5 @@ bool Reconstruct::runReconstruction()
         ok = true;
     } while (false);
     if (!ok && slr_last_error()[0]) fprintf(stderr, "Reconstruct: %s\n", slr_last_error());
-    slr_destroy(eng);
     return ok;
 }

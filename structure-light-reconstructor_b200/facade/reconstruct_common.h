@@ -19,6 +19,14 @@ slr_camera to_slr_camera(const VirtualCamera &vc);
 bool load_stack(const std::string &folder, const std::string &prefix, const std::string &suffix, int n, int W, int H,
                 uint8_t *dst);
 
+// Process-wide engine for (device, W, H): created on first use and kept, so that only the first reconstruction of a
+// session pays for CUDA context creation (~0.5 s) and the device / pinned allocations.  The reference news a
+// reconstructor per scan (mainwindow.cpp:577-649) on one GUI thread; so do the facades, which is why a plain
+// mutex-protected cache is enough.  Returns nullptr (slr_last_error() says why) when no engine can be created.
+slr_engine *shared_engine(int device, int W, int H);
+// Grow-only pinned host buffers shared by the facades (slot 0 image stack, 1 xyz / sums, 2 valid / counts, 3 colour)
+void *pinned_scratch(int slot, size_t bytes);
+
 // 3x4 matrix of scan/transfer_mat<sn>.txt (mfreconstruct.cpp:276-282); false if unreadable
 bool load_rigid(const std::string &path, float out[12]);
 

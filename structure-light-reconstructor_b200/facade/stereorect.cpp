@@ -1,5 +1,8 @@
 #include "stereorect.h"
 
+#include <mutex>
+#include <thread>
+
 #include <fstream>
 
 #include "rectify.h"
@@ -18,23 +21,45 @@ void stereoRect::getParameters()
     loaded_ = ok;
 }
 
+namespace {
+// The reference recomputes stereoRectify + both map pairs on every loadCamImgs (mfreconstruct.cpp:117): a pure
+// function of the six calibration matrices and the image size, so the last result is kept for the process.
+struct CalCache {
+    std::vector<double> key;
+    duke::RectifyResult r;
+    std::vector<int16_t> map1;
+    std::vector<uint16_t> map2;
+};
+std::mutex g_cal_mu;
+CalCache g_cal;
+}  // namespace
+
 void stereoRect::calParameters()
 {
     if (!loaded_) return;
-    duke::RectifyResult r = duke::stereo_rectify(M1, D1, M2, D2, img_size, R, T);
-    R1 = r.R1;
-    R2 = r.R2;
-    P1 = r.P1;
-    P2 = r.P2;
-    Q = r.Q;
-    std::vector<int16_t> a1, b1;
-    std::vector<uint16_t> a2, b2;
-    duke::init_undistort_rectify_map(M1, D1, R1, P1, img_size, a1, a2);
-    duke::init_undistort_rectify_map(M2, D2, R2, P2, img_size, b1, b2);
-    map1_ = a1;
-    map1_.insert(map1_.end(), b1.begin(), b1.end());
-    map2_ = a2;
-    map2_.insert(map2_.end(), b2.begin(), b2.end());
+    std::vector<double> key = {(double)img_size.width, (double)img_size.height};
+    for (const duke::Matrix *m : {&M1, &D1, &M2, &D2, &R, &T}) key.insert(key.end(), m->v.begin(), m->v.end());
+    std::lock_guard<std::mutex> lk(g_cal_mu);
+    if (g_cal.key != key) {
+        g_cal.r = duke::stereo_rectify(M1, D1, M2, D2, img_size, R, T);
+        std::vector<int16_t> a1, b1;
+        std::vector<uint16_t> a2, b2;
+        std::thread right([&] { duke::init_undistort_rectify_map(M2, D2, g_cal.r.R2, g_cal.r.P2, img_size, b1, b2); });
+        duke::init_undistort_rectify_map(M1, D1, g_cal.r.R1, g_cal.r.P1, img_size, a1, a2);
+        right.join();
+        g_cal.map1 = a1;
+        g_cal.map1.insert(g_cal.map1.end(), b1.begin(), b1.end());
+        g_cal.map2 = a2;
+        g_cal.map2.insert(g_cal.map2.end(), b2.begin(), b2.end());
+        g_cal.key = key;
+    }
+    R1 = g_cal.r.R1;
+    R2 = g_cal.r.R2;
+    P1 = g_cal.r.P1;
+    P2 = g_cal.r.P2;
+    Q = g_cal.r.Q;
+    map1_ = g_cal.map1;
+    map2_ = g_cal.map2;
 }
 
 void stereoRect::doStereoRectify(duke::Image &img, bool isleft)

@@ -73,10 +73,13 @@ def make_project(tmp, W, H, sn, stacks, rigid=None):
     return [cams["left"], cams["right"]]
 
 
-def run_demo(kind, tmp, sn, scan_w, scan_h, W, H, black, white, color):
+def run_demo(kind, tmp, sn, scan_w, scan_h, W, H, black, white, color, ply=None):
     out = os.path.join(tmp, "out.bin")
+    env = dict(os.environ)
+    if ply:
+        env["DUKE_EXPORT_PLY"] = ply      # the caller's export step (MeshCreator, mainwindow.cpp:637-646)
     r = subprocess.run([DEMO, kind, tmp, str(sn), str(scan_w), str(scan_h), str(W), str(H), str(black), str(white),
-                        str(int(color)), out], capture_output=True, text=True, timeout=120)
+                        str(int(color)), out], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stderr + r.stdout
     buf = open(out, "rb").read()
     w, h = struct.unpack_from("<ii", buf, 0)
@@ -112,7 +115,11 @@ def test_mfreconstruct_facade_end_to_end(tmp_path, oracle, sn, rigid):
     scan_w, scan_h = 320, 64        # as in the reference's defaults scan == camera size: F7 drops columns >= scan_h
     stacks = synth.synth_mf(W, H, seed=61, noise_dn=1.0)
     cams = make_project(str(tmp_path), W, H, sn, stacks, rigid)
-    sums, cnt, Q, m1, m2, probes = run_demo("mf", str(tmp_path), sn, scan_w, scan_h, W, H, 40, 0, False)
+    ply = str(tmp_path / "cloud.ply")
+    sums, cnt, Q, m1, m2, probes = run_demo("mf", str(tmp_path), sn, scan_w, scan_h, W, H, 40, 0, False, ply=ply)
+    # startreconstruct's last step: MeshCreator(points3DProjView).exportPlyMesh == the reference's file for this cloud
+    oracle.export_mesh(sums, cnt, scan_w, scan_h, tmp_path / "oracle.ply", False, None)
+    assert open(ply, "rb").read() == open(tmp_path / "oracle.ply", "rb").read()
     rect = np.stack([[oracle.remap_linear(stacks[c, i], m1[c], m2[c]) for i in range(14)] for c in range(2)])
     xyz, valid, k, n = oracle.run_mf(rect, cams, Q, rigid=f32(rigid) if rigid else None)
     pts_o, cnt_o = oracle.pointcloud_from_dense(xyz, valid, scan_w, scan_h)
