@@ -722,6 +722,9 @@ slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch,
     else
         SLR_REQUIRE(mode == SLR_MODE_CORRECTED && F >= 1 && F <= 8 && S >= 3 && S <= 16,
                     "corrected mode supports 1<=F<=8, 3<=S<=16; got mode %d F=%d S=%d", mode, F, S);
+    if (e->W % 16 != 0)   // TMA rows need 16-byte multiples: zero-padded copies on a child engine (slr_engine.cu)
+        return slr_padded_run(e, 0, d_stack, nullptr, batch, 2 + F * S, F, S, black_thr, mode, 0, d_xyz, d_valid, d_match_k,
+                              nullptr, d_n_points);
     bool handled = false;
     slr_status st = launch_fused(e, mode, d_stack, nullptr, nullptr, batch, F, S, black_thr, d_xyz, d_valid, d_match_k,
                                  d_n_points, &handled);
@@ -743,6 +746,9 @@ slr_status slr_launch_fused_ge(slr_engine *e, const uint8_t *d_stack, int batch,
                                int white_thr, int scan_w, int have_color, float *d_xyz, uint8_t *d_valid,
                                int32_t *d_match_k, uint8_t *d_color, unsigned long long *d_n_points)
 {
+    if (e->W % 16 != 0)
+        return slr_padded_run(e, 1, d_stack, nullptr, batch, 2 + 2 * nbits_col, nbits_col, black_thr, white_thr, scan_w,
+                              have_color, d_xyz, d_valid, d_match_k, have_color ? d_color : nullptr, d_n_points);
     return slr_unfused_ge(e, d_stack, batch, nbits_col, black_thr, white_thr, scan_w, have_color, d_xyz, d_valid,
                           d_match_k, d_color, d_n_points);
 }

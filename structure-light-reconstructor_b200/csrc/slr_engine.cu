@@ -46,6 +46,12 @@ static void free_engine(slr_engine *e)
     cudaFree(e->d_mesh_src);
     cudaFree(e->d_mesh_faces);
     cudaFree(e->d_mesh_counts);
+    for (int i = 0; i < 6; i++) cudaFree(e->d_pad[i]);
+    if (e->child) {
+        e->child->stream = e->child->own_stream;
+        slr_destroy(e->child);
+        e->child = nullptr;
+    }
     cudaFree(e->d_phase);
     cudaFree(e->d_code);
     cudaFree(e->d_mask);
@@ -188,6 +194,7 @@ extern "C" slr_status slr_set_calib(slr_engine *e, const slr_camera cams[2], con
     slr_status st = slr_launch_undistort_maps(e);
     if (st != SLR_OK) return st;
     e->calib_set = true;
+    e->calib_version++;
     return SLR_OK;
 }
 
@@ -307,6 +314,8 @@ extern "C" slr_status slr_match_triangulate_phase(slr_engine *e, const float *d_
         slr_set_error("slr_match_triangulate_phase: call slr_set_calib first");
         return SLR_ERR_STATE;
     }
+    if (e->W % 16 != 0)
+        return slr_padded_run(e, 2, d_phase, d_mask, batch, 1, 0, 0, 0, 0, 0, d_xyz, d_valid, d_match_k, nullptr, d_n_points);
     return slr_launch_match_phase(e, d_phase, d_mask, batch, d_xyz, d_valid, d_match_k, d_n_points);
 }
 
@@ -321,6 +330,11 @@ extern "C" slr_status slr_match_triangulate_code(slr_engine *e, const int32_t *d
     if (!e->calib_set) {
         slr_set_error("slr_match_triangulate_code: call slr_set_calib first");
         return SLR_ERR_STATE;
+    }
+    if (e->W % 16 != 0) {
+        SLR_REQUIRE(d_color == nullptr, "slr_match_triangulate_code: colour output needs an image width that is a multiple "
+                                        "of 16 (use slr_run_ge, which pads the whole stack); got %d", e->W);
+        return slr_padded_run(e, 3, d_col, d_mask, batch, 1, 0, 0, 0, 0, 0, d_xyz, d_valid, d_match_k, nullptr, d_n_points);
     }
     return slr_launch_match_code(e, d_col, d_mask, batch, d_white, (size_t)e->W * e->H, d_xyz, d_valid, d_match_k,
                                  d_color, d_n_points);
@@ -366,6 +380,91 @@ extern "C" slr_status slr_run_ge(slr_engine *e, const uint8_t *d_stack, int batc
     }
     return slr_launch_fused_ge(e, d_stack, batch, nbits_col, black_thr, white_thr, scan_w, have_color, d_xyz,
                                d_valid, d_match_k, d_color, d_n_points);
+}
+
+// ------------------------------------------------------------------------------------------------
+// widths that are not a multiple of 16
+// ------------------------------------------------------------------------------------------------
+// The match kernels move rows with TMA bulk copies (16-byte rows).  Other widths run on a child engine of the padded
+// width Wp over zero-padded device copies: padded columns have white == black == 0 (MF/GE stacks) or mask == 0
+// (phase / code rows), so they carry no phase or code, can never be matched and never match; column indices of real
+// pixels are unchanged.  Outputs are copied back row by row.  Costs one extra pass over the data, for odd widths only.
+static slr_status pad_buffer(slr_engine *e, int slot, size_t bytes)
+{
+    if (e->pad_bytes[slot] >= bytes) return SLR_OK;
+    cudaFree(e->d_pad[slot]);
+    e->d_pad[slot] = nullptr;
+    e->pad_bytes[slot] = 0;
+    SLR_CHECK_CUDA(cudaMalloc(&e->d_pad[slot], bytes));
+    e->pad_bytes[slot] = bytes;
+    return SLR_OK;
+}
+
+slr_status slr_padded_run(slr_engine *e, int kind, const void *d_in0, const uint8_t *d_in1, int batch, int planes,
+                          int a0, int a1, int a2, int a3, int a4, float *d_xyz, uint8_t *d_valid, int32_t *d_match_k,
+                          uint8_t *d_color, unsigned long long *d_n_points)
+{
+    const int W = e->W, H = e->H, Wp = (W + 15) & ~15;
+    if (!e->child) {
+        slr_status st = slr_create(&e->child, e->device, Wp, H, e->max_batch);
+        if (st != SLR_OK) return st;
+    }
+    slr_engine *c = e->child;
+    c->stream = e->stream;
+    if (c->calib_version == 0 || e->child_calib_version != e->calib_version) {
+        slr_status st = slr_set_calib(c, e->cams, e->calib.Q, e->calib.has_rigid ? e->calib.rigid : nullptr);
+        if (st != SLR_OK) return st;
+        e->child_calib_version = e->calib_version;
+    }
+    const size_t rows_in = (size_t)batch * 2 * planes * H, rows_out = (size_t)batch * H;
+    const size_t es0 = (kind <= 1) ? 1 : 4;   // element size of input 0: image bytes, or f32 phase / i32 code
+    slr_status st;
+    if ((st = pad_buffer(e, 0, rows_in * Wp * es0)) != SLR_OK) return st;
+    if (kind >= 2 && (st = pad_buffer(e, 1, rows_in * Wp)) != SLR_OK) return st;
+    if ((st = pad_buffer(e, 2, rows_out * Wp * 12)) != SLR_OK) return st;
+    if ((st = pad_buffer(e, 3, rows_out * Wp)) != SLR_OK) return st;
+    if (d_match_k && (st = pad_buffer(e, 4, rows_out * Wp * 4)) != SLR_OK) return st;
+    if (d_color && (st = pad_buffer(e, 5, rows_out * Wp)) != SLR_OK) return st;
+    cudaStream_t cs = e->stream;
+    // input 0 needs no defined padding for phase / code rows (their mask decides), image stacks need zeros
+    SLR_CHECK_CUDA(cudaMemsetAsync(e->d_pad[kind >= 2 ? 1 : 0], 0, rows_in * Wp * (kind >= 2 ? 1 : es0), cs));
+    if (kind >= 2) SLR_CHECK_CUDA(cudaMemsetAsync(e->d_pad[0], 0, rows_in * Wp * es0, cs));
+    SLR_CHECK_CUDA(cudaMemcpy2DAsync(e->d_pad[0], (size_t)Wp * es0, d_in0, (size_t)W * es0, (size_t)W * es0, rows_in,
+                                     cudaMemcpyDeviceToDevice, cs));
+    if (kind >= 2)
+        SLR_CHECK_CUDA(cudaMemcpy2DAsync(e->d_pad[1], Wp, d_in1, W, W, rows_in, cudaMemcpyDeviceToDevice, cs));
+    float *p_xyz = (float *)e->d_pad[2];
+    uint8_t *p_valid = (uint8_t *)e->d_pad[3];
+    int32_t *p_k = d_match_k ? (int32_t *)e->d_pad[4] : nullptr;
+    uint8_t *p_color = d_color ? (uint8_t *)e->d_pad[5] : nullptr;
+    const unsigned long long l0 = c->launches;
+    switch (kind) {
+    case 0:  // a0 = F, a1 = S, a2 = black_thr, a3 = mode
+        st = slr_launch_fused_mf(c, (const uint8_t *)e->d_pad[0], batch, a0, a1, a2, a3, p_xyz, p_valid, p_k, d_n_points);
+        break;
+    case 1:  // a0 = nbits_col, a1 = black_thr, a2 = white_thr, a3 = scan_w, a4 = have_color
+        st = slr_launch_fused_ge(c, (const uint8_t *)e->d_pad[0], batch, a0, a1, a2, a3, a4, p_xyz, p_valid, p_k, p_color,
+                                 d_n_points);
+        break;
+    case 2:
+        st = slr_launch_match_phase(c, (const float *)e->d_pad[0], (const uint8_t *)e->d_pad[1], batch, p_xyz, p_valid, p_k,
+                                    d_n_points);
+        break;
+    default:
+        st = slr_launch_match_code(c, (const int32_t *)e->d_pad[0], (const uint8_t *)e->d_pad[1], batch, nullptr, 0, p_xyz,
+                                   p_valid, p_k, nullptr, d_n_points);
+        break;
+    }
+    e->launches += c->launches - l0;
+    if (st != SLR_OK) return st;
+    SLR_CHECK_CUDA(cudaMemcpy2DAsync(d_xyz, (size_t)W * 12, p_xyz, (size_t)Wp * 12, (size_t)W * 12, rows_out,
+                                     cudaMemcpyDeviceToDevice, cs));
+    SLR_CHECK_CUDA(cudaMemcpy2DAsync(d_valid, W, p_valid, Wp, W, rows_out, cudaMemcpyDeviceToDevice, cs));
+    if (d_match_k)
+        SLR_CHECK_CUDA(cudaMemcpy2DAsync(d_match_k, (size_t)W * 4, p_k, (size_t)Wp * 4, (size_t)W * 4, rows_out,
+                                         cudaMemcpyDeviceToDevice, cs));
+    if (d_color) SLR_CHECK_CUDA(cudaMemcpy2DAsync(d_color, W, p_color, Wp, W, rows_out, cudaMemcpyDeviceToDevice, cs));
+    return SLR_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -75,6 +75,13 @@ struct slr_engine {
     void *d_bucket_scratch = nullptr;  // K3c counting-sort scratch (one scan)
     size_t bucket_scratch_bytes = 0;
 
+    // widths that are not a multiple of 16 (TMA bulk rows need 16-byte rows): the match stages run on a child engine
+    // of the padded width over zero-padded copies (slr_engine.cu: padded_*)
+    slr_engine *child = nullptr;
+    unsigned calib_version = 0, child_calib_version = 0;
+    void *d_pad[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t pad_bytes[6] = {0, 0, 0, 0, 0, 0};
+
     unsigned long long launches = 0;
 };
 
@@ -129,6 +136,11 @@ slr_status slr_launch_fused_ge(slr_engine *e, const uint8_t *d_stack, int batch,
 slr_status slr_launch_undistort_maps(slr_engine *e);
 slr_status slr_launch_rectify(slr_engine *e, const uint8_t *d_raw, int batch, int N, uint8_t *d_out);
 slr_status slr_build_strict_tables(slr_engine *e);
+// padded route for e->W % 16 != 0 (slr_engine.cu); kind: 0 = image stacks (MF), 1 = image stacks (GE),
+// 2 = phase + mask rows, 3 = code + mask rows
+slr_status slr_padded_run(slr_engine *e, int kind, const void *d_in0, const uint8_t *d_in1, int batch, int planes,
+                          int a0, int a1, int a2, int a3, int a4, float *d_xyz, uint8_t *d_valid, int32_t *d_match_k,
+                          uint8_t *d_color, unsigned long long *d_n_points);
 slr_status slr_launch_mesh_index(slr_engine *e, const float *d_sum, const uint8_t *d_count, int w, int h,
                                  int first_vertex, int *d_pn, int *d_tiles, float *d_vertices, int32_t *d_vertex_src,
                                  int32_t *d_faces, unsigned long long *d_counts);

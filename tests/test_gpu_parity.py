@@ -515,3 +515,45 @@ def test_k5_mesh_index_full_frame_cloud(cuda_engine_factory, oracle):
     # face count never exceeds two per pixel
     f = faces.cpu().numpy()
     assert f.min() >= 1 and f.max() <= len(vo) and len(f) <= 2 * W * H
+
+
+# ------------------------------------------------------------------------------------------------
+# widths that are not a multiple of 16 (the match kernels' TMA rows): zero-padded copies on a child engine
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("W,H", [(1000, 12), (52, 9), (37, 7), (1290, 6)])
+def test_ragged_widths_match_the_oracle(cuda_engine_factory, oracle, W, H):
+    """The reference takes any image size; here rows move by TMA in 16-byte multiples, so other widths run padded.
+    Same exactness bar for the MF and GE pipelines, the phase / code match entry points and the host entry point."""
+    eng = cuda_engine_factory(W, H, 2)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    # ---- MF: device entry, un-fused entry points, host entry ----
+    stack = np.stack([synth.synth_mf(W, H, seed=s, noise_dn=1.0) for s in (5, 6)])
+    xyz, valid, k, n = eng.run_mf(_t(stack), black_thr=40)
+    tot = 0
+    for b in range(2):
+        xyz_o, valid_o, k_o, n_o = oracle.run_mf(stack[b], cams, Q)
+        assert (k[b].cpu().numpy() == k_o).all() and (valid[b].cpu().numpy() == valid_o).all()
+        assert (bits(xyz[b].cpu().numpy()) == bits(xyz_o)).all()
+        tot += n_o
+    assert int(n.item()) == tot and tot > 0
+    ph, mk = eng.mf_decode(_t(stack), black_thr=40)
+    xyz2, valid2, k2, n2 = eng.match_triangulate_phase(ph, mk)
+    assert (k2.cpu().numpy() == k.cpu().numpy()).all() and (bits(xyz2.cpu().numpy()) == bits(xyz.cpu().numpy())).all()
+    h_xyz = np.empty((2, H, W, 3), np.float32)
+    h_valid = np.empty((2, H, W), np.uint8)
+    h_k = np.empty((2, H, W), np.int32)
+    n_host = eng.run_mf_host(stack, h_xyz, h_valid, h_k)
+    assert n_host == tot and (h_k == k.cpu().numpy()).all() and (bits(h_xyz) == bits(xyz.cpu().numpy())).all()
+    # ---- GE: fused entry with colour, and the code match entry point ----
+    nc = oracle.gray_num_bits(W)
+    g = synth.synth_gray(W, H, seed=8, integer_disparity=False, noise_dn=2.0)[None]
+    xyz, valid, k, colr, n = eng.run_ge(_t(g), nc, black_thr=40, white_thr=3, have_color=True)
+    cols, mks = zip(*[(lambda r: (r[0], r[2]))(oracle.gray_decode(g[0, cam], nc, 0, 40, 3, W, H)) for cam in range(2)])
+    xyz_o, valid_o, k_o, col_o, n_o = oracle.ge_triangulate(cols[0], mks[0], cols[1], mks[1], Q, whiteL=g[0, 0, 0], whiteR=g[0, 1, 0])
+    assert (k[0].cpu().numpy() == k_o).all() and (valid[0].cpu().numpy() == valid_o).all()
+    assert (colr[0].cpu().numpy() == col_o).all() and (bits(xyz[0].cpu().numpy()) == bits(xyz_o)).all()
+    assert int(n.item()) == n_o and n_o > 0
+    col, _, gm = eng.gray_decode(_t(g), nc, 0, 40, 3, W, H)
+    xyz3, valid3, k3, _, n3 = eng.match_triangulate_code(col, gm)
+    assert (k3[0].cpu().numpy() == k_o).all() and (bits(xyz3[0].cpu().numpy()) == bits(xyz_o)).all()
