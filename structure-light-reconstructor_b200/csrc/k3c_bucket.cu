@@ -12,6 +12,8 @@
 //   kc_count    histogram of cells per camera (global atomics)
 //   kc_scan*    exclusive scan over the 2*ncell counters (three small kernels)
 //   kc_scatter  pixel keys (x*H + y, i.e. column-major rank) into their cell's slice, any order
+//   kc_rays     (once per calibration) the unit ray of every camera pixel: undistortPoints in fp64, image -> world,
+//               normalise; 31 MB at 1280x1024, so that pairs cost loads instead of 300 fp64 instructions per ray
 //   kc_cells    one thread per cell: order both slices by key (the reference's push order), walk the pairs in
 //               the reference's (c1 outer, c2 inner) order with the exact fp32/fp64 operation sequence
 // This path is latency bound (tiny irregular lists), not an HBM streaming kernel; it is not on the north-star
@@ -195,6 +197,20 @@ __device__ __forceinline__ void pixel_ray(int x, int y, const slr_camera &cam, c
     ray[2] = __fdiv_rn(ray[2], m);
 }
 
+// unit rays of every pixel of both cameras, once per calibration: [2][H*W][3]
+__global__ void kc_rays(BucketCalib cal, int W, int H, float *__restrict__ rays)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over 2*P
+    const int P = W * H;
+    if (idx >= 2 * P) return;
+    const int cam = idx / P, p = idx - cam * P;
+    float ray[3];
+    pixel_ray(p % W, p / W, cal.cam[cam], cal.pos[cam], ray);
+    rays[(size_t)idx * 3 + 0] = ray[0];
+    rays[(size_t)idx * 3 + 1] = ray[1];
+    rays[(size_t)idx * 3 + 2] = ray[2];
+}
+
 __device__ __forceinline__ void sort_slice(int *a, int n)
 {
     for (int i = 1; i < n; i++) {  // insertion sort: slices hold a handful of pixels
@@ -208,9 +224,9 @@ __device__ __forceinline__ void sort_slice(int *a, int n)
     }
 }
 
-__global__ void kc_cells(const int *__restrict__ start, const int *__restrict__ count, int *__restrict__ items, int H,
-                         int ncell, BucketCalib cal, float *__restrict__ sum, uint8_t *__restrict__ cnt,
-                         unsigned long long *__restrict__ n_cells)
+__global__ void kc_cells(const int *__restrict__ start, const int *__restrict__ count, int *__restrict__ items, int W, int H,
+                         int ncell, BucketCalib cal, const float *__restrict__ rays, float *__restrict__ sum,
+                         uint8_t *__restrict__ cnt, unsigned long long *__restrict__ n_cells)
 {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned filled = 0;
@@ -223,11 +239,13 @@ __global__ void kc_cells(const int *__restrict__ start, const int *__restrict__ 
             sort_slice(l1, n1);
             sort_slice(l2, n2);
             for (int c1 = 0; c1 < n1; c1++) {
-                float ray1[3];
-                pixel_ray(l1[c1] / H, l1[c1] % H, cal.cam[0], cal.pos[0], ray1);
+                // the pixel's unit ray (pixel_ray: undistort -> image space -> world -> normalise, :440-447) comes from
+                // the per-calibration table; items hold the column-major rank x*H + y
+                const size_t p1 = (size_t)(l1[c1] % H) * W + l1[c1] / H;
+                const float ray1[3] = {__ldg(rays + p1 * 3), __ldg(rays + p1 * 3 + 1), __ldg(rays + p1 * 3 + 2)};
                 for (int c2 = 0; c2 < n2; c2++) {
-                    float ray2[3];
-                    pixel_ray(l2[c2] / H, l2[c2] % H, cal.cam[1], cal.pos[1], ray2);
+                    const size_t p2 = (size_t)W * H + (size_t)(l2[c2] % H) * W + l2[c2] / H;
+                    const float ray2[3] = {__ldg(rays + p2 * 3), __ldg(rays + p2 * 3 + 1), __ldg(rays + p2 * 3 + 2)};
                     // Utilities::line_lineIntersection, utilities.cpp:399-425 (all fp32)
                     const float v12[3] = {__fsub_rn(cal.pos[0][0], cal.pos[1][0]), __fsub_rn(cal.pos[0][1], cal.pos[1][1]),
                                           __fsub_rn(cal.pos[0][2], cal.pos[1][2])};
@@ -324,6 +342,14 @@ slr_status slr_launch_bucket_triangulate(slr_engine *e, const int32_t *d_col, co
     memcpy(cal.rigid, e->calib.rigid, sizeof(cal.rigid));
     cal.has_rigid = e->calib.has_rigid;
 
+    // per-pixel unit rays: a function of the calibration only (fp64 undistortion, 5 iterations per pixel)
+    if (!e->d_rays || e->rays_version != e->calib_version) {
+        if (!e->d_rays) SLR_CHECK_CUDA(cudaMalloc(&e->d_rays, (size_t)2 * P * 3 * sizeof(float)));
+        kc_rays<<<(int)((2 * P + KC_THREADS - 1) / KC_THREADS), KC_THREADS, 0, e->stream>>>(cal, W, H, e->d_rays);
+        SLR_CHECK_LAUNCH(e);
+        e->rays_version = e->calib_version;
+    }
+
     for (int b = 0; b < batch; b++) {
         const int32_t *col = d_col + (size_t)b * 2 * P, *row = d_row + (size_t)b * 2 * P;
         const uint8_t *mask = d_mask + (size_t)b * 2 * P;
@@ -340,7 +366,7 @@ slr_status slr_launch_bucket_triangulate(slr_engine *e, const int32_t *d_col, co
         SLR_CHECK_LAUNCH(e);
         kc_scatter<<<pix_blocks, KC_THREADS, 0, e->stream>>>(col, row, mask, W, H, scan_h, ncell, start, cursor, items);
         SLR_CHECK_LAUNCH(e);
-        kc_cells<<<(ncell + 127) / 128, 128, 0, e->stream>>>(start, count, items, H, ncell, cal,
+        kc_cells<<<(ncell + 127) / 128, 128, 0, e->stream>>>(start, count, items, W, H, ncell, cal, e->d_rays,
                                                              d_sum + (size_t)b * ncell * 3, d_cnt + (size_t)b * ncell,
                                                              d_n_cells);
         SLR_CHECK_LAUNCH(e);

@@ -46,6 +46,7 @@ static void free_engine(slr_engine *e)
     cudaFree(e->d_mesh_src);
     cudaFree(e->d_mesh_faces);
     cudaFree(e->d_mesh_counts);
+    cudaFree(e->d_rays);
     for (int i = 0; i < 6; i++) cudaFree(e->d_pad[i]);
     if (e->child) {
         e->child->stream = e->child->own_stream;

@@ -73,6 +73,8 @@ struct slr_engine {
     size_t mesh_host_px = 0;
 
     void *d_bucket_scratch = nullptr;  // K3c counting-sort scratch (one scan)
+    float *d_rays = nullptr;           // K3c: unit ray of every pixel of both cameras [2][H*W][3], per calibration
+    unsigned rays_version = 0;
     size_t bucket_scratch_bytes = 0;
 
     // widths that are not a multiple of 16 (TMA bulk rows need 16-byte rows): the match stages run on a child engine
