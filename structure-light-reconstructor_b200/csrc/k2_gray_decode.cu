@@ -121,29 +121,6 @@ k2_gray_decode(const uint8_t *__restrict__ stack, size_t P, long long chunks_per
 // ---- byte-parallel form (the common case: 0 <= black_thr <= 255, white_thr <= 255, <= 16 bits per axis) ----------
 // One 32-bit word = 4 pixels of one plane; every comparison below runs on the four bytes at once.
 
-// bit 7 of every byte = (that byte of a > that byte of d), unsigned; the other bits are garbage
-__device__ __forceinline__ uint32_t gt7(uint32_t a, uint32_t d)
-{
-    const uint32_t s = (a & 0x7f7f7f7fu) + (~d & 0x7f7f7f7fu);   // carry into bit 7 = (low 7 bits of a > low 7 bits of d)
-    return (a & ~d) | (~(a ^ d) & s);
-}
-
-// Gray accumulator of 4 pixels x 8 bits: planes are visited LSB first, the new bit enters at bit 7 of each byte
-__device__ __forceinline__ uint32_t push_bit(uint32_t acc, uint32_t t7)
-{
-    return ((acc >> 1) & 0x7f7f7f7fu) | (t7 & 0x80808080u);
-}
-
-// GrayCodes::grayToDec on two 16-bit lanes: prefix XOR from the MSB down
-__device__ __forceinline__ uint32_t gray_to_binary_x2(uint32_t g)
-{
-    g ^= (g >> 1) & 0x7fff7fffu;
-    g ^= (g >> 2) & 0x3fff3fffu;
-    g ^= (g >> 4) & 0x0fff0fffu;
-    g ^= (g >> 8) & 0x00ff00ffu;
-    return g;
-}
-
 struct GrayAcc {
     uint32_t lo[4], hi[4];   // [word]: gray bits 0..7 and 8..15 of 4 pixels each
 };
@@ -162,12 +139,12 @@ __device__ __forceinline__ void gray_axis(const uint8_t *__restrict__ src, size_
         const uint32_t a[4] = {v1.x, v1.y, v1.z, v1.w}, d[4] = {v2.x, v2.y, v2.z, v2.w};
 #pragma unroll
         for (int w = 0; w < 4; w++) {
-            const uint32_t t = gt7(a[w], d[w]);                                   // bit = v1 > v2   (reconstruct.cpp:396)
+            const uint32_t t = slr::gt7(a[w], d[w]);                                   // bit = v1 > v2   (reconstruct.cpp:396)
             if (k < 8)
-                g.lo[w] = push_bit(g.lo[w], t);
+                g.lo[w] = slr::push_bit(g.lo[w], t);
             else
-                g.hi[w] = push_bit(g.hi[w], t);
-            if (CHECK_WHITE) bad7[w] |= ~gt7(__vabsdiffu4(a[w], d[w]) | 0u, thr4);  // |v1-v2| < whiteThreshold (:393)
+                g.hi[w] = slr::push_bit(g.hi[w], t);
+            if (CHECK_WHITE) bad7[w] |= ~slr::gt7(__vabsdiffu4(a[w], d[w]) | 0u, thr4);  // |v1-v2| < whiteThreshold (:393)
         }
     }
     const int kl = nbits < 8 ? nbits : 8, kh = nbits - kl;                         // right-align both bytes
@@ -199,7 +176,7 @@ k2_gray_decode_x4(const uint8_t *__restrict__ stack, size_t P, long long chunks_
         uint32_t bad7[4];
 #pragma unroll
         for (int w = 0; w < 4; w++)   // white - black > blackThreshold (>= 0)  <=>  white > black and |white-black| > thr
-            bad7[w] = ~(gt7(wh[w], bl[w]) & gt7(__vabsdiffu4(wh[w], bl[w]), bthr4));
+            bad7[w] = ~(slr::gt7(wh[w], bl[w]) & slr::gt7(__vabsdiffu4(wh[w], bl[w]), bthr4));
         GrayAcc gx, gy;
         gray_axis<CHECK_WHITE>(src, P, 2, nbits_col, wthr4, gx, bad7);
         if (ROWS) gray_axis<CHECK_WHITE>(src, P, 2 + 2 * nbits_col, nbits_row, wthr4, gy, bad7);
@@ -209,13 +186,13 @@ k2_gray_decode_x4(const uint8_t *__restrict__ stack, size_t P, long long chunks_
 #pragma unroll
         for (int w = 0; w < 4; w++) {
             // pixels (0,1) and (2,3) of this word as 16-bit lanes: [lo0 hi0 lo1 hi1], [lo2 hi2 lo3 hi3]
-            const uint32_t x01 = gray_to_binary_x2(__byte_perm(gx.lo[w], gx.hi[w], 0x5140));
-            const uint32_t x23 = gray_to_binary_x2(__byte_perm(gx.lo[w], gx.hi[w], 0x7362));
+            const uint32_t x01 = slr::gray_to_binary_x2(__byte_perm(gx.lo[w], gx.hi[w], 0x5140));
+            const uint32_t x23 = slr::gray_to_binary_x2(__byte_perm(gx.lo[w], gx.hi[w], 0x7362));
             int xs[4] = {(int)(x01 & 0xffffu), (int)(x01 >> 16), (int)(x23 & 0xffffu), (int)(x23 >> 16)};
             int ys[4] = {0, 0, 0, 0};
             if (ROWS) {
-                const uint32_t y01 = gray_to_binary_x2(__byte_perm(gy.lo[w], gy.hi[w], 0x5140));
-                const uint32_t y23 = gray_to_binary_x2(__byte_perm(gy.lo[w], gy.hi[w], 0x7362));
+                const uint32_t y01 = slr::gray_to_binary_x2(__byte_perm(gy.lo[w], gy.hi[w], 0x5140));
+                const uint32_t y23 = slr::gray_to_binary_x2(__byte_perm(gy.lo[w], gy.hi[w], 0x7362));
                 ys[0] = (int)(y01 & 0xffffu), ys[1] = (int)(y01 >> 16), ys[2] = (int)(y23 & 0xffffu), ys[3] = (int)(y23 >> 16);
             }
             uint32_t m4 = 0;

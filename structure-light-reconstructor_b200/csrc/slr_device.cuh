@@ -280,6 +280,32 @@ __device__ __forceinline__ float atan2_pos(float a, float b)
 }
 
 // ------------------------------------------------------------------------------------------------
+// byte-parallel Gray decode helpers (k2_gray_decode.cu, k_fused_ge.cu): one 32-bit word = 4 pixels of one plane
+// ------------------------------------------------------------------------------------------------
+// bit 7 of every byte = (that byte of a > that byte of d), unsigned; the other bits are garbage
+__device__ __forceinline__ uint32_t gt7(uint32_t a, uint32_t d)
+{
+    const uint32_t s = (a & 0x7f7f7f7fu) + (~d & 0x7f7f7f7fu);   // carry into bit 7 = (low 7 bits of a > low 7 bits of d)
+    return (a & ~d) | (~(a ^ d) & s);
+}
+
+// Gray accumulator of 4 pixels x 8 bits: planes are visited LSB first, the new bit enters at bit 7 of each byte
+__device__ __forceinline__ uint32_t push_bit(uint32_t acc, uint32_t t7)
+{
+    return ((acc >> 1) & 0x7f7f7f7fu) | (t7 & 0x80808080u);
+}
+
+// GrayCodes::grayToDec on two 16-bit lanes: prefix XOR from the MSB down
+__device__ __forceinline__ uint32_t gray_to_binary_x2(uint32_t g)
+{
+    g ^= (g >> 1) & 0x7fff7fffu;
+    g ^= (g >> 2) & 0x3fff3fffu;
+    g ^= (g >> 4) & 0x0fff0fffu;
+    g ^= (g >> 8) & 0x00ff00ffu;
+    return g;
+}
+
+// ------------------------------------------------------------------------------------------------
 // match predicate: Duke/mfreconstruct.cpp:295  fabs(pL - pR) < 0.1  (float difference, float fabs,
 // compared against the double 0.1 — equivalent to the float compare against 0.1f because
 // pred(0.1f) < 0.1 < 0.1f).
