@@ -13,7 +13,8 @@
 //      max-scan), and only chunks whose start changed are re-run.  After t rounds the first t
 //      chunks are final, so the fixed point is the sequential answer (exact); on real rows it is
 //      reached in 2-3 rounds because the chain state merges at the first matched pixel;
-//   3. matches are reprojected with Q in fp64 and leave through smem staging + TMA bulk stores.
+//   3. matches are reprojected with Q in fp64; XYZ is written from registers, valid / k / colour leave through
+//      smem staging + TMA bulk stores (47 KB of shared memory per row context: four CTAs per SM).
 #include <limits.h>
 
 #include "slr_device.cuh"
@@ -49,7 +50,7 @@ __device__ __forceinline__ int first_at_or_after(const int *head, const int *nex
     return best;
 }
 
-__global__ void __launch_bounds__(K3B_THREADS)
+__global__ void __launch_bounds__(K3B_THREADS, 4)
 k3b_code_match(const K3bParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -64,8 +65,7 @@ k3b_code_match(const K3bParams p)
     const size_t stage_bytes = (size_t)10 * W;  // cL i32[W] | cR i32[W] | mL u8[W] | mR u8[W]
     int *head = reinterpret_cast<int *>(stage0 + 2 * stage_bytes);
     int *next = head + HB;
-    float *o_xyz = reinterpret_cast<float *>(next + W);
-    int *o_k = reinterpret_cast<int *>(o_xyz + 3 * W);
+    int *o_k = next + W;
     uint8_t *o_valid = reinterpret_cast<uint8_t *>(o_k + W);
     uint8_t *o_color = o_valid + W;
 
@@ -169,16 +169,16 @@ k3b_code_match(const K3bParams p)
                 }
                 n_local++;
             }
-            o_xyz[3 * j + 0] = X;
-            o_xyz[3 * j + 1] = Y;
-            o_xyz[3 * j + 2] = Z;
+            float *dst = p.xyz + ((size_t)r * W + j) * 3;   // 12 bytes per lane, contiguous across the warp
+            dst[0] = X;
+            dst[1] = Y;
+            dst[2] = Z;
             o_valid[j] = (k >= 0) ? 1 : 0;
             o_color[j] = colr;
         }
         slr::fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
-            slr::tma_store_1d(p.xyz + (size_t)r * W * 3, o_xyz, 12 * W);
             slr::tma_store_1d(p.valid + (size_t)r * W, o_valid, W);
             if (p.match_k) slr::tma_store_1d(p.match_k + (size_t)r * W, o_k, 4 * W);
             if (p.color) slr::tma_store_1d(p.color + (size_t)r * W, o_color, W);
@@ -225,8 +225,7 @@ slr_status slr_launch_match_code(slr_engine *e, const int32_t *d_col, const uint
     p.color = d_color;
     p.n_points = d_n_points;
     p.calib = e->calib;
-    const size_t smem = 64 + (size_t)20 * e->W + (size_t)4 * p.HB + (size_t)4 * e->W + (size_t)12 * e->W +
-                        (size_t)4 * e->W + (size_t)2 * e->W;
+    const size_t smem = 64 + (size_t)20 * e->W + (size_t)4 * p.HB + (size_t)4 * e->W + (size_t)4 * e->W + (size_t)2 * e->W;
     SLR_REQUIRE(smem <= 226 * 1024, "image width %d needs %zu bytes of shared memory per row", e->W, smem);
     SLR_CHECK_CUDA(cudaFuncSetAttribute(k3b_code_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
