@@ -557,3 +557,45 @@ def test_ragged_widths_match_the_oracle(cuda_engine_factory, oracle, W, H):
     col, _, gm = eng.gray_decode(_t(g), nc, 0, 40, 3, W, H)
     xyz3, valid3, k3, _, n3 = eng.match_triangulate_code(col, gm)
     assert (k3[0].cpu().numpy() == k_o).all() and (bits(xyz3[0].cpu().numpy()) == bits(xyz_o)).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# fuzz: pure-noise and low-entropy stacks (stress the hash table, the chains, duplicate handling, thresholds)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_fuzz_random_stacks_match_the_oracle(cuda_engine_factory, oracle, seed):
+    """Random image bytes are the opposite of a scene: phases / codes are uncorrelated between cameras, values collide
+    and repeat at random.  Every pipeline must still reproduce the oracle bit for bit."""
+    rng = np.random.default_rng(1000 + seed)
+    W = int(rng.choice([16, 48, 64, 160, 256, 320, 1280]))
+    H = int(rng.integers(1, 6))
+    levels = int(rng.choice([2, 3, 8, 256]))          # few grey levels -> many equal phases, degenerate (0/0) pixels
+    black_thr = int(rng.choice([0, 5, 40, 120]))
+    eng = cuda_engine_factory(W, H, 1)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    rigid = None
+    if seed % 2:
+        rigid = np.array([[0.98, -0.17, 0.05, 12.5], [0.17, 0.98, 0.02, -3.25], [-0.05, -0.01, 0.99, 40.0]], np.float32)
+    eng.set_calib(cams, Q, rigid)
+
+    def noise(n):
+        st = (rng.integers(0, levels, (1, 2, n, H, W)) * (255 // max(levels - 1, 1))).astype(np.uint8)
+        st[:, :, 0] = rng.integers(100, 256, (1, 2, H, W))       # white / black so that part of the image is lit
+        st[:, :, 1] = rng.integers(0, 120, (1, 2, H, W))
+        return st
+
+    mf = noise(14)
+    xyz, valid, k, n = eng.run_mf(_t(mf), black_thr=black_thr)
+    xyz_o, valid_o, k_o, n_o = oracle.run_mf(mf[0], cams, Q, black_thr=black_thr, rigid=rigid)
+    assert (k[0].cpu().numpy() == k_o).all() and (valid[0].cpu().numpy() == valid_o).all()
+    assert (bits(xyz[0].cpu().numpy())[valid_o > 0] == bits(xyz_o)[valid_o > 0]).all() and int(n.item()) == n_o
+
+    nc = oracle.gray_num_bits(W)
+    white_thr = int(rng.choice([0, 1, 30, 200]))
+    ge = noise(2 + 2 * nc)
+    xyz, valid, k, colr, n = eng.run_ge(_t(ge), nc, black_thr=black_thr, white_thr=white_thr, have_color=True)
+    cols, mks = zip(*[(lambda r: (r[0], r[2]))(oracle.gray_decode(ge[0, cam], nc, 0, black_thr, white_thr, W, H)) for cam in range(2)])
+    xyz_o, valid_o, k_o, col_o, n_o = oracle.ge_triangulate(cols[0], mks[0], cols[1], mks[1], Q, rigid=rigid, whiteL=ge[0, 0, 0], whiteR=ge[0, 1, 0])
+    assert (k[0].cpu().numpy() == k_o).all() and (valid[0].cpu().numpy() == valid_o).all()
+    assert (colr[0].cpu().numpy() == col_o).all()
+    assert (bits(xyz[0].cpu().numpy())[valid_o > 0] == bits(xyz_o)[valid_o > 0]).all() and int(n.item()) == n_o
