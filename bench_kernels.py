@@ -88,6 +88,10 @@ def main():
     c = cpu_time(lambda: [orc.mf_decode(h_mf[0, cam], nthreads=nthreads) for cam in range(2)]) if orc else None
     report("k1_mf_decode (strict)", "computeShadows+decodePatterns+getPhase", ms, B * 2 * P * (14 + 5), c, B * 2 * P, "pixels")
 
+    ms = timed(lambda: eng.mf_decode(mf, mode=slr_b200.MODE_CORRECTED))
+    c = cpu_time(lambda: [orc.mf_decode(h_mf[0, cam], mode=1, nthreads=nthreads) for cam in range(2)]) if orc else None
+    report("k1_mf_decode (corrected: atan2 + heterodyne, BASELINE config 2)", "(no reference counterpart)", ms, B * 2 * P * (14 + 5), c, B * 2 * P, "pixels")
+
     ms = timed(lambda: eng.match_triangulate_phase(ph, mk, want_k=False))
     ph_h2, mk_h2 = ph[0].cpu().numpy(), mk[0].cpu().numpy()
     c = cpu_time(lambda: orc.mf_triangulate(ph_h2[0], mk_h2[0], ph_h2[1], mk_h2[1], cams, Q, nthreads=nthreads)) if orc else None

@@ -15,8 +15,8 @@ constexpr int K1_THREADS = 256;
 // strict mode, F = 3, S = 4, 16 pixels per thread, table-driven exact decode (slr_device.cuh: the integer quotient by
 // reciprocal multiplication, the wrapped phase from the table of the reference's float values held in exact
 // 2^-24 fixed point); persistent grid-stride CTAs load the 8 KB of tables into shared memory once
-template <int NW>  // 32-bit words (4 pixels each) per thread per plane: 4 = 128-bit loads, 2 = 64-bit loads
-__global__ void __launch_bounds__(K1_THREADS, NW == 4 ? 2 : 3)
+template <int NW>  // 32-bit words (4 pixels each) per thread per plane: 4 = 128-bit loads, 2 = 64-bit, 1 = 32-bit
+__global__ void __launch_bounds__(K1_THREADS, NW == 4 ? 2 : NW == 2 ? 3 : 5)
 k1_mf_decode_strict(const uint8_t *__restrict__ stack, size_t P, long long chunks_per_view, long long total_chunks,
                     int black_thr, const int *__restrict__ g_ptab, const uint32_t *__restrict__ g_btab,
                     float *__restrict__ phase, uint8_t *__restrict__ mask)
@@ -37,10 +37,12 @@ k1_mf_decode_strict(const uint8_t *__restrict__ stack, size_t P, long long chunk
         for (int n = 0; n < 14; n++) {
             if (NW == 4) {
                 const uint4 v = slr::ldg_stream_u4(src + (size_t)n * P);
-                img[n][0] = v.x, img[n][1] = v.y, img[n][NW - 2] = v.z, img[n][NW - 1] = v.w;
-            } else {
+                img[n][0] = v.x, img[n][NW > 1 ? 1 : 0] = v.y, img[n][NW > 2 ? NW - 2 : 0] = v.z, img[n][NW - 1] = v.w;
+            } else if (NW == 2) {
                 const uint2 v = slr::ldg_stream_u2(src + (size_t)n * P);
-                img[n][0] = v.x, img[n][1] = v.y;
+                img[n][0] = v.x, img[n][NW - 1] = v.y;
+            } else {
+                img[n][0] = slr::ldg_stream_u32(src + (size_t)n * P);
             }
         }
 
@@ -68,9 +70,11 @@ k1_mf_decode_strict(const uint8_t *__restrict__ stack, size_t P, long long chunk
             mk[w] = m4;
         }
         if (NW == 4)
-            slr::stg_stream_u4(mask + o, make_uint4(mk[0], mk[1], mk[NW - 2], mk[NW - 1]));
+            slr::stg_stream_u4(mask + o, make_uint4(mk[0], mk[NW > 1 ? 1 : 0], mk[NW > 2 ? NW - 2 : 0], mk[NW - 1]));
+        else if (NW == 2)
+            *reinterpret_cast<uint2 *>(mask + o) = make_uint2(mk[0], mk[NW - 1]);
         else
-            *reinterpret_cast<uint2 *>(mask + o) = make_uint2(mk[0], mk[1]);
+            *reinterpret_cast<uint32_t *>(mask + o) = mk[0];
     }
 }
 
@@ -96,6 +100,64 @@ k1_mf_decode_strict_scalar(const uint8_t *__restrict__ stack, size_t P, long lon
         m = m && ok;
         phase[idx] = m ? ph : slr::qnan();
         mask[idx] = m ? 1 : 0;
+    }
+}
+
+// corrected mode for the reference's stack shape (3 frequencies x 4 steps): 16 pixels per thread, all 14 plane loads
+// issued up front as 128-bit streaming loads, atan2 by the branch-free polynomial of slr_device.cuh, cascade and scale
+// in registers, vector stores.  Same arithmetic, pixel for pixel, as the generic kernel below and as the fused
+// kernel's corrected branch.
+template <int NW>
+__global__ void __launch_bounds__(K1_THREADS, NW == 4 ? 2 : 3)
+k1_mf_decode_corrected_3x4(const uint8_t *__restrict__ stack, size_t P, long long chunks_per_view, long long total_chunks,
+                           int black_thr, float *__restrict__ phase, uint8_t *__restrict__ mask)
+{
+    for (long long chunk = (long long)blockIdx.x * K1_THREADS + threadIdx.x; chunk < total_chunks;
+         chunk += (long long)gridDim.x * K1_THREADS) {
+        const long long view = chunk / chunks_per_view;
+        const long long c = chunk - view * chunks_per_view;
+        const uint8_t *src = stack + (size_t)view * 14 * P + (size_t)c * (4 * NW);
+        uint32_t img[14][NW];
+#pragma unroll
+        for (int n = 0; n < 14; n++) {
+            if (NW == 4) {
+                const uint4 v = slr::ldg_stream_u4(src + (size_t)n * P);
+                img[n][0] = v.x, img[n][1] = v.y, img[n][NW - 2] = v.z, img[n][NW - 1] = v.w;
+            } else {
+                const uint2 v = slr::ldg_stream_u2(src + (size_t)n * P);
+                img[n][0] = v.x, img[n][1] = v.y;
+            }
+        }
+        const size_t o = (size_t)view * P + (size_t)c * (4 * NW);
+        uint32_t mk[NW];
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            float ph[4];
+            uint32_t m4 = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                bool ok = (int)slr::byte_of(img[0][w], i) - (int)slr::byte_of(img[1][w], i) > black_thr;
+                float l[3];
+#pragma unroll
+                for (int f = 0; f < 3; f++) {
+                    const int a = (int)slr::byte_of(img[5 + 4 * f][w], i) - (int)slr::byte_of(img[3 + 4 * f][w], i);   // G4 - G2
+                    const int b = (int)slr::byte_of(img[2 + 4 * f][w], i) - (int)slr::byte_of(img[4 + 4 * f][w], i);   // G1 - G3
+                    ok = ok && ((a | b) != 0);
+                    l[f] = slr::atan2_pos((float)a, (float)b);
+                }
+                const float d01 = slr::wrap_2pi(__fsub_rn(l[0], l[1]));
+                const float d12 = slr::wrap_2pi(__fsub_rn(l[1], l[2]));
+                const float p = slr::phase_scale_corrected(slr::wrap_2pi(__fsub_rn(d01, d12)));
+                ph[i] = ok ? p : slr::qnan();
+                m4 |= (ok ? 1u : 0u) << (8 * i);
+            }
+            slr::stg_stream_f4(phase + o + 4 * w, make_float4(ph[0], ph[1], ph[2], ph[3]));
+            mk[w] = m4;
+        }
+        if (NW == 4)
+            slr::stg_stream_u4(mask + o, make_uint4(mk[0], mk[1], mk[NW - 2], mk[NW - 1]));
+        else
+            *reinterpret_cast<uint2 *>(mask + o) = make_uint2(mk[0], mk[1]);
     }
 }
 
@@ -187,15 +249,19 @@ slr_status slr_launch_mf_decode(slr_engine *e, const uint8_t *d_stack, int views
                                       "(Duke/mfreconstruct.cpp:237); got F=%d S=%d", F, S);
         const bool vec = (P % 16 == 0) && (((uintptr_t)d_stack | (uintptr_t)d_phase | (uintptr_t)d_mask) % 16 == 0);
         if (vec) {
-            const int nw = getenv("SLR_K1_NW2") ? 2 : 4;  // 128-bit loads measured best (0.139 vs 0.148 ms per 8 scans)
+            int nw = 2;   // 8 pixels per thread, three CTAs per SM measured best (0.091 vs 0.097 ms per 8 scans for 16 pixels)
+            if (const char *ev = getenv("SLR_K1_NW")) nw = atoi(ev) == 1 ? 1 : atoi(ev) == 2 ? 2 : 4;   // tuning knob
             const long long cpv = (long long)(P / (4 * nw));
             const long long total = cpv * views;
             long long blocks = (total + K1_THREADS - 1) / K1_THREADS;
-            const long long cap = (long long)e->num_sms * (nw == 4 ? 2 : 3);   // persistent: tables loaded once per CTA
+            const long long cap = (long long)e->num_sms * (nw == 4 ? 2 : nw == 2 ? 3 : 5);   // persistent: tables loaded once per CTA
             if (blocks > cap) blocks = cap;
             if (blocks < 1) blocks = 1;
             if (nw == 4)
                 k1_mf_decode_strict<4><<<(unsigned)blocks, K1_THREADS, 0, e->stream>>>(d_stack, P, cpv, total, black_thr,
+                                                                                       e->d_ptab, e->d_btab, d_phase, d_mask);
+            else if (nw == 1)
+                k1_mf_decode_strict<1><<<(unsigned)blocks, K1_THREADS, 0, e->stream>>>(d_stack, P, cpv, total, black_thr,
                                                                                        e->d_ptab, e->d_btab, d_phase, d_mask);
             else
                 k1_mf_decode_strict<2><<<(unsigned)blocks, K1_THREADS, 0, e->stream>>>(d_stack, P, cpv, total, black_thr,
@@ -218,6 +284,17 @@ slr_status slr_launch_mf_decode(slr_engine *e, const uint8_t *d_stack, int views
     for (int s = 0; s < 16; s++) {
         coef.cs[s] = (s < S) ? (float)cos(2.0 * 3.14159265358979323846 * s / S) : 0.0f;
         coef.sn[s] = (s < S) ? (float)sin(2.0 * 3.14159265358979323846 * s / S) : 0.0f;
+    }
+    if (F == 3 && S == 4 && P % 16 == 0 && (((uintptr_t)d_stack | (uintptr_t)d_phase | (uintptr_t)d_mask) % 16) == 0) {
+        const long long cpv = (long long)(P / 16), total = cpv * views;   // 16 pixels per thread (8 spills: 0.115 vs 0.099 ms)
+        long long blocks = (total + K1_THREADS - 1) / K1_THREADS;
+        const long long cap = (long long)e->num_sms * 2 * 4;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        k1_mf_decode_corrected_3x4<4><<<(unsigned)blocks, K1_THREADS, 0, e->stream>>>(d_stack, P, cpv, total, black_thr,
+                                                                                     d_phase, d_mask);
+        SLR_CHECK_LAUNCH(e);
+        return SLR_OK;
     }
     const bool vec = (P % 4 == 0) && (((uintptr_t)d_stack) % 4 == 0);
     const int px = vec ? 4 : 1;
