@@ -29,7 +29,7 @@
 #include <limits.h>
 #include <stdlib.h>
 
-#include "slr_device.cuh"
+#include "k_fused_common.cuh"
 
 slr_status slr_unfused_mf(slr_engine *e, const uint8_t *d_stack, int batch, int F, int S, int black_thr, int mode,
                           float *d_xyz, uint8_t *d_valid, int32_t *d_match_k, unsigned long long *d_n_points);
@@ -39,291 +39,7 @@ slr_status slr_unfused_ge(slr_engine *e, const uint8_t *d_stack, int batch, int 
 
 namespace {
 
-constexpr int FUSED_MAX_THREADS = 1024;   // one CTA per SM (rows too wide for two row contexts): 64 registers as well
-constexpr uint32_t KEY_EMPTY = 0xFFFFFFFFu;
-constexpr int MODE_PHASE_INPUT = 2;  // rows of already decoded phase + mask (slr_match_triangulate_phase) instead of images
-
-struct FusedParams {
-    const uint8_t *stack;  // [batch][2][N][H][W]
-    const float *phase;    // MODE_PHASE_INPUT: [batch][2][H][W]
-    const uint8_t *mask;   // MODE_PHASE_INPUT: [batch][2][H][W]
-    int W, H, batch, F, S, N;
-    int T, logT;           // dedupe table size (power of two); 2T bucket heads
-    int black_thr;
-    const float *lx, *ly, *rx;
-    const int *ptab;       // strict: [SLR_PTAB_SIZE] wrapped-phase values, 2^-24 fixed point (slr_device.cuh)
-    const uint32_t *btab;  // strict: [SLR_BTAB_SIZE] reciprocal multipliers + row bases
-    float cs[16], sn[16];  // corrected: cos/sin(2 pi s / S)
-    float *xyz;
-    uint8_t *valid;
-    int32_t *match_k;
-    unsigned long long *n_points;
-    slr_calib_dev calib;
-#ifdef SLR_PHASE_CLOCKS
-    long long *dbg;        // [grid][DBG_ROWS][16 warps][DBG_PTS] clock64 stamps (debug builds only)
-#endif
-#ifdef SLR_ABLATION
-    int ablate;            // SLR_ABLATE bit mask: skip 1 reprojection, 2 chain walk, 4 insert, 8 decode math, 16 stores
-#endif
-};
-
-#ifdef SLR_PHASE_CLOCKS
-constexpr int DBG_ROWS = 8, DBG_PTS = 7, DBG_SKIP = 4;
-#define SLR_STAMP(pt)                                                                                          \
-    do {                                                                                                       \
-        __syncwarp();                                                                                          \
-        if (lane == 0 && tid < 512 && it >= DBG_SKIP && it < DBG_SKIP + DBG_ROWS)                                          \
-            p.dbg[(((size_t)blockIdx.x * DBG_ROWS + (it - DBG_SKIP)) * 16 + (tid >> 5)) * DBG_PTS + (pt)] = clock64(); \
-    } while (0)
-#else
-#define SLR_STAMP(pt) do { } while (0)
-#endif
-#ifdef SLR_ABLATION   // cost-attribution builds (csrc/Makefile ABLATE=1): results are wrong by construction
-#define SLR_ABLATE(bit) ((p.ablate & (bit)) != 0)
-#else
-#define SLR_ABLATE(bit) false
-#endif
-
-__device__ __forceinline__ uint64_t make_evict_first_policy()
-{
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar,
-                                                 uint64_t policy)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-            slr::smem_u32(smem_dst)),
-        "l"(gmem_src), "r"(bytes), "r"(slr::smem_u32(bar)), "l"(policy)
-        : "memory");
-}
-
-// Window buckets.  Bucket width 1/4; a right value pR is filed under every bucket that the interval
-// [pR - 0.11, pR + 0.11] touches (one or two), so a left value only probes its own bucket: any pL with
-// fabs(pL - pR) < 0.1 lies inside that interval, and the clamp keeps the mapping monotone for huge values
-// (where float spacing exceeds the margin every such value shares the end bucket).
-template <bool CLAMP>
-__device__ __forceinline__ int window_bucket(float p)
-{
-    // decoded phases are bounded (|p| < 1000); caller-supplied phase maps (MODE_PHASE_INPUT) are arbitrary floats
-    if (CLAMP) p = fminf(fmaxf(p, -30000.0f), 30000.0f);
-    return __float2int_rd(__fmul_rn(p, 4.0f));
-}
-
-// Slot of a phase value.  Two multiply rounds: a single multiplicative hash maps the arithmetic progressions that
-// smooth (corrected-mode) phase ramps form in float-bit space onto a handful of slots for unlucky strides, and
-// probing then degenerates into scans of hundreds of entries.
-__device__ __forceinline__ uint32_t slot_of(uint32_t key, int logT)
-{
-    uint32_t h = key * 0x9E3779B1u;
-    h ^= h >> 15;
-    h *= 0x85EBCA77u;
-    return h >> (32 - logT);
-}
-
-// PX consecutive pixels (4 / 2 / 1: one 32- / 16- / 8-bit load per plane) of one camera row held in shared
-// memory as rows = [N][W] u8; x0 = first pixel (a multiple of PX).
-template <int MODE, int PX>
-__device__ __forceinline__ void decode_px(const uint8_t *__restrict__ rows, int W, int x0, const FusedParams &p,
-                                          const int *s_ptab, const uint32_t *s_btab, float (&ph)[PX], bool (&ok)[PX])
-{
-    auto plane = [&](int n) -> uint32_t {
-        if (PX == 4) return *reinterpret_cast<const uint32_t *>(rows + (size_t)n * W + x0);
-        if (PX == 2) return *reinterpret_cast<const uint16_t *>(rows + (size_t)n * W + x0);
-        return rows[(size_t)n * W + x0];
-    };
-    const uint32_t wv = plane(0), bv = plane(1);
-#pragma unroll
-    for (int i = 0; i < PX; i++) ok[i] = (int)slr::byte_of(wv, i) - (int)slr::byte_of(bv, i) > p.black_thr;  // computeShadows
-    if (MODE == SLR_MODE_STRICT) {
-        int P[3][PX];
-#pragma unroll
-        for (int f = 0; f < 3; f++) {
-            const uint32_t g1 = plane(2 + 4 * f), g2 = plane(3 + 4 * f), g3 = plane(4 + 4 * f), g4 = plane(5 + 4 * f);
-#pragma unroll
-            for (int i = 0; i < PX; i++)
-                P[f][i] = slr::wrapped_strict_fx((int)slr::byte_of(g4, i) - (int)slr::byte_of(g2, i),
-                                                 (int)slr::byte_of(g1, i) - (int)slr::byte_of(g3, i), s_ptab, s_btab);
-        }
-#pragma unroll
-        for (int i = 0; i < PX; i++) ph[i] = slr::heterodyne_strict_fx(P[0][i], P[1][i], P[2][i], ok[i]);
-    } else if (p.F == 3 && p.S == 4) {
-        // the reference's 3 frequencies x 4 steps, fully unrolled (same arithmetic as the generic branch below)
-        float l[3][PX];
-#pragma unroll
-        for (int f = 0; f < 3; f++) {
-            const uint32_t g1 = plane(2 + 4 * f), g2 = plane(3 + 4 * f), g3 = plane(4 + 4 * f), g4 = plane(5 + 4 * f);
-#pragma unroll
-            for (int i = 0; i < PX; i++) {
-                const int a = (int)slr::byte_of(g4, i) - (int)slr::byte_of(g2, i);
-                const int b = (int)slr::byte_of(g1, i) - (int)slr::byte_of(g3, i);
-                ok[i] = ok[i] && ((a | b) != 0);
-                l[f][i] = slr::atan2_pos((float)a, (float)b);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < PX; i++) {
-            const float d01 = slr::wrap_2pi(__fsub_rn(l[0][i], l[1][i]));
-            const float d12 = slr::wrap_2pi(__fsub_rn(l[1][i], l[2][i]));
-            const float d = slr::wrap_2pi(__fsub_rn(d01, d12));
-            ph[i] = slr::phase_scale_corrected(d);
-        }
-    } else {
-        float lvl[8][PX];
-        const int F = p.F, S = p.S;
-        for (int f = 0; f < F; f++) {
-            float num[PX], den[PX];
-            int inum[PX], iden[PX];
-#pragma unroll
-            for (int i = 0; i < PX; i++) num[i] = den[i] = 0.0f, inum[i] = iden[i] = 0;
-            for (int s = 0; s < S; s++) {
-                const uint32_t v = plane(2 + S * f + s);
-#pragma unroll
-                for (int i = 0; i < PX; i++) {
-                    const int g = (int)slr::byte_of(v, i);
-                    if (S == 4) {
-                        inum[i] += (s == 3) ? g : (s == 1) ? -g : 0;
-                        iden[i] += (s == 0) ? g : (s == 2) ? -g : 0;
-                    } else {
-                        num[i] = __fsub_rn(num[i], __fmul_rn((float)g, p.sn[s]));
-                        den[i] = __fadd_rn(den[i], __fmul_rn((float)g, p.cs[s]));
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < PX; i++) {
-                float nn = num[i], dd = den[i];
-                if (S == 4) {
-                    nn = (float)inum[i];
-                    dd = (float)iden[i];
-                    if (inum[i] == 0 && iden[i] == 0) ok[i] = false;
-                } else if (__fadd_rn(__fmul_rn(nn, nn), __fmul_rn(dd, dd)) < 0.25f) {
-                    ok[i] = false;
-                }
-                lvl[f][i] = slr::atan2_pos(nn, dd);
-            }
-        }
-        for (int n = F; n > 1; n--)
-            for (int j = 0; j + 1 < n; j++)
-#pragma unroll
-                for (int i = 0; i < PX; i++) lvl[j][i] = slr::wrap_2pi(__fsub_rn(lvl[j][i], lvl[j + 1][i]));
-#pragma unroll
-        for (int i = 0; i < PX; i++) ph[i] = slr::phase_scale_corrected(lvl[0][i]);
-    }
-}
-
-// phases of PX pixels of the right or left row, from the staged image rows (or the staged phase + mask rows)
-template <int MODE, int PX>
-__device__ __forceinline__ void load_phases(const unsigned char *stage, int W, int N, int x0, bool right,
-                                            const FusedParams &p, const int *s_ptab, const uint32_t *s_btab,
-                                            float (&ph)[PX], bool (&ok)[PX])
-{
-    if (MODE == MODE_PHASE_INPUT) {  // stage = pL f32[W] | pR f32[W] | mL u8[W] | mR u8[W]
-        const float *src = reinterpret_cast<const float *>(stage + (right ? 4 * W : 0)) + x0;
-        const unsigned char *m = stage + (right ? 9 * W : 8 * W) + x0;
-#pragma unroll
-        for (int q = 0; q < PX; q++) {
-            ph[q] = src[q];
-            ok[q] = m[q] != 0 && (!right || ph[q] == ph[q]);  // a NaN on the right never matches
-        }
-    } else if (SLR_ABLATE(8)) {
-        const unsigned char *r0 = stage + (right ? (size_t)N * W : 0) + x0;
-#pragma unroll
-        for (int q = 0; q < PX; q++) ph[q] = (float)r0[2 * W + q] + 0.01f * (float)r0[6 * W + q], ok[q] = r0[q] > r0[W + q];
-    } else {
-        decode_px<MODE, PX>(stage + (right ? (size_t)N * W : 0), W, x0, p, s_ptab, s_btab, ph, ok);
-    }
-}
-
-// Shared-memory tables of one row.
-struct RowTables {
-    uint2 *ent;   // [T]  {x = distinct right phase (float bits), y = smallest right column carrying it}
-    int *head;    // [2T] bucket heads (-1 = empty)
-    int *nxt;     // [2T] node n = entry + T*(0|1)
-    int T, logT;
-};
-
-// value -> min column, deduplicated, for PX right pixels of columns col0 .. col0+PX-1.  The pixels advance in lock
-// step (all first probes, then all claims, then all minima, then all bucket links) so that their shared-memory
-// round trips overlap.  The thread that claims a new value also files it under the bucket(s) its +-0.1 match
-// window touches.
-template <int PX, bool CLAMP>
-__device__ __forceinline__ void insert_right(const RowTables &t, const float (&ph)[PX], const bool (&ok)[PX], int col0)
-{
-    const int T = t.T, HB = 2 * t.T;
-    uint32_t key[PX], h[PX], cur[PX];
-    int mk[PX];
-    bool need[PX], claimed[PX];
-#pragma unroll
-    for (int q = 0; q < PX; q++) {
-        key[q] = __float_as_uint(__fadd_rn(ph[q], 0.0f));  // -0 -> +0
-        h[q] = slot_of(key[q], t.logT);
-        // the same value one column to the left is already filed with a smaller column
-        need[q] = ok[q] && !(q > 0 && ok[q > 0 ? q - 1 : 0] && key[q] == key[q > 0 ? q - 1 : 0]);
-    }
-#pragma unroll
-    for (int q = 0; q < PX; q++) {
-        const uint2 e = need[q] ? t.ent[h[q]] : make_uint2(key[q], 0u);
-        cur[q] = e.x;
-        mk[q] = (int)e.y;
-    }
-#pragma unroll
-    for (int q = 0; q < PX; q++) {
-        claimed[q] = false;
-        if (need[q] && cur[q] == KEY_EMPTY) {
-            cur[q] = atomicCAS(&t.ent[h[q]].x, KEY_EMPTY, key[q]);
-            mk[q] = INT_MAX;
-            claimed[q] = cur[q] == KEY_EMPTY;
-            if (claimed[q]) cur[q] = key[q];
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < PX; q++) {
-        // collision (need[q] is set here): double hashing, odd stride.  Linear probing's longest run at the 0.6 load
-        // of a row of all-distinct phases is ~75 slots, and one such lane stalls its warp for thousands of cycles.
-        const uint32_t stride = ((key[q] * 0x7FEB352Du) >> 9) | 1u;
-        while (cur[q] != key[q]) {
-            h[q] = (h[q] + stride) & (T - 1);
-            const uint2 n = t.ent[h[q]];
-            cur[q] = n.x;
-            mk[q] = (int)n.y;
-            if (cur[q] == KEY_EMPTY) {
-                cur[q] = atomicCAS(&t.ent[h[q]].x, KEY_EMPTY, key[q]);
-                mk[q] = INT_MAX;
-                claimed[q] = cur[q] == KEY_EMPTY;
-                if (claimed[q]) cur[q] = key[q];
-            }
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < PX; q++)
-        if (need[q] && col0 + q < mk[q]) atomicMin(reinterpret_cast<int *>(&t.ent[h[q]].y), col0 + q);
-#pragma unroll
-    for (int q = 0; q < PX; q++) {
-        if (claimed[q]) {
-            const float v = __uint_as_float(key[q]);
-            const int lo = window_bucket<CLAMP>(__fsub_rn(v, 0.11f)), hi = window_bucket<CLAMP>(__fadd_rn(v, 0.11f));
-            t.nxt[h[q]] = atomicExch(&t.head[lo & (HB - 1)], (int)h[q]);
-            if (hi != lo) t.nxt[h[q] + T] = atomicExch(&t.head[hi & (HB - 1)], (int)h[q] + T);
-        }
-    }
-}
-
-// smallest right column whose phase matches v (INT_MAX = none): walk the chain of v's bucket
-template <bool CLAMP>
-__device__ __forceinline__ int first_match(const RowTables &t, float v)
-{
-    int best = INT_MAX;
-    int n = t.head[window_bucket<CLAMP>(v) & (2 * t.T - 1)];
-    while (n >= 0) {
-        const uint2 e = t.ent[n & (t.T - 1)];
-        n = t.nxt[n];
-        if (slr::phase_match(v, __uint_as_float(e.x))) best = min(best, (int)e.y);
-    }
-    return best;
-}
+using namespace slr_fused;
 
 // MAXT/MINB: launch bounds.  QPX: left pixels per lane in one query group (group = 32*QPX pixels).
 template <int MODE, int MAXT, int MINB, int QPX>
