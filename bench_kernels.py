@@ -210,6 +210,24 @@ def main():
     rows[rows_before]["speedup_vs_cpu_port"] = (c / (ms * 1e-3)) if c else None
     e2.close()
 
+    # the same at the camera's full size (one scan)
+    W3, H3 = 1280, 1024
+    e3 = slr_b200.Engine(W3, H3, max_batch=1)
+    cams3 = cases.gray_only_rig(W3, H3)
+    e3.set_calib(cams3, Q)
+    h_go3 = synth.synth_gray(W3, H3, seed=31, rows=True, integer_disparity=True, noise_dn=1.0)[None]
+    go3 = torch.from_numpy(h_go3).cuda()
+    nc3, nr3 = slr_b200.gray_num_bits(W3), slr_b200.gray_num_bits(H3)
+    col3, row3, m3 = e3.gray_decode(go3, nc3, nr3, 40, 3, W3, H3)
+    ms = timed(lambda: e3.bucket_triangulate(col3, row3, m3, W3, H3))
+    d3 = [orc.gray_decode(h_go3[0, cam], nc3, nr3, 40, 3, W3, H3) for cam in range(2)] if orc else None
+    c = cpu_time(lambda: orc.gray_triangulate(d3[0][0], d3[0][1], d3[0][2], d3[1][0], d3[1][1], d3[1][2], W3, H3, cams3)) if orc else None
+    rows_before = len(rows)
+    report("k3c bucket triangulate (1280x1024, 1 scan)", "decodePaterns buckets + Reconstruct::triangulation", ms,
+           2 * W3 * H3 * 9 + W3 * H3 * 13, c, W3 * H3, "cells")
+    rows[rows_before]["speedup_vs_cpu_port"] = (c / (ms * 1e-3)) if c else None
+    e3.close()
+
     print(f"\n| kernel | replaces | ms ({B} scans) | algorithmic MB | GB/s | of {peak:.0f} GB/s ({peak_src.split(' ')[0]}) | CPU port s/scan ({nthreads} thr) | x CPU port |")
     print("|---|---|---|---|---|---|---|---|")
     for r in rows:
