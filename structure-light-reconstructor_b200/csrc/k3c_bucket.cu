@@ -9,7 +9,7 @@
 // (float sum, u8 count that wraps and resets).  The summation order matters for the float sum, so it is kept.
 //
 // GPU plan per scan (a counting sort by cell, then one thread per projector cell):
-//   kc_count    histogram of cells per camera (global atomics)
+//   kc_count    histogram of cells per camera (global atomics; the returned value is the pixel's slot in its slice)
 //   kc_scan*    exclusive scan over the 2*ncell counters (three small kernels)
 //   kc_scatter  pixel keys (x*H + y, i.e. column-major rank) into their cell's slice, any order
 //   kc_rays     (once per calibration) the unit ray of every camera pixel: undistortPoints in fp64, image -> world,
@@ -31,15 +31,21 @@ struct BucketCalib {
     int has_rigid;
 };
 
+// histogram of cells per camera; the value the atomic returns is the pixel's slot inside its cell's slice (any order
+// will do: kc_cells sorts each slice), kept for kc_scatter so that the second pass needs no atomics
 __global__ void kc_count(const int32_t *__restrict__ col, const int32_t *__restrict__ row,
-                         const uint8_t *__restrict__ mask, int P, int scan_h, int ncell, int *__restrict__ count)
+                         const uint8_t *__restrict__ mask, int P, int scan_h, int ncell, int *__restrict__ count,
+                         int *__restrict__ slot)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over 2*P (cam-major)
     if (idx >= 2 * P) return;
-    if (!mask[idx]) return;
-    const int cam = idx / P;
-    const long long cell = (long long)col[idx] * scan_h + row[idx];  // ac(x, y) = x*scan_h + y (reconstruct.h:94-97)
-    if (cell >= 0 && cell < ncell) atomicAdd(&count[cam * ncell + (int)cell], 1);  // out-of-table cells: dropped
+    int s = -1;
+    if (mask[idx]) {
+        const int cam = idx / P;
+        const long long cell = (long long)col[idx] * scan_h + row[idx];  // ac(x, y) = x*scan_h + y (reconstruct.h:94-97)
+        if (cell >= 0 && cell < ncell) s = atomicAdd(&count[cam * ncell + (int)cell], 1);  // out-of-table cells: dropped
+    }
+    slot[idx] = s;
 }
 
 // exclusive scan of n ints: per-block partial sums, scan of the partials, final add
@@ -104,18 +110,18 @@ __global__ void kc_scan_add(int *__restrict__ out, int n, const int *__restrict_
 }
 
 __global__ void kc_scatter(const int32_t *__restrict__ col, const int32_t *__restrict__ row,
-                           const uint8_t *__restrict__ mask, int W, int H, int scan_h, int ncell,
-                           const int *__restrict__ start, int *__restrict__ cursor, int *__restrict__ items)
+                           const int *__restrict__ slot, int W, int H, int scan_h, int ncell,
+                           const int *__restrict__ start, int *__restrict__ items)
 {
     const int P = W * H;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 2 * P) return;
-    if (!mask[idx]) return;
+    const int sl = slot[idx];
+    if (sl < 0) return;
     const int cam = idx / P, p = idx - cam * P;
     const long long cell = (long long)col[idx] * scan_h + row[idx];
-    if (cell < 0 || cell >= ncell) return;
     const int c = cam * ncell + (int)cell;
-    const int pos = start[c] + atomicAdd(&cursor[c], 1);
+    const int pos = start[c] + sl;
     const int x = p % W, y = p / W;
     items[pos] = x * H + y;  // column-major rank: the order decodePaterns visits camera pixels (:60-61)
 }
@@ -319,7 +325,7 @@ slr_status slr_launch_bucket_triangulate(slr_engine *e, const int32_t *d_col, co
     const int nblocks = (n + KC_THREADS * 4 - 1) / (KC_THREADS * 4);
 
     // scratch for one scan (sized on first use / growth)
-    const size_t need = ((size_t)3 * n + nblocks + 2 * (size_t)P + 16) * sizeof(int);
+    const size_t need = ((size_t)2 * n + nblocks + 4 * (size_t)P + 16) * sizeof(int);
     if (e->bucket_scratch_bytes < need) {
         if (e->d_bucket_scratch) SLR_CHECK_CUDA(cudaFree(e->d_bucket_scratch));
         e->d_bucket_scratch = nullptr;
@@ -327,8 +333,8 @@ slr_status slr_launch_bucket_triangulate(slr_engine *e, const int32_t *d_col, co
         SLR_CHECK_CUDA(cudaMalloc(&e->d_bucket_scratch, need));
         e->bucket_scratch_bytes = need;
     }
-    int *count = (int *)e->d_bucket_scratch, *start = count + n, *cursor = start + n, *bsum = cursor + n;
-    int *items = bsum + nblocks;
+    int *count = (int *)e->d_bucket_scratch, *start = count + n, *bsum = start + n;
+    int *items = bsum + nblocks, *slot = items + 2 * P;
 
     BucketCalib cal;
     cal.cam[0] = e->cams[0];
@@ -354,9 +360,8 @@ slr_status slr_launch_bucket_triangulate(slr_engine *e, const int32_t *d_col, co
         const int32_t *col = d_col + (size_t)b * 2 * P, *row = d_row + (size_t)b * 2 * P;
         const uint8_t *mask = d_mask + (size_t)b * 2 * P;
         SLR_CHECK_CUDA(cudaMemsetAsync(count, 0, (size_t)n * sizeof(int), e->stream));
-        SLR_CHECK_CUDA(cudaMemsetAsync(cursor, 0, (size_t)n * sizeof(int), e->stream));
         const int pix_blocks = (int)((2 * P + KC_THREADS - 1) / KC_THREADS);
-        kc_count<<<pix_blocks, KC_THREADS, 0, e->stream>>>(col, row, mask, (int)P, scan_h, ncell, count);
+        kc_count<<<pix_blocks, KC_THREADS, 0, e->stream>>>(col, row, mask, (int)P, scan_h, ncell, count, slot);
         SLR_CHECK_LAUNCH(e);
         kc_scan_blocks<<<nblocks, KC_THREADS, 0, e->stream>>>(count, n, start, bsum);
         SLR_CHECK_LAUNCH(e);
@@ -364,7 +369,7 @@ slr_status slr_launch_bucket_triangulate(slr_engine *e, const int32_t *d_col, co
         SLR_CHECK_LAUNCH(e);
         kc_scan_add<<<(n + KC_THREADS - 1) / KC_THREADS, KC_THREADS, 0, e->stream>>>(start, n, bsum);
         SLR_CHECK_LAUNCH(e);
-        kc_scatter<<<pix_blocks, KC_THREADS, 0, e->stream>>>(col, row, mask, W, H, scan_h, ncell, start, cursor, items);
+        kc_scatter<<<pix_blocks, KC_THREADS, 0, e->stream>>>(col, row, slot, W, H, scan_h, ncell, start, items);
         SLR_CHECK_LAUNCH(e);
         kc_cells<<<(ncell + 127) / 128, 128, 0, e->stream>>>(start, count, items, W, H, ncell, cal, e->d_rays,
                                                              d_sum + (size_t)b * ncell * 3, d_cnt + (size_t)b * ncell,
