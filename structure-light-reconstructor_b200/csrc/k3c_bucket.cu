@@ -10,7 +10,8 @@
 //
 // GPU plan per scan (a counting sort by cell, then one thread per projector cell):
 //   kc_count    histogram of cells per camera (global atomics; the returned value is the pixel's slot in its slice)
-//   kc_scan*    exclusive scan over the 2*ncell counters (three small kernels)
+//   kc_scan*    exclusive scan over the 2*ncell counters (block-local prefixes + scanned block totals; the users add
+//               the two)
 //   kc_scatter  pixel keys (x*H + y, i.e. column-major rank) into their cell's slice, any order
 //   kc_rays     (once per calibration) the unit ray of every camera pixel: undistortPoints in fp64, image -> world,
 //               normalise; 31 MB at 1280x1024, so that pairs cost loads instead of 300 fp64 instructions per ray
@@ -48,7 +49,7 @@ __global__ void kc_count(const int32_t *__restrict__ col, const int32_t *__restr
     slot[idx] = s;
 }
 
-// exclusive scan of n ints: per-block partial sums, scan of the partials, final add
+// exclusive scan of n ints: block-local exclusive prefixes + per-block totals (scanned by kc_scan_partials)
 __global__ void kc_scan_blocks(const int *__restrict__ in, int n, int *__restrict__ out, int *__restrict__ block_sums)
 {
     __shared__ int s[KC_THREADS];
@@ -103,15 +104,9 @@ __global__ void kc_scan_partials(int *__restrict__ block_sums, int nblocks)
     }
 }
 
-__global__ void kc_scan_add(int *__restrict__ out, int n, const int *__restrict__ block_sums)
-{
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < n) out[idx] += block_sums[idx / (KC_THREADS * 4)];
-}
-
 __global__ void kc_scatter(const int32_t *__restrict__ col, const int32_t *__restrict__ row,
                            const int *__restrict__ slot, int W, int H, int scan_h, int ncell,
-                           const int *__restrict__ start, int *__restrict__ items)
+                           const int *__restrict__ start, const int *__restrict__ block_sums, int *__restrict__ items)
 {
     const int P = W * H;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -121,7 +116,7 @@ __global__ void kc_scatter(const int32_t *__restrict__ col, const int32_t *__res
     const int cam = idx / P, p = idx - cam * P;
     const long long cell = (long long)col[idx] * scan_h + row[idx];
     const int c = cam * ncell + (int)cell;
-    const int pos = start[c] + sl;
+    const int pos = start[c] + block_sums[c / (KC_THREADS * 4)] + sl;   // block-local prefix + scanned block total
     const int x = p % W, y = p / W;
     items[pos] = x * H + y;  // column-major rank: the order decodePaterns visits camera pixels (:60-61)
 }
@@ -230,7 +225,8 @@ __device__ __forceinline__ void sort_slice(int *a, int n)
     }
 }
 
-__global__ void kc_cells(const int *__restrict__ start, const int *__restrict__ count, int *__restrict__ items, int W, int H,
+__global__ void kc_cells(const int *__restrict__ start, const int *__restrict__ block_sums, const int *__restrict__ count,
+                         int *__restrict__ items, int W, int H,
                          int ncell, BucketCalib cal, const float *__restrict__ rays, float *__restrict__ sum,
                          uint8_t *__restrict__ cnt, unsigned long long *__restrict__ n_cells)
 {
@@ -241,7 +237,8 @@ __global__ void kc_cells(const int *__restrict__ start, const int *__restrict__ 
         float acc[3] = {0.0f, 0.0f, 0.0f};
         unsigned char num = 0;
         if (n1 > 0 && n2 > 0) {                                            // :436
-            int *l1 = items + start[cell], *l2 = items + start[ncell + cell];
+            int *l1 = items + start[cell] + block_sums[cell / (KC_THREADS * 4)];
+            int *l2 = items + start[ncell + cell] + block_sums[(ncell + cell) / (KC_THREADS * 4)];
             sort_slice(l1, n1);
             sort_slice(l2, n2);
             for (int c1 = 0; c1 < n1; c1++) {
@@ -367,11 +364,9 @@ slr_status slr_launch_bucket_triangulate(slr_engine *e, const int32_t *d_col, co
         SLR_CHECK_LAUNCH(e);
         kc_scan_partials<<<1, KC_THREADS, 0, e->stream>>>(bsum, nblocks);
         SLR_CHECK_LAUNCH(e);
-        kc_scan_add<<<(n + KC_THREADS - 1) / KC_THREADS, KC_THREADS, 0, e->stream>>>(start, n, bsum);
+        kc_scatter<<<pix_blocks, KC_THREADS, 0, e->stream>>>(col, row, slot, W, H, scan_h, ncell, start, bsum, items);
         SLR_CHECK_LAUNCH(e);
-        kc_scatter<<<pix_blocks, KC_THREADS, 0, e->stream>>>(col, row, slot, W, H, scan_h, ncell, start, items);
-        SLR_CHECK_LAUNCH(e);
-        kc_cells<<<(ncell + 127) / 128, 128, 0, e->stream>>>(start, count, items, W, H, ncell, cal, e->d_rays,
+        kc_cells<<<(ncell + 127) / 128, 128, 0, e->stream>>>(start, bsum, count, items, W, H, ncell, cal, e->d_rays,
                                                              d_sum + (size_t)b * ncell * 3, d_cnt + (size_t)b * ncell,
                                                              d_n_cells);
         SLR_CHECK_LAUNCH(e);
