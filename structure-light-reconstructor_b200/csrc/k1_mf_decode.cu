@@ -167,6 +167,70 @@ struct CorrectedCoef {
     float sn[16];
 };
 
+// corrected mode with compile-time F and S (BASELINE config 5: 4 frequencies x 8 steps): 8 pixels per thread, all
+// 2 + F*S plane loads issued up front as 64-bit streaming loads, the N-step sums, the cascade and its levels in
+// registers.  Same arithmetic, pixel for pixel, as the generic kernel below.
+template <int F, int S>
+__global__ void __launch_bounds__(K1_THREADS, 2)
+k1_mf_decode_corrected_fs(const uint8_t *__restrict__ stack, size_t P, long long chunks_per_view, long long total_chunks,
+                          int black_thr, CorrectedCoef coef, float *__restrict__ phase, uint8_t *__restrict__ mask)
+{
+    constexpr int N = 2 + F * S;
+    for (long long chunk = (long long)blockIdx.x * K1_THREADS + threadIdx.x; chunk < total_chunks;
+         chunk += (long long)gridDim.x * K1_THREADS) {
+        const long long view = chunk / chunks_per_view;
+        const long long c = chunk - view * chunks_per_view;
+        const uint8_t *src = stack + (size_t)view * N * P + (size_t)c * 8;
+        uint32_t img[N][2];
+#pragma unroll
+        for (int n = 0; n < N; n++) {
+            const uint2 v = slr::ldg_stream_u2(src + (size_t)n * P);
+            img[n][0] = v.x, img[n][1] = v.y;
+        }
+        const size_t o = (size_t)view * P + (size_t)c * 8;
+        uint32_t mk[2];
+#pragma unroll
+        for (int w = 0; w < 2; w++) {
+            float ph[4];
+            uint32_t m4 = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                bool ok = (int)slr::byte_of(img[0][w], i) - (int)slr::byte_of(img[1][w], i) > black_thr;
+                float lvl[F];
+#pragma unroll
+                for (int f = 0; f < F; f++) {
+                    float nn = 0.0f, dd = 0.0f;
+                    if (S == 4) {   // exact integer form: num = G4-G2, den = G1-G3
+                        const int in = (int)slr::byte_of(img[2 + 4 * f + 3][w], i) - (int)slr::byte_of(img[2 + 4 * f + 1][w], i);
+                        const int id = (int)slr::byte_of(img[2 + 4 * f + 0][w], i) - (int)slr::byte_of(img[2 + 4 * f + 2][w], i);
+                        if (in == 0 && id == 0) ok = false;
+                        nn = (float)in, dd = (float)id;
+                    } else {
+#pragma unroll
+                        for (int s2 = 0; s2 < S; s2++) {
+                            const float g = (float)(int)slr::byte_of(img[2 + S * f + s2][w], i);
+                            nn = __fsub_rn(nn, __fmul_rn(g, coef.sn[s2]));
+                            dd = __fadd_rn(dd, __fmul_rn(g, coef.cs[s2]));
+                        }
+                        if (__fadd_rn(__fmul_rn(nn, nn), __fmul_rn(dd, dd)) < 0.25f) ok = false;
+                    }
+                    lvl[f] = slr::atan2_pos(nn, dd);
+                }
+#pragma unroll
+                for (int n2 = F; n2 > 1; n2--)
+#pragma unroll
+                    for (int j = 0; j + 1 < n2; j++) lvl[j] = slr::wrap_2pi(__fsub_rn(lvl[j], lvl[j + 1]));
+                const float p = slr::phase_scale_corrected(lvl[0]);
+                ph[i] = ok ? p : slr::qnan();
+                m4 |= (ok ? 1u : 0u) << (8 * i);
+            }
+            slr::stg_stream_f4(phase + o + 4 * w, make_float4(ph[0], ph[1], ph[2], ph[3]));
+            mk[w] = m4;
+        }
+        *reinterpret_cast<uint2 *>(mask + o) = make_uint2(mk[0], mk[1]);
+    }
+}
+
 template <int PX>
 __global__ void __launch_bounds__(K1_THREADS)
 k1_mf_decode_corrected(const uint8_t *__restrict__ stack, size_t P, long long chunks_per_view, long long total_chunks,
@@ -293,6 +357,17 @@ slr_status slr_launch_mf_decode(slr_engine *e, const uint8_t *d_stack, int views
         if (blocks < 1) blocks = 1;
         k1_mf_decode_corrected_3x4<4><<<(unsigned)blocks, K1_THREADS, 0, e->stream>>>(d_stack, P, cpv, total, black_thr,
                                                                                      d_phase, d_mask);
+        SLR_CHECK_LAUNCH(e);
+        return SLR_OK;
+    }
+    if (F == 4 && S == 8 && P % 8 == 0 && (((uintptr_t)d_stack | (uintptr_t)d_mask) % 8) == 0 && ((uintptr_t)d_phase % 16) == 0) {
+        const long long cpv = (long long)(P / 8), total = cpv * views;
+        long long blocks = (total + K1_THREADS - 1) / K1_THREADS;
+        const long long cap = (long long)e->num_sms * 2 * 4;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        k1_mf_decode_corrected_fs<4, 8><<<(unsigned)blocks, K1_THREADS, 0, e->stream>>>(d_stack, P, cpv, total, black_thr, coef,
+                                                                                       d_phase, d_mask);
         SLR_CHECK_LAUNCH(e);
         return SLR_OK;
     }
