@@ -19,7 +19,7 @@
 
 namespace {
 
-constexpr int K3_THREADS = 256;
+constexpr int K3_MAX_THREADS = 1024;   // rows whose context allows one CTA per SM only run the widest CTA
 
 struct K3aParams {
     const float *phase;     // [batch][2][H][W]
@@ -33,7 +33,7 @@ struct K3aParams {
     slr_calib_dev calib;
 };
 
-__global__ void __launch_bounds__(K3_THREADS)
+__global__ void __launch_bounds__(K3_MAX_THREADS)
 k3a_phase_match(const K3aParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -50,7 +50,7 @@ k3a_phase_match(const K3aParams p)
     int *o_k = reinterpret_cast<int *>(o_xyz + 3 * W);
     uint8_t *o_valid = reinterpret_cast<uint8_t *>(o_k + W);
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     if (tid == 0) {
         slr::mbar_init(&bar[0], 1);
         slr::mbar_init(&bar[1], 1);
@@ -79,7 +79,7 @@ k3a_phase_match(const K3aParams p)
         const int s = it & 1;
         if (tid == 0 && r + gridDim.x < rows) issue_row(r + gridDim.x, s ^ 1);
 
-        for (int h = tid; h < HB; h += K3_THREADS) head[h] = -1;
+        for (int h = tid; h < HB; h += nthr) head[h] = -1;
         slr::mbar_wait(&bar[s], (it >> 1) & 1);
         const unsigned char *st = stage0 + s * stage_bytes;
         const float *pL = reinterpret_cast<const float *>(st);
@@ -89,11 +89,11 @@ k3a_phase_match(const K3aParams p)
         __syncthreads();
 
         // hash the right row: chained lists keyed by phase bucket.  Columns are pushed in descending blocks of
-        // K3_THREADS (one barrier per block), so every chain lists block 0's columns first, then block 1's, ...:
+        // blockDim.x (one barrier per block), so every chain lists block 0's columns first, then block 1's, ...:
         // a walk can stop at the first entry of a later block than its best match (rows whose phases repeat
         // hundreds of times would otherwise cost a full chain per left pixel)
-        for (int kb = (W - 1) / K3_THREADS; kb >= 0; kb--) {
-            const int k = kb * K3_THREADS + tid;
+        for (int kb = (W - 1) / nthr; kb >= 0; kb--) {
+            const int k = kb * nthr + tid;
             if (k < W && mR[k]) {
                 const int slot = slr::phase_bucket(pR[k]) & (HB - 1);
                 next[k] = atomicExch(&head[slot], k);
@@ -106,7 +106,7 @@ k3a_phase_match(const K3aParams p)
         const long long b = r / p.H;
         const int i = (int)(r - b * p.H);
         const size_t map_row = (size_t)i * W;
-        for (int j = tid; j < W; j += K3_THREADS) {
+        for (int j = tid; j < W; j += nthr) {
             int best = INT_MAX;
             if (mL[j]) {
                 const float pl = pL[j];
@@ -115,7 +115,7 @@ k3a_phase_match(const K3aParams p)
                 for (int db = -1; db <= 1; db++) {
                     int k = head[(b0 + db) & (HB - 1)];
                     while (k >= 0) {
-                        if (best != INT_MAX && k / K3_THREADS > best / K3_THREADS) break;  // only later blocks follow
+                        if (best != INT_MAX && k / nthr > best / nthr) break;  // only later blocks follow
                         if (slr::phase_match(pl, pR[k])) best = min(best, k);
                         k = next[k];
                     }
@@ -201,14 +201,19 @@ slr_status slr_launch_match_phase(slr_engine *e, const float *d_phase, const uin
                         + (size_t)12 * e->W + (size_t)4 * e->W + (size_t)e->W;        // xyz, k, valid
     SLR_REQUIRE(smem <= 227 * 1024, "image width %d needs %zu bytes of shared memory per row", e->W, smem);
     SLR_CHECK_CUDA(cudaFuncSetAttribute(k3a_phase_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    SLR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3a_phase_match, K3_THREADS, smem));
+    // 256-thread CTAs while several row contexts fit an SM; a single resident CTA gets 1024 threads
+    int threads = 256, occ = 0;
+    SLR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3a_phase_match, threads, smem));
+    if (occ <= 1) {
+        threads = (e->W >= 2048) ? 1024 : 512;
+        SLR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k3a_phase_match, threads, smem));
+    }
     if (occ < 1) occ = 1;
     long long grid = (long long)e->num_sms * occ;
     const long long rows = (long long)batch * e->H;
     if (grid > rows) grid = rows;
     if (grid < 1) return SLR_OK;
-    k3a_phase_match<<<(unsigned)grid, K3_THREADS, smem, e->stream>>>(p);
+    k3a_phase_match<<<(unsigned)grid, threads, smem, e->stream>>>(p);
     SLR_CHECK_LAUNCH(e);
     return SLR_OK;
 }
