@@ -62,6 +62,26 @@ def load_traffic():
     return None
 
 
+def bind_to_gpu_numa_node(index):
+    """N > 1: run this rank's host threads (and first-touch its pinned staging buffers) on the CPUs NVML reports as
+    local to the GPU, so that the end-to-end leg's host<->device copies do not cross the socket interconnect.
+    Returns the number of CPUs bound to, or None when NVML / the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -209,6 +229,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -334,6 +355,7 @@ def main():
                        "scans_per_gpu_per_step": B, "mode": "strict (reference arithmetic)", "black_threshold": BLACK_THR,
                        "l2": f"inputs {B * 2 * N_IMG * W * H / 1e6:.0f} MB per step exceed the 126 MB L2",
                        "parallelism": f"scans sharded over {world} GPU(s), no data-path collective",
+                       "host_cpus_bound_per_rank": numa,
                        "points_per_step": points_all, "mpixels_per_s": world * B * W * H / (ms_per_step * 1e-3) / 1e6},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic(), "peak_source": peak_src,
