@@ -5,7 +5,7 @@ lib = os.environ.get("LIB", "/root/repo/structure-light-reconstructor_b200/libsl
 os.makedirs("/tmp/cub", exist_ok=True)
 for f in glob.glob("/tmp/cub/*.cubin"): os.remove(f)
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd="/tmp/cub", capture_output=True)
-cub = [f for f in glob.glob("/tmp/cub/*.cubin") if "k_fused" in f][0]
+cub = [f for f in glob.glob("/tmp/cub/*.cubin") if os.environ.get("CUBIN", "k_fused") in f][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout.splitlines()
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
