@@ -113,4 +113,23 @@ int duke_export_mesh(const float *sums, const uint8_t *counts, const int *color,
     if (nf) *nf = mc.faceCount();
     return mc.ok() ? 0 : -1;
 }
+
+// The text stage of MeshCreator alone (no GPU): index arrays supplied by the caller (the CPU tests pass the oracle's)
+int duke_write_mesh_text(const float *sums, const uint8_t *counts, const int *color, int w, int h, int obj, const float *vert,
+                         const int32_t *src, const int32_t *faces, unsigned long long nv, unsigned long long nf, const char *path)
+{
+    PointCloudImage pc(w, h, color != nullptr);
+    for (int j = 0; j < h; j++)
+        for (int i = 0; i < w; i++) {
+            const size_t q = (size_t)j * w + i;
+            for (int k = 0; k < counts[q]; k++) {
+                const duke::Point3f p(k == 0 ? sums[q * 3] : -0.f, k == 0 ? sums[q * 3 + 1] : -0.f, k == 0 ? sums[q * 3 + 2] : -0.f);
+                if (color)
+                    pc.addPoint(i, j, p, k == 0 ? duke::Vec3i(color[q * 3], color[q * 3 + 1], color[q * 3 + 2]) : duke::Vec3i(0, 0, 0));
+                else
+                    pc.addPoint(i, j, p);
+            }
+        }
+    return duke::write_mesh_text(path, obj != 0, &pc, vert, src, faces, (size_t)nv, (size_t)nf) ? 0 : -1;
+}
 }  // extern "C"

@@ -54,26 +54,14 @@ std::vector<std::string> format_parallel(size_t n, size_t max_bytes_per_item, Fn
 
 }  // namespace
 
-bool MeshCreator::exportMesh(const std::string &path, bool obj)
+namespace duke {
+
+// The text of exportPlyMesh / exportObjMesh (meshcreator.cpp:112-163 / :30-62) from the index arrays of
+// slr_mesh_index: nv vertices (x y z, source element j*w+i for the colour lookup), nf faces.
+bool write_mesh_text(const std::string &path, bool obj, PointCloudImage *pc, const float *vert, const int32_t *src,
+                     const int32_t *faces, size_t nv, size_t nf)
 {
-    ok_ = false;
-    nv_ = nf_ = 0;
-    const size_t px = (size_t)w * h;
-    std::vector<float> vert(px * 3);
-    std::vector<int32_t> src(px), faces(px * 6);
-    unsigned long long counts[2] = {0, 0};
-
-    slr_engine *eng = duke::shared_engine(0, w, h);
-    if (!eng) {
-        fprintf(stderr, "MeshCreator: %s\n", slr_last_error());
-        return false;
-    }
-    const slr_status st = slr_mesh_index_host(eng, cloud->sums().data(), cloud->counts().data(), w, h, obj ? 1 : 0,
-                                              vert.data(), src.data(), faces.data(), counts);
-    if (st != SLR_OK) fprintf(stderr, "MeshCreator: %s\n", slr_last_error());
-    if (st != SLR_OK) return false;
-    const size_t nv = (size_t)counts[0], nf = (size_t)counts[1];
-
+    const int W = pc->getWidth();
     FILE *fp = fopen(path.c_str(), "wb");
     if (!fp) return false;
     if (!obj) {   // meshcreator.cpp:112-123
@@ -82,8 +70,6 @@ bool MeshCreator::exportMesh(const std::string &path, bool obj)
         fprintf(fp, "property uchar red\nproperty uchar green\nproperty uchar blue\n");
         fprintf(fp, "element face %zu\nproperty list uchar int vertex_indices\nend_header\n", nf);
     }
-    PointCloudImage *pc = cloud;
-    const int W = w;
     auto vtext = format_parallel(nv, 3 * 32 + 3 * 12 + 8, [&](char *p, size_t v) {
         if (obj) *p++ = 'v', *p++ = ' ';                       // "v x y z"            (:30)
         p = put_float(p, vert[3 * v + 0]), *p++ = ' ';
@@ -112,7 +98,32 @@ bool MeshCreator::exportMesh(const std::string &path, bool obj)
         return p;
     });
     for (auto &s : ftext) fwrite(s.data(), 1, s.size(), fp);
-    const bool good = fclose(fp) == 0;
+    return fclose(fp) == 0;
+}
+
+}  // namespace duke
+
+bool MeshCreator::exportMesh(const std::string &path, bool obj)
+{
+    ok_ = false;
+    nv_ = nf_ = 0;
+    const size_t px = (size_t)w * h;
+    std::vector<float> vert(px * 3);
+    std::vector<int32_t> src(px), faces(px * 6);
+    unsigned long long counts[2] = {0, 0};
+
+    slr_engine *eng = duke::shared_engine(0, w, h);
+    if (!eng) {
+        fprintf(stderr, "MeshCreator: %s\n", slr_last_error());
+        return false;
+    }
+    const slr_status st = slr_mesh_index_host(eng, cloud->sums().data(), cloud->counts().data(), w, h, obj ? 1 : 0,
+                                              vert.data(), src.data(), faces.data(), counts);
+    if (st != SLR_OK) fprintf(stderr, "MeshCreator: %s\n", slr_last_error());
+    if (st != SLR_OK) return false;
+    const size_t nv = (size_t)counts[0], nf = (size_t)counts[1];
+
+    const bool good = duke::write_mesh_text(path, obj, cloud, vert.data(), src.data(), faces.data(), nv, nf);
     nv_ = nv;
     nf_ = nf;
     ok_ = good;

@@ -7,6 +7,11 @@
 
 #include "pointcloudimage.h"
 
+namespace duke {
+bool write_mesh_text(const std::string &path, bool obj, PointCloudImage *pc, const float *vert, const int32_t *src,
+                     const int32_t *faces, size_t nv, size_t nf);
+}
+
 class MeshCreator {
 public:
     MeshCreator(PointCloudImage *in);

@@ -168,3 +168,42 @@ def test_virtualcamera_loader(duke, tmp_path):
     assert duke.duke_load_camera_matrix(str(tmp_path / "cam_matrix.txt").encode(), v) == 1
     assert list(v) == [np.float32(2400.123456789), np.float32(2401.25), np.float32(640.5), np.float32(511.75)]
     assert duke.duke_load_camera_matrix(str(tmp_path / "missing.txt").encode(), v) == 0
+
+
+@pytest.mark.parametrize("color", [True, False])
+@pytest.mark.parametrize("obj", [False, True])
+def test_mesh_text_stage_writes_the_reference_bytes(duke, tmp_path, color, obj):
+    """MeshCreator's text stage (threaded std::to_chars formatting) on the oracle's index arrays == the reference's
+    exportPlyMesh / exportObjMesh bytes (golden fixture made by the reference's own MeshCreator).  The index passes
+    themselves run on the GPU and are checked in the -m gpu suite."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    import oracle_lib
+    orc = oracle_lib.load()
+    golden = dict(np.load(os.path.join(ROOT, "tests", "golden", "ref_mesh.npz")))
+    pts, cnt, col = cases.mesh_cloud(color=color)
+    h, w = cnt.shape
+    vert, src, faces = orc.mesh_index(pts, cnt, w, h, 1 if obj else 0)
+    vert, src, faces = np.ascontiguousarray(vert), np.ascontiguousarray(src), np.ascontiguousarray(faces)
+    ci = None if col is None else np.ascontiguousarray(col, np.int32)
+    path = tmp_path / "m.txt"
+    rc = duke.duke_write_mesh_text(ptr(pts), ptr(cnt), ptr(ci) if ci is not None else None, w, h, int(obj), ptr(vert), ptr(src),
+                                   ptr(faces), C.c_ulonglong(len(vert)), C.c_ulonglong(len(faces)), str(path).encode())
+    assert rc == 0
+    assert open(path, "rb").read() == golden[f"{'c' if color else 'n'}_{'obj' if obj else 'ply'}"].tobytes()
+    # a larger cloud: enough items for the multi-threaded formatter (>= 4096), against the oracle's writer
+    rng = np.random.default_rng(5)
+    h, w = 120, 97
+    cnt = (rng.random((h, w)) < 0.8).astype(np.uint8)
+    pts = (rng.normal(0, 400, (h, w, 3)) * cnt[..., None]).astype(np.float32)
+    col = rng.integers(0, 256, (h, w, 3)).astype(np.uint8) if color else None
+    vert, src, faces = orc.mesh_index(pts, cnt, w, h, 1 if obj else 0)
+    vert, src, faces = np.ascontiguousarray(vert), np.ascontiguousarray(src), np.ascontiguousarray(faces)
+    ci = None if col is None else np.ascontiguousarray(col, np.int32)
+    rc = duke.duke_write_mesh_text(ptr(pts), ptr(cnt), ptr(ci) if ci is not None else None, w, h, int(obj), ptr(vert), ptr(src),
+                                   ptr(faces), C.c_ulonglong(len(vert)), C.c_ulonglong(len(faces)), str(tmp_path / "b.txt").encode())
+    assert rc == 0 and len(vert) >= 4096
+    orc.export_mesh(pts, cnt, w, h, tmp_path / "o.txt", obj, ci)
+    assert open(tmp_path / "b.txt", "rb").read() == open(tmp_path / "o.txt", "rb").read()
