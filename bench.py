@@ -282,7 +282,12 @@ def main():
     gather = None
     if args.gather and world > 1:
         from slr_b200 import parallel
-        asm = parallel.CloudAssembly(B, H, W, torch.device("cuda", local_rank), slots=2)
+        # the collective goes through the C ABI (slr_allgather: NCCL bound by the library); torch.distributed only
+        # carries the 128-byte NCCL id to the other ranks
+        ids = [slr_b200.Engine.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = eng.nccl_comm_create(world, rank, ids[0])
+        asm = parallel.CloudAssembly(B, H, W, torch.device("cuda", local_rank), slots=2, native=(eng, comm))
         outs = []
         for slot in range(2):   # the kernels write straight into this rank's block of the assembled cloud
             xl, vl = asm.local_views(slot)
@@ -374,7 +379,7 @@ def main():
             g_ms = gather["ms"] / args.steps
             result["with_allgather"] = {"value": points_all / (g_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": g_ms,
                                         "bytes_received_per_rank_per_step": gather["bytes_received_per_rank_per_step"],
-                                        "note": "every step followed by an in-place all_gather_into_tensor of xyz+valid (NCCL over NVLink) on a side stream, double buffered; not in 'value'"}
+                                        "note": "every step followed by slr_allgather (in-place ncclAllGather of xyz+valid over NVLink through the C ABI) on a side stream, double buffered; not in 'value'"}
         if world == 1 and not args.no_cpu:
             h = h_in[:2]
             v1, sc1, dt1, nt1 = cpu_port_rate(h, cams, Q, 0, 10.0, 2000)

@@ -184,6 +184,22 @@ SLR_API slr_status slr_run_ge_host(slr_engine *e, const uint8_t *h_stack, int ba
 SLR_API slr_status slr_run_gray_host(slr_engine *e, const uint8_t *h_stack, int batch, int nbits_col, int nbits_row,
                                      int black_thr, int white_thr, int scan_w, int scan_h, float *h_sum,
                                      uint8_t *h_cnt, unsigned long long *h_n_cells);
+/* ---- multi-GPU assembly ------------------------------------------------------------- */
+/* Scans are independent, so the data path needs no collective (one engine per GPU, each with its own scans).  Where a
+ * caller wants every rank's cloud on every GPU (the north star's "single NCCL all-gather of the output point cloud"),
+ * slr_allgather assembles them IN PLACE over NVLink: d_xyz_all = float [world*scans_per_rank][H][W][3] and
+ * d_valid_all = uint8 [world*scans_per_rank][H][W], of which this rank has already filled block `rank` (pass
+ * d_xyz_all + rank*scans_per_rank*H*W*3 as the d_xyz of slr_run_mf / slr_run_ge).  Stream-ordered on the engine's
+ * stream.  nccl_comm is an ncclComm_t of the NCCL library in the process (libnccl.so.2 is bound at run time with
+ * dlopen; libslr_b200.so has no link-time NCCL dependency) — the caller's own, or one made by the helpers below,
+ * which wrap ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy (id128 = 128 bytes, created on one rank and
+ * handed to the others by any means). */
+SLR_API slr_status slr_allgather(slr_engine *e, void *nccl_comm, int world, int rank, int scans_per_rank,
+                                 float *d_xyz_all, uint8_t *d_valid_all);
+SLR_API slr_status slr_nccl_unique_id(void *id128);
+SLR_API slr_status slr_nccl_comm_create(slr_engine *e, void **comm, int world, int rank, const void *id128);
+SLR_API slr_status slr_nccl_comm_destroy(void *comm);
+
 /* ---- mesh indexing ---------------------------------------------------------- */
 /* The index passes of MeshCreator::exportPlyMesh / exportObjMesh, Duke/meshcreator.cpp:16-65, 67-166, on a
  * PointCloudImage stored as the reference stores it (Duke/pointcloudimage.cpp:3-13): d_sum = float [h][w][3]

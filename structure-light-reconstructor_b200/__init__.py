@@ -60,7 +60,8 @@ EXPORTS = [
     "slr_generate_mf_patterns", "slr_mf_decode", "slr_gray_decode", "slr_match_triangulate_phase",
     "slr_match_triangulate_code", "slr_bucket_triangulate", "slr_run_mf", "slr_run_ge", "slr_run_mf_host",
     "slr_run_ge_host", "slr_host_alloc", "slr_host_free", "slr_synth_mf", "slr_synth_gray",
-    "slr_kernel_launches", "slr_mesh_index", "slr_mesh_index_host", "slr_set_rectify_maps", "slr_rectify_stack", "slr_set_host_input_raw", "slr_run_gray_host",
+    "slr_kernel_launches", "slr_mesh_index", "slr_mesh_index_host", "slr_allgather", "slr_nccl_unique_id",
+    "slr_nccl_comm_create", "slr_nccl_comm_destroy", "slr_set_rectify_maps", "slr_rectify_stack", "slr_set_host_input_raw", "slr_run_gray_host",
 ]
 
 
@@ -105,6 +106,10 @@ def capi():
     lib.slr_run_gray_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, C.POINTER(C.c_ulonglong)]
     lib.slr_mesh_index.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
     lib.slr_mesh_index_host.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.slr_allgather.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    lib.slr_nccl_unique_id.argtypes = [vp]
+    lib.slr_nccl_comm_create.argtypes = [vp, C.POINTER(vp), i32, i32, vp]
+    lib.slr_nccl_comm_destroy.argtypes = [vp]
     lib.slr_kernel_launches.argtypes = [vp]
     lib.slr_kernel_launches.restype = C.c_ulonglong
     _lib = lib
@@ -338,6 +343,28 @@ class Engine:
         return int(n.value)
 
     # -- synthetic inputs ---------------------------------------------------------------------
+    # ---- multi-GPU assembly through the C ABI (NCCL bound at run time) ----
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(capi().slr_nccl_unique_id(buf), "slr_nccl_unique_id")
+        return buf.raw
+
+    def nccl_comm_create(self, world: int, rank: int, unique_id: bytes):
+        comm = C.c_void_p(0)
+        buf = C.create_string_buffer(unique_id, 128)
+        _check(self.lib.slr_nccl_comm_create(self.h, C.byref(comm), world, rank, buf), "slr_nccl_comm_create")
+        return comm
+
+    def nccl_comm_destroy(self, comm):
+        _check(self.lib.slr_nccl_comm_destroy(comm), "slr_nccl_comm_destroy")
+
+    def allgather(self, comm, world: int, rank: int, scans_per_rank: int, xyz_all, valid_all):
+        """slr_allgather: in-place NCCL all-gather of the assembled cloud tensors (block `rank` already filled)."""
+        self._bind_stream()
+        _check(self.lib.slr_allgather(self.h, comm, world, rank, scans_per_rank, self._p(xyz_all), self._p(valid_all)),
+               "slr_allgather")
+
     def mesh_index(self, sums, counts, first_vertex=0):
         """slr_mesh_index on device tensors sums [h,w,3] f32 / counts [h,w] u8 -> (vertices [nv,3], vertex_src [nv],
         faces [nf,3]) device tensors (MeshCreator's vertex numbering + faces, Duke/meshcreator.cpp:16-166)."""

@@ -46,12 +46,15 @@ class CloudAssembly:
     stream while step k+1 computes into the other slot (events order producer and consumer both ways).
     Equal shards only (b_local scans on every rank); ragged batches go through `gather_clouds`."""
 
-    def __init__(self, b_local: int, H: int, W: int, device, slots: int = 2, group=None):
+    def __init__(self, b_local: int, H: int, W: int, device, slots: int = 2, group=None, native=None):
+        # native = (engine, ncclComm_t from engine.nccl_comm_create): gather through the C ABI (slr_allgather, NCCL bound
+        # by libslr_b200.so itself) instead of torch.distributed's collective
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.group = torch, dist, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.b = b_local
+        self.native = native
         n = self.world * b_local
         self.xyz = [torch.empty((n, H, W, 3), dtype=torch.float32, device=device) for _ in range(slots)]
         self.valid = [torch.empty((n, H, W), dtype=torch.uint8, device=device) for _ in range(slots)]
@@ -83,8 +86,12 @@ class CloudAssembly:
         self.filled[slot].record(torch.cuda.current_stream())
         with torch.cuda.stream(self.comm):
             self.comm.wait_event(self.filled[slot])
-            self.dist.all_gather_into_tensor(self.xyz[slot], xl, group=self.group)
-            self.dist.all_gather_into_tensor(self.valid[slot], vl, group=self.group)
+            if self.native is not None:
+                eng, comm = self.native   # the engine binds to the current (= communication) stream for this call
+                eng.allgather(comm, self.world, self.rank, self.b, self.xyz[slot], self.valid[slot])
+            else:
+                self.dist.all_gather_into_tensor(self.xyz[slot], xl, group=self.group)
+                self.dist.all_gather_into_tensor(self.valid[slot], vl, group=self.group)
             self.gathered[slot].record(self.comm)
         self.used[slot] = True
         return self.xyz[slot], self.valid[slot]
