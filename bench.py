@@ -52,11 +52,14 @@ def load_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic():
+def load_traffic(scans_per_launch):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), scaled
+    from the capture's scans per launch to this run's."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
+            d = json.load(open(p))
+            return int(d["dram_bytes_per_launch"] * scans_per_launch / d.get("scans_per_launch", 16))
         except Exception:
             return None
     return None
@@ -363,7 +366,7 @@ def main():
                        "host_cpus_bound_per_rank": numa,
                        "points_per_step": points_all, "mpixels_per_s": world * B * W * H / (ms_per_step * 1e-3) / 1e6},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_traffic(), "peak_source": peak_src,
+                         "traffic": load_traffic(B), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg, "kernel_ms_mean": statistics.mean(step_ms),
                          "kernel_ms_median": med_ms,
                          "kernels_per_step": launches / args.steps},
