@@ -75,7 +75,10 @@ typedef struct {
 /* ---- engine --------------------------------------------------------------------------------- */
 
 /* One engine per GPU.  width/height = camera image size (Reconstruct::getParameters camw/camh,
- * Duke/reconstruct.cpp:615-621); max_batch = scans per call the host-buffer entry points stage. */
+ * Duke/reconstruct.cpp:615-621); max_batch = scans per call the host-buffer entry points stage.
+ * Any width is accepted, as in the reference: the match kernels move rows in 16-byte multiples (TMA), so widths that
+ * are not a multiple of 16 run the same kernels over zero-padded device copies (one extra pass over the data);
+ * multiples of 16 with 16-byte aligned device pointers take the fused single-kernel paths. */
 SLR_API slr_status slr_create(slr_engine **out, int device, int width, int height, int max_batch);
 SLR_API slr_status slr_destroy(slr_engine *e);
 /* Run on a caller-owned cudaStream_t (e.g. torch's current stream).  As in the CUDA API, NULL is the
