@@ -381,4 +381,20 @@ int ref_export_mesh(const float *points, const uint8_t *count, const uint8_t *co
     return 0;
 }
 
+// PointCloudImage::exportXYZ (pointcloudimage.cpp:99-122) on a cloud given as sums + counts (+ colour u8)
+int ref_export_xyz(const float *points, const uint8_t *count, const uint8_t *color, int w, int h, int export_off, int color_flag,
+                   const char *path)
+{
+    PointCloudImage pc(w, h, color != nullptr);
+    for (int r = 0; r < h; r++)
+        for (int c = 0; c < w; c++) {
+            const size_t q = (size_t)r * w + c;
+            pc.numOfPointsForPixel.at<uchar>(r, c) = count[q];
+            pc.points.at<cv::Vec3f>(r, c) = cv::Vec3f(points[q * 3], points[q * 3 + 1], points[q * 3 + 2]);
+            if (color) pc.color.at<cv::Vec3b>(r, c) = cv::Vec3b(color[q * 3], color[q * 3 + 1], color[q * 3 + 2]);
+        }
+    pc.exportXYZ((char *)path, export_off != 0, color_flag != 0);
+    return 0;
+}
+
 }  // extern "C"

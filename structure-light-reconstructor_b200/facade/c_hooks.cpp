@@ -132,4 +132,24 @@ int duke_write_mesh_text(const float *sums, const uint8_t *counts, const int *co
         }
     return duke::write_mesh_text(path, obj != 0, &pc, vert, src, faces, (size_t)nv, (size_t)nf) ? 0 : -1;
 }
+
+// PointCloudImage::exportXYZ of a cloud given as sums + counts (+ colour values), host only
+int duke_export_xyz(const float *sums, const uint8_t *counts, const int *color, int w, int h, int export_off, int color_flag,
+                    const char *path)
+{
+    PointCloudImage pc(w, h, color != nullptr);
+    for (int j = 0; j < h; j++)
+        for (int i = 0; i < w; i++) {
+            const size_t q = (size_t)j * w + i;
+            for (int k = 0; k < counts[q]; k++) {
+                const duke::Point3f p(k == 0 ? sums[q * 3] : -0.f, k == 0 ? sums[q * 3 + 1] : -0.f, k == 0 ? sums[q * 3 + 2] : -0.f);
+                if (color)
+                    pc.addPoint(i, j, p, k == 0 ? duke::Vec3i(color[q * 3], color[q * 3 + 1], color[q * 3 + 2]) : duke::Vec3i(0, 0, 0));
+                else
+                    pc.addPoint(i, j, p);
+            }
+        }
+    pc.exportXYZ(path, export_off != 0, color_flag != 0);
+    return 0;
+}
 }  // extern "C"

@@ -95,6 +95,10 @@ def main():
             with tempfile.NamedTemporaryFile(suffix=".txt") as f:
                 r.export_mesh(pts, cnt, w, h, f.name, obj, col)
                 mesh[f"{tag}_{'obj' if obj else 'ply'}"] = np.frombuffer(open(f.name, "rb").read(), np.uint8)
+        for off in (True, False):
+            with tempfile.NamedTemporaryFile(suffix=".txt") as f:
+                r.export_xyz(pts, cnt, w, h, f.name, off, True, col)
+                mesh[f"{tag}_xyz_{'off' if off else 'on'}"] = np.frombuffer(open(f.name, "rb").read(), np.uint8)
     out["mesh"] = mesh
 
     for name, arrs in out.items():

@@ -167,6 +167,16 @@ class Ref:
         self.lib.ref_export_mesh(C.c_void_p(points.ctypes.data), C.c_void_p(count.ctypes.data), cptr, int(w), int(h),
                                  int(obj), str(path).encode())
 
+    def export_xyz(self, points, count, w, h, path, export_off=True, color_flag=True, color=None):
+        points = np.ascontiguousarray(points, np.float32)
+        count = np.ascontiguousarray(count, np.uint8)
+        cptr = None
+        if color is not None:
+            color = np.ascontiguousarray(color, np.uint8)
+            cptr = C.c_void_p(color.ctypes.data)
+        self.lib.ref_export_xyz(C.c_void_p(points.ctypes.data), C.c_void_p(count.ctypes.data), cptr, int(w), int(h),
+                                int(export_off), int(color_flag), str(path).encode())
+
 
 _ref = None
 

@@ -207,3 +207,27 @@ def test_mesh_text_stage_writes_the_reference_bytes(duke, tmp_path, color, obj):
     assert rc == 0 and len(vert) >= 4096
     orc.export_mesh(pts, cnt, w, h, tmp_path / "o.txt", obj, ci)
     assert open(tmp_path / "b.txt", "rb").read() == open(tmp_path / "o.txt", "rb").read()
+
+
+@pytest.mark.parametrize("color", [True, False])
+@pytest.mark.parametrize("export_off", [True, False])
+def test_pointcloudimage_export_xyz_writes_the_reference_bytes(duke, tmp_path, color, export_off):
+    """PointCloudImage::exportXYZ (Duke/pointcloudimage.cpp:99-122): the facade's accumulator writes the bytes the
+    reference's own class writes (fixture made by oracle/_ref; re-derived live where /root/reference is mounted)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    import ref_lib
+    golden = dict(np.load(os.path.join(ROOT, "tests", "golden", "ref_mesh.npz")))
+    pts, cnt, col = cases.mesh_cloud(color=color)
+    h, w = cnt.shape
+    ci = None if col is None else np.ascontiguousarray(col, np.int32)
+    path = tmp_path / "c.xyz"
+    rc = duke.duke_export_xyz(ptr(pts), ptr(cnt), ptr(ci) if ci is not None else None, w, h, int(export_off), 1, str(path).encode())
+    assert rc == 0
+    want = golden[f"{'c' if color else 'n'}_xyz_{'off' if export_off else 'on'}"].tobytes()
+    assert open(path, "rb").read() == want
+    if ref_lib.available():
+        ref_lib.load().export_xyz(pts, cnt, w, h, tmp_path / "r.xyz", export_off, True, col)
+        assert open(tmp_path / "r.xyz", "rb").read() == want
