@@ -59,7 +59,7 @@ EXPORTS = [
     "slr_version", "slr_gray_num_bits", "slr_gray_num_imgs", "slr_generate_gray_patterns",
     "slr_generate_mf_patterns", "slr_mf_decode", "slr_gray_decode", "slr_match_triangulate_phase",
     "slr_match_triangulate_code", "slr_bucket_triangulate", "slr_run_mf", "slr_run_ge", "slr_run_mf_host",
-    "slr_run_ge_host", "slr_host_alloc", "slr_host_free", "slr_synth_mf", "slr_synth_gray",
+    "slr_run_ge_host", "slr_host_alloc", "slr_host_free", "slr_synth_mf", "slr_synth_mf_fs", "slr_synth_gray",
     "slr_kernel_launches", "slr_mesh_index", "slr_mesh_index_host", "slr_allgather", "slr_nccl_unique_id",
     "slr_nccl_comm_create", "slr_nccl_comm_destroy", "slr_set_rectify_maps", "slr_rectify_stack", "slr_set_host_input_raw", "slr_run_gray_host",
 ]
@@ -99,6 +99,7 @@ def capi():
     lib.slr_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     lib.slr_host_free.argtypes = [vp]
     lib.slr_synth_mf.argtypes = [vp, vp, i32, i32, u32, i32, C.c_float]
+    lib.slr_synth_mf_fs.argtypes = [vp, vp, i32, i32, i32, i32, u32, i32, C.c_float]
     lib.slr_synth_gray.argtypes = [vp, vp, i32, i32, u32, i32, C.c_float]
     lib.slr_set_rectify_maps.argtypes = [vp, vp, vp]
     lib.slr_rectify_stack.argtypes = [vp, vp, i32, i32, vp]
@@ -381,12 +382,12 @@ class Engine:
         nv, nf = (int(v) for v in cnts.tolist())
         return vert[:nv], src[:nv], faces[:nf]
 
-    def synth_mf(self, batch, proj_w=None, seed=0, integer_disparity=True, noise_dn=0.0):
+    def synth_mf(self, batch, proj_w=None, seed=0, integer_disparity=True, noise_dn=0.0, F=3, S=4):
         t = self._torch
-        stack = self._empty((batch, 2, 14, self.H, self.W), t.uint8)
+        stack = self._empty((batch, 2, 2 + F * S, self.H, self.W), t.uint8)
         self._bind_stream()
-        _check(self.lib.slr_synth_mf(self.h, self._p(stack), batch, proj_w or self.W, seed, int(integer_disparity),
-                                     float(noise_dn)), "slr_synth_mf")
+        _check(self.lib.slr_synth_mf_fs(self.h, self._p(stack), batch, F, S, proj_w or self.W, seed,
+                                        int(integer_disparity), float(noise_dn)), "slr_synth_mf_fs")
         return stack
 
     def synth_gray(self, batch, scan_w=None, seed=0, integer_disparity=True, noise_dn=0.0):

@@ -122,7 +122,7 @@ __device__ __forceinline__ uint8_t add_noise(float v, float noise_dn, uint32_t k
 }
 
 // one thread per (row, col) of one view; writes all N planes
-__global__ void k_synth_mf(uint8_t *__restrict__ stack, int W, int H, int batch, int proj_w, unsigned seed,
+__global__ void k_synth_mf(uint8_t *__restrict__ stack, int W, int H, int batch, int F, int S, int proj_w, unsigned seed,
                            int integer_disp, float noise_dn)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,19 +134,22 @@ __global__ void k_synth_mf(uint8_t *__restrict__ stack, int W, int H, int batch,
     float u;
     const bool lit = scene_coord(s, cam, x, i, proj_w, integer_disp, u);
     const size_t P = (size_t)W * H;
-    uint8_t *base = stack + (size_t)view * 14 * P + (size_t)i * W + x;
-    const uint32_t key0 = hash_u32(seed ^ (uint32_t)(view * 0x01000193u)) + (uint32_t)(i * W + x) * 16u;
+    uint8_t *base = stack + (size_t)view * (2 + F * S) * P + (size_t)i * W + x;
+    // 16 noise keys per pixel for the reference's 14-image stack (unchanged streams), 2 + F*S rounded up otherwise
+    const uint32_t keys_per_px = (F * S <= 14) ? 16u : (uint32_t)((2 + F * S + 15) & ~15);
+    const uint32_t key0 = hash_u32(seed ^ (uint32_t)(view * 0x01000193u)) + (uint32_t)(i * W + x) * keys_per_px;
     base[0] = add_noise(lit ? 200.0f : 30.0f, noise_dn, key0);
     base[P] = add_noise(20.0f, noise_dn, key0 + 1);
-    const int freq[3] = {70, 64, 59};  // Duke/multifrequency.cpp:3
-    for (int f = 0; f < 3; f++)
-        for (int sft = 0; sft < 4; sft++) {
-            // same form as the reference's generator (Duke/multifrequency.cpp:27) at a fractional column u
-            const double arg = 3.1416 * 2 * (double)u * (double)freq[f] / (double)proj_w + 3.1416 * (double)sft / 2;
+    const int freq[8] = {70, 64, 59, 55, 52, 50, 47, 45};  // first three: Duke/multifrequency.cpp:3
+    for (int f = 0; f < F; f++)
+        for (int sft = 0; sft < S; sft++) {
+            // same form as the reference's generator (Duke/multifrequency.cpp:27) at a fractional column u; the shift
+            // PI*2*s/S equals the reference's PI*s/2 for S = 4 bit for bit
+            const double arg = 3.1416 * 2 * (double)u * (double)freq[f] / (double)proj_w + 3.1416 * 2 * (double)sft / S;
             float v = 135.0f + 79.0f * cosf((float)arg);
             v = truncf(v);
             if (!lit) v = 20.0f;
-            base[(size_t)(2 + 4 * f + sft) * P] = add_noise(v, noise_dn, key0 + 2 + 4 * f + sft);
+            base[(size_t)(2 + S * f + sft) * P] = add_noise(v, noise_dn, key0 + 2 + S * f + sft);
         }
 }
 
@@ -188,11 +191,11 @@ slr_status slr_launch_undistort_maps(slr_engine *e)
     return SLR_OK;
 }
 
-slr_status slr_launch_synth_mf(slr_engine *e, uint8_t *d_stack, int batch, int proj_w, unsigned seed,
+slr_status slr_launch_synth_mf(slr_engine *e, uint8_t *d_stack, int batch, int F, int S, int proj_w, unsigned seed,
                                int integer_disparity, float noise_dn)
 {
     dim3 block(128), grid((e->W + 127) / 128, e->H, batch * 2);
-    k_synth_mf<<<grid, block, 0, e->stream>>>(d_stack, e->W, e->H, batch, proj_w, seed, integer_disparity, noise_dn);
+    k_synth_mf<<<grid, block, 0, e->stream>>>(d_stack, e->W, e->H, batch, F, S, proj_w, seed, integer_disparity, noise_dn);
     SLR_CHECK_LAUNCH(e);
     return SLR_OK;
 }

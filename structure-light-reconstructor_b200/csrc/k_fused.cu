@@ -438,7 +438,8 @@ slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch,
     else
         SLR_REQUIRE(mode == SLR_MODE_CORRECTED && F >= 1 && F <= 8 && S >= 3 && S <= 16,
                     "corrected mode supports 1<=F<=8, 3<=S<=16; got mode %d F=%d S=%d", mode, F, S);
-    if (e->W % 16 != 0)   // TMA rows need 16-byte multiples: zero-padded copies on a child engine (slr_engine.cu)
+    // TMA rows need 16-byte multiples and aligned bases: zero-padded / aligned copies on a child engine (slr_engine.cu)
+    if (e->W % 16 != 0 || slr_misaligned16(d_stack, d_xyz, d_valid, d_match_k))
         return slr_padded_run(e, 0, d_stack, nullptr, batch, 2 + F * S, F, S, black_thr, mode, 0, d_xyz, d_valid, d_match_k,
                               nullptr, d_n_points);
     bool handled = false;
@@ -462,7 +463,7 @@ slr_status slr_launch_fused_ge(slr_engine *e, const uint8_t *d_stack, int batch,
                                int white_thr, int scan_w, int have_color, float *d_xyz, uint8_t *d_valid,
                                int32_t *d_match_k, uint8_t *d_color, unsigned long long *d_n_points)
 {
-    if (e->W % 16 != 0)
+    if (e->W % 16 != 0 || slr_misaligned16(d_stack, d_xyz, d_valid, d_match_k, have_color ? d_color : nullptr))
         return slr_padded_run(e, 1, d_stack, nullptr, batch, 2 + 2 * nbits_col, nbits_col, black_thr, white_thr, scan_w,
                               have_color, d_xyz, d_valid, d_match_k, have_color ? d_color : nullptr, d_n_points);
     return slr_unfused_ge(e, d_stack, batch, nbits_col, black_thr, white_thr, scan_w, have_color, d_xyz, d_valid,

@@ -315,7 +315,8 @@ extern "C" slr_status slr_match_triangulate_phase(slr_engine *e, const float *d_
         slr_set_error("slr_match_triangulate_phase: call slr_set_calib first");
         return SLR_ERR_STATE;
     }
-    if (e->W % 16 != 0)
+    // TMA rows need 16-byte multiples and 16-byte aligned bases: anything else is staged through aligned copies
+    if (e->W % 16 != 0 || slr_misaligned16(d_phase, d_mask, d_xyz, d_valid, d_match_k))
         return slr_padded_run(e, 2, d_phase, d_mask, batch, 1, 0, 0, 0, 0, 0, d_xyz, d_valid, d_match_k, nullptr, d_n_points);
     return slr_launch_match_phase(e, d_phase, d_mask, batch, d_xyz, d_valid, d_match_k, d_n_points);
 }
@@ -332,9 +333,10 @@ extern "C" slr_status slr_match_triangulate_code(slr_engine *e, const int32_t *d
         slr_set_error("slr_match_triangulate_code: call slr_set_calib first");
         return SLR_ERR_STATE;
     }
-    if (e->W % 16 != 0) {
+    if (e->W % 16 != 0 || slr_misaligned16(d_col, d_mask, d_xyz, d_valid, d_match_k, d_white, d_color)) {
         SLR_REQUIRE(d_color == nullptr, "slr_match_triangulate_code: colour output needs an image width that is a multiple "
-                                        "of 16 (use slr_run_ge, which pads the whole stack); got %d", e->W);
+                                        "of 16 and 16-byte aligned pointers (use slr_run_ge, which stages the whole stack); "
+                                        "got width %d", e->W);
         return slr_padded_run(e, 3, d_col, d_mask, batch, 1, 0, 0, 0, 0, 0, d_xyz, d_valid, d_match_k, nullptr, d_n_points);
     }
     return slr_launch_match_code(e, d_col, d_mask, batch, d_white, (size_t)e->W * e->H, d_xyz, d_valid, d_match_k,
@@ -551,7 +553,16 @@ extern "C" slr_status slr_synth_mf(slr_engine *e, uint8_t *d_stack, int batch, i
 {
     SLR_ENTER(e);
     SLR_REQUIRE(d_stack && batch > 0 && batch <= 32767 && proj_w > 0, "slr_synth_mf: bad argument");
-    return slr_launch_synth_mf(e, d_stack, batch, proj_w, seed, integer_disparity, noise_dn);
+    return slr_launch_synth_mf(e, d_stack, batch, 3, 4, proj_w, seed, integer_disparity, noise_dn);
+}
+
+extern "C" slr_status slr_synth_mf_fs(slr_engine *e, uint8_t *d_stack, int batch, int F, int S, int proj_w,
+                                      unsigned seed, int integer_disparity, float noise_dn)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(d_stack && batch > 0 && batch <= 32767 && proj_w > 0 && F >= 1 && F <= 8 && S >= 3 && S <= 16,
+                "slr_synth_mf_fs: bad argument");
+    return slr_launch_synth_mf(e, d_stack, batch, F, S, proj_w, seed, integer_disparity, noise_dn);
 }
 
 extern "C" slr_status slr_synth_gray(slr_engine *e, uint8_t *d_stack, int batch, int scan_w, unsigned seed,

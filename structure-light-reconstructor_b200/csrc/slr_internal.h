@@ -112,6 +112,13 @@ void slr_set_error(const char *fmt, ...);
         SLR_CHECK_CUDA(cudaGetLastError());                  \
     } while (0)
 
+// true when any of the (possibly NULL) pointers is not 16-byte aligned: such calls are staged through aligned copies
+template <typename... P>
+static inline bool slr_misaligned16(const P *...ptrs)
+{
+    return ((... | (uintptr_t)ptrs) & 15u) != 0;
+}
+
 // kernel launchers (defined in the k*.cu files)
 slr_status slr_launch_mf_decode(slr_engine *e, const uint8_t *d_stack, int views, int F, int S,
                                 int black_thr, int mode, float *d_phase, uint8_t *d_mask);
@@ -147,7 +154,7 @@ slr_status slr_launch_mesh_index(slr_engine *e, const float *d_sum, const uint8_
                                  int first_vertex, int *d_pn, int *d_tiles, float *d_vertices, int32_t *d_vertex_src,
                                  int32_t *d_faces, unsigned long long *d_counts);
 int slr_mesh_tiles(int w, int h);
-slr_status slr_launch_synth_mf(slr_engine *e, uint8_t *d_stack, int batch, int proj_w, unsigned seed,
+slr_status slr_launch_synth_mf(slr_engine *e, uint8_t *d_stack, int batch, int F, int S, int proj_w, unsigned seed,
                                int integer_disparity, float noise_dn);
 slr_status slr_launch_synth_gray(slr_engine *e, uint8_t *d_stack, int batch, int scan_w, unsigned seed,
                                  int integer_disparity, float noise_dn);

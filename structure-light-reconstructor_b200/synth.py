@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import numpy as np
 
-FREQ = (70, 64, 59)        # Duke/multifrequency.cpp:3
+FREQ = (70, 64, 59, 55, 52, 50, 47, 45)   # first three: Duke/multifrequency.cpp:3; the rest extend the series
 PI_GEN = 3.1416            # Duke/multifrequency.h:5
 
 
@@ -39,19 +39,19 @@ def _finish(img, noise_dn, rng):
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
-def synth_mf(W, H, proj_w=None, seed=0, integer_disparity=True, noise_dn=0.0):
-    """uint8 [2, 14, H, W] multi-frequency stack (layout of Duke/multifrequency.cpp:16-17,30)."""
+def synth_mf(W, H, proj_w=None, seed=0, integer_disparity=True, noise_dn=0.0, F=3, S=4):
+    """uint8 [2, 2+F*S, H, W] multi-frequency stack (layout of Duke/multifrequency.cpp:16-17,30 for F=3, S=4)."""
     proj_w = proj_w or W
     u, lit = scene_coords(W, H, proj_w, seed, integer_disparity)
     rng = np.random.default_rng(seed + 1000)
-    out = np.empty((2, 14, H, W), np.uint8)
+    out = np.empty((2, 2 + F * S, H, W), np.uint8)
     out[:, 0] = _finish(np.where(lit, 200.0, 30.0), noise_dn, rng)
     out[:, 1] = _finish(np.full(lit.shape, 20.0), noise_dn, rng)
-    for f in range(3):
-        for s in range(4):
-            arg = (PI_GEN * 2 * u * FREQ[f] / proj_w + PI_GEN * s / 2).astype(np.float32)
+    for f in range(F):
+        for s in range(S):
+            arg = (PI_GEN * 2 * u * FREQ[f] / proj_w + PI_GEN * 2 * s / S).astype(np.float32)
             v = np.trunc(np.float32(135.0) + np.float32(79.0) * np.cos(arg))
-            out[:, 2 + 4 * f + s] = _finish(np.where(lit, v, 20.0), noise_dn, rng)
+            out[:, 2 + S * f + s] = _finish(np.where(lit, v, 20.0), noise_dn, rng)
     return out
 
 

@@ -1,0 +1,214 @@
+"""GPU parity tests (-m gpu) for the launch routes that round 1 only compared with themselves: every test here
+compares the CUDA path (through the C ABI) with the CPU ORACLE, never with another CUDA kernel.
+
+  * BASELINE config 4's route: 2048-wide rows (one wide CTA per SM in the fused kernel), strict mode;
+  * BASELINE config 5's route: 4096-wide rows, 4 frequencies x 8 shifts, corrected mode (K1 4x8 + wide-row match);
+  * a full 1280x1024 frame with sub-pixel disparity and sensor noise (the dedupe tables see ~2x the distinct
+    phase values of the noise-free case);
+  * Gray-only bucket triangulation at 640x480 (BASELINE config 1's resolution);
+  * device pointers that are not 16-byte aligned (staged through aligned copies by the library).
+"""
+import numpy as np
+import pytest
+
+import slr_b200
+from slr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4          # BASELINE.json north_star: "within 1e-4 relative on unwrapped phase and XYZ"
+
+
+def _t(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _assert_cloud_equal(xyz, valid, k, n, xyz_o, valid_o, k_o, n_o, what):
+    k, valid, xyz = k.cpu().numpy(), valid.cpu().numpy(), xyz.cpu().numpy()
+    assert (k == k_o).all(), f"{what}: {(k != k_o).sum()} match columns differ"
+    assert (valid == valid_o).all(), f"{what}: valid flags differ"
+    assert (np.isnan(xyz) == np.isnan(xyz_o)).all(), f"{what}: NaN pattern differs"
+    ok = ~np.isnan(xyz_o)
+    assert np.allclose(xyz[ok], xyz_o[ok], rtol=RTOL, atol=1e-6), f"{what}: XYZ outside 1e-4 relative"
+    assert (bits(xyz) == bits(xyz_o)).all(), f"{what}: XYZ not bit-exact"
+    assert n == n_o, f"{what}: point count {n} != {n_o}"
+
+
+# ------------------------------------------------------------------------------------------------
+# config 4's route: W = 2048 (Duke/mfreconstruct.cpp:160-334 at a width the reference's GUI cannot select)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("intd,noise,rigid", [(True, 0.0, False), (False, 2.0, True)])
+def test_run_mf_2048_wide_strict_vs_oracle(cuda_engine_factory, oracle, intd, noise, rigid):
+    W, H, B = 2048, 48, 2
+    eng = cuda_engine_factory(W, H, B)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    M = np.array([[0.98, -0.17, 0.05, 12.5], [0.17, 0.98, 0.02, -3.25], [-0.05, -0.01, 0.99, 40.0]], np.float32) \
+        if rigid else None
+    eng.set_calib(cams, Q, M)
+    stack = np.stack([synth.synth_mf(W, H, seed=s, integer_disparity=intd, noise_dn=noise) for s in (21, 22)])
+    xyz, valid, k, n = eng.run_mf(_t(stack), black_thr=40)
+    tot = 0
+    for b in range(B):
+        xyz_o, valid_o, k_o, n_o = oracle.run_mf(stack[b], cams, Q, rigid=M, nthreads=oracle.max_threads())
+        _assert_cloud_equal(xyz[b], valid[b], k[b], n_o, xyz_o, valid_o, k_o, n_o, f"2048-wide scan {b}")
+        tot += n_o
+    assert int(n.item()) == tot and tot > 0.3 * B * W * H
+
+
+def test_match_phase_2048_wide_vs_oracle(cuda_engine_factory, oracle):
+    """slr_match_triangulate_phase on 2048-wide rows: oracle-decoded phases in, oracle match out."""
+    W, H = 2048, 24
+    eng = cuda_engine_factory(W, H, 1)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    stack = synth.synth_mf(W, H, seed=31, integer_disparity=False, noise_dn=1.0)
+    ph = np.empty((1, 2, H, W), np.float32)
+    mk = np.empty((1, 2, H, W), np.uint8)
+    for cam in range(2):
+        ph[0, cam], mk[0, cam] = oracle.mf_decode(stack[cam], black_thr=40)
+    xyz, valid, k, n = eng.match_triangulate_phase(_t(ph), _t(mk))
+    xyz_o, valid_o, k_o, n_o = oracle.mf_triangulate(ph[0, 0], mk[0, 0], ph[0, 1], mk[0, 1], cams, Q,
+                                                     nthreads=oracle.max_threads())
+    _assert_cloud_equal(xyz[0], valid[0], k[0], int(n.item()), xyz_o, valid_o, k_o, n_o, "2048-wide phase match")
+    assert n_o > 0.3 * W * H
+
+
+# ------------------------------------------------------------------------------------------------
+# config 5's route: 4096 wide, F = 4, S = 8, corrected mode.  Corrected mode has no reference counterpart
+# (SURVEY.md §0 F8): every comparison below is ORACLE-ONLY.
+# ------------------------------------------------------------------------------------------------
+def test_run_mf_config5_route_vs_oracle(cuda_engine_factory, oracle):
+    W, H, F, S = 4096, 16, 4, 8
+    eng = cuda_engine_factory(W, H, 1)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    stack = synth.synth_mf(W, H, seed=51, integer_disparity=False, noise_dn=1.0, F=F, S=S)[None]
+    st = _t(stack)
+    # (1) decode: within the north star's 1e-4 (phase is circular with period 255)
+    ph, mk = eng.mf_decode(st, F=F, S=S, black_thr=40, mode=slr_b200.MODE_CORRECTED)
+    ph, mk = ph.cpu().numpy(), mk.cpu().numpy()
+    for cam in range(2):
+        ph_o, mk_o = oracle.mf_decode(stack[0, cam], F=F, S=S, black_thr=40, mode=1, nthreads=oracle.max_threads())
+        assert (mk[0, cam] == mk_o).all()
+        ok = mk_o == 1
+        d = np.abs(ph[0, cam][ok] - ph_o[ok])
+        d = np.minimum(d, 255.0 - d)
+        assert (d <= RTOL * 255.0).all(), d.max()
+    # (2) match + triangulate of the whole pipeline == the oracle's match on the very phases the GPU decoded: exact
+    xyz, valid, k, n = eng.run_mf(st, F=F, S=S, black_thr=40, mode=slr_b200.MODE_CORRECTED)
+    xyz_o, valid_o, k_o, n_o = oracle.mf_triangulate(ph[0, 0], mk[0, 0], ph[0, 1], mk[0, 1], cams, Q,
+                                                     nthreads=oracle.max_threads())
+    _assert_cloud_equal(xyz[0], valid[0], k[0], int(n.item()), xyz_o, valid_o, k_o, n_o, "config-5 route, GPU phases")
+    assert n_o > 0.3 * W * H
+    # (3) end to end against oracle.run_mf(mode=1): a phase difference of 1e-5 can move a |pL - pR| < 0.1 decision,
+    # so match columns agree for all but a sliver of borderline pixels; where they agree XYZ is within 1e-4
+    xyz_e, valid_e, k_e, n_e = oracle.run_mf(stack[0], cams, Q, F=F, S=S, black_thr=40, mode=1,
+                                             nthreads=oracle.max_threads())
+    kg = k[0].cpu().numpy()
+    same = kg == k_e
+    assert same.mean() > 0.995, same.mean()
+    sel = same & (k_e >= 0)
+    g = xyz[0].cpu().numpy()[sel]
+    assert np.allclose(g, xyz_e[sel], rtol=RTOL, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# full frame, sub-pixel disparity + noise (sigma in {0, 2} DN)
+# ------------------------------------------------------------------------------------------------
+def test_run_mf_full_frame_noisy_vs_oracle(cuda_engine_factory, oracle):
+    W, H = 1280, 1024
+    eng = cuda_engine_factory(W, H, 1)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    stack = eng.synth_mf(1, seed=43, integer_disparity=False, noise_dn=2.0)
+    xyz, valid, k, n = eng.run_mf(stack, black_thr=40)
+    hs = stack.cpu().numpy()
+    xyz_o, valid_o, k_o, n_o = oracle.run_mf(hs[0], cams, Q, nthreads=oracle.max_threads())
+    _assert_cloud_equal(xyz[0], valid[0], k[0], int(n.item()), xyz_o, valid_o, k_o, n_o, "noisy full frame")
+    assert n_o > 0.2 * W * H
+    # size-independent property: a second run reproduces the first bit for bit
+    xyz2, valid2, k2, n2 = eng.run_mf(stack, black_thr=40)
+    assert (bits(xyz2.cpu().numpy()) == bits(xyz.cpu().numpy())).all() and int(n2.item()) == int(valid2.sum().item())
+
+
+# ------------------------------------------------------------------------------------------------
+# Gray-only buckets at 640x480 (Duke/reconstruct.cpp:56-74, 417-481)
+# ------------------------------------------------------------------------------------------------
+def test_k3c_bucket_triangulate_640x480_vs_oracle(cuda_engine_factory, oracle):
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import cases
+    W, H = 640, 480
+    eng = cuda_engine_factory(W, H, 1)
+    cams = cases.gray_only_rig(W, H)
+    _, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q, cases.RIGID)
+    stack = synth.synth_gray(W, H, seed=61, noise_dn=2.0, rows=True, integer_disparity=True)[None]
+    nc, nr = oracle.gray_num_bits(W), oracle.gray_num_bits(H)
+    col, row, mk = eng.gray_decode(_t(stack), nc, nr, black_thr=40, white_thr=3, scan_w=W, scan_h=H)
+    ssum, cnt, n = eng.bucket_triangulate(col, row, mk, W, H)
+    d = [oracle.gray_decode(stack[0, cam], nc, nr, 40, 3, W, H) for cam in range(2)]
+    for cam in range(2):
+        assert (col[0, cam].cpu().numpy() == d[cam][0]).all() and (row[0, cam].cpu().numpy() == d[cam][1]).all()
+        assert (mk[0, cam].cpu().numpy() == d[cam][2]).all()
+    s_o, c_o, n_o = oracle.gray_triangulate(d[0][0], d[0][1], d[0][2], d[1][0], d[1][1], d[1][2], W, H, cams, cases.RIGID)
+    assert (cnt[0].cpu().numpy() == c_o).all()
+    g = ssum[0].cpu().numpy()
+    assert (bits(g[c_o > 0]) == bits(s_o[c_o > 0])).all()
+    assert int(n.item()) == n_o and n_o > 1000
+
+
+# ------------------------------------------------------------------------------------------------
+# device pointers off the 16-byte grid (the fast paths need aligned bases; others are staged)
+# ------------------------------------------------------------------------------------------------
+def _offset_like(t, off_bytes):
+    """A tensor with t's contents whose data pointer is t-aligned + off_bytes (off_bytes a multiple of the item size)."""
+    import torch
+    raw = torch.empty(t.numel() * t.element_size() + 64, dtype=torch.uint8, device=t.device)
+    base = (-raw.data_ptr()) % 16 + off_bytes
+    view = raw[base:base + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+    view.copy_(t)
+    assert view.data_ptr() % 16 == off_bytes % 16
+    return view
+
+
+def test_unaligned_device_pointers_match_the_oracle(cuda_engine_factory, oracle):
+    import torch
+    W, H = 320, 12
+    eng = cuda_engine_factory(W, H, 1)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    stack = synth.synth_mf(W, H, seed=71, noise_dn=1.0)[None]
+    xyz_o, valid_o, k_o, n_o = oracle.run_mf(stack[0], cams, Q)
+    # MF pipeline: input stack 4 bytes off, outputs 4 / 1 / 4 bytes off
+    st = _offset_like(_t(stack), 4)
+    out = (_offset_like(torch.zeros((1, H, W, 3), dtype=torch.float32, device="cuda"), 4),
+           _offset_like(torch.zeros((1, H, W), dtype=torch.uint8, device="cuda"), 1),
+           _offset_like(torch.zeros((1, H, W), dtype=torch.int32, device="cuda"), 4), None,
+           torch.zeros(1, dtype=torch.int64, device="cuda"))
+    xyz, valid, k, n = eng.run_mf(st, black_thr=40, out=out)
+    _assert_cloud_equal(xyz[0], valid[0], k[0], int(n.item()), xyz_o, valid_o, k_o, n_o, "unaligned run_mf")
+    # phase-match entry point with unaligned phase rows
+    ph = np.empty((1, 2, H, W), np.float32)
+    mk = np.empty((1, 2, H, W), np.uint8)
+    for cam in range(2):
+        ph[0, cam], mk[0, cam] = oracle.mf_decode(stack[0, cam], black_thr=40)
+    xyz, valid, k, n = eng.match_triangulate_phase(_offset_like(_t(ph), 8), _offset_like(_t(mk), 3))
+    _assert_cloud_equal(xyz[0], valid[0], k[0], int(n.item()), xyz_o, valid_o, k_o, n_o, "unaligned phase match")
+    # Gray-EPI pipeline
+    nc = oracle.gray_num_bits(W)
+    g = synth.synth_gray(W, H, seed=72, integer_disparity=False, noise_dn=2.0)[None]
+    xyz, valid, k, colr, n = eng.run_ge(_offset_like(_t(g), 2), nc, black_thr=40, white_thr=3, have_color=False)
+    cols, mks = zip(*[(lambda r: (r[0], r[2]))(oracle.gray_decode(g[0, cam], nc, 0, 40, 3, W, H)) for cam in range(2)])
+    xyz_g, valid_g, k_g, _, n_g = oracle.ge_triangulate(cols[0], mks[0], cols[1], mks[1], Q)
+    _assert_cloud_equal(xyz[0], valid[0], k[0], int(n.item()), xyz_g, valid_g, k_g, n_g, "unaligned run_ge")
+    col = np.stack(cols)[None]
+    gm = np.stack(mks)[None]
+    xyz, valid, k, _, n = eng.match_triangulate_code(_offset_like(_t(col), 4), _offset_like(_t(gm), 5))
+    _assert_cloud_equal(xyz[0], valid[0], k[0], int(n.item()), xyz_g, valid_g, k_g, n_g, "unaligned code match")
