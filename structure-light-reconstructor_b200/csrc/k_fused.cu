@@ -37,6 +37,9 @@ slr_status slr_unfused_ge(slr_engine *e, const uint8_t *d_stack, int batch, int 
                           int white_thr, int scan_w, int have_color, float *d_xyz, uint8_t *d_valid,
                           int32_t *d_match_k, uint8_t *d_color, unsigned long long *d_n_points);
 
+// k_fused_flow.cu: the barrier-free dataflow schedule of the same pipeline (preferred when its row contexts fit)
+slr_status slr_launch_fused_flow(slr_engine *e, int mode, const slr_fused::FusedParams &p, bool *handled);
+
 namespace {
 
 using namespace slr_fused;
@@ -66,6 +69,7 @@ k_fused_mf(const FusedParams p)
     RowTables tab;
     tab.T = T;
     tab.logT = p.logT;
+    tab.HB = 2 * T;
     tab.ent = reinterpret_cast<uint2 *>(stage + stage_bytes);
     tab.head = reinterpret_cast<int *>(tab.ent + T);
     tab.nxt = tab.head + 2 * T;
@@ -369,6 +373,13 @@ static slr_status launch_fused(slr_engine *e, int mode, const uint8_t *d_stack, 
     p.match_k = d_match_k;
     p.n_points = d_n_points;
     p.calib = e->calib;
+#if !defined(SLR_ABLATION) && !defined(SLR_PHASE_CLOCKS)
+    {
+        bool flow = false;
+        const slr_status st = slr_launch_fused_flow(e, mode, p, &flow);
+        if (st != SLR_OK || flow) return st;
+    }
+#endif
 
     void (*kern)(const FusedParams);
 #define SLR_PICK_Q(MAXT, MINB, Q)                                                                                 \

@@ -208,22 +208,24 @@ __device__ __forceinline__ void load_phases(const unsigned char *stage, int W, i
     }
 }
 
-// Shared-memory tables of one row.
-struct RowTables {
+// Shared-memory tables of one row.  LinkT = int (k_fused_mf) or int16_t (k_fused_flow: three row contexts per SM).
+template <typename LinkT>
+struct RowTablesT {
     uint2 *ent;   // [T]  {x = distinct right phase (float bits), y = smallest right column carrying it}
-    int *head;    // [2T] bucket heads (-1 = empty)
-    int *nxt;     // [2T] node n = entry + T*(0|1)
-    int T, logT;
+    int *head;    // [HB] bucket heads (-1 = empty); a bucket index is taken modulo HB (a power of two)
+    LinkT *nxt;   // [2T] node n = entry + T*(0|1); -1 ends a chain
+    int T, logT, HB;
 };
+using RowTables = RowTablesT<int>;
 
 // value -> min column, deduplicated, for PX right pixels of columns col0 .. col0+PX-1.  The pixels advance in lock
 // step (all first probes, then all claims, then all minima, then all bucket links) so that their shared-memory
 // round trips overlap.  The thread that claims a new value also files it under the bucket(s) its +-0.1 match
 // window touches.
-template <int PX, bool CLAMP>
-__device__ __forceinline__ void insert_right(const RowTables &t, const float (&ph)[PX], const bool (&ok)[PX], int col0)
+template <int PX, bool CLAMP, typename LinkT>
+__device__ __forceinline__ void insert_right(const RowTablesT<LinkT> &t, const float (&ph)[PX], const bool (&ok)[PX], int col0)
 {
-    const int T = t.T, HB = 2 * t.T;
+    const int T = t.T, HB = t.HB;
     uint32_t key[PX], h[PX], cur[PX];
     int mk[PX];
     bool need[PX], claimed[PX];
@@ -276,18 +278,18 @@ __device__ __forceinline__ void insert_right(const RowTables &t, const float (&p
         if (claimed[q]) {
             const float v = __uint_as_float(key[q]);
             const int lo = window_bucket<CLAMP>(__fsub_rn(v, 0.11f)), hi = window_bucket<CLAMP>(__fadd_rn(v, 0.11f));
-            t.nxt[h[q]] = atomicExch(&t.head[lo & (HB - 1)], (int)h[q]);
-            if (hi != lo) t.nxt[h[q] + T] = atomicExch(&t.head[hi & (HB - 1)], (int)h[q] + T);
+            t.nxt[h[q]] = (LinkT)atomicExch(&t.head[lo & (HB - 1)], (int)h[q]);
+            if (hi != lo) t.nxt[h[q] + T] = (LinkT)atomicExch(&t.head[hi & (HB - 1)], (int)h[q] + T);
         }
     }
 }
 
 // smallest right column whose phase matches v (INT_MAX = none): walk the chain of v's bucket
-template <bool CLAMP>
-__device__ __forceinline__ int first_match(const RowTables &t, float v)
+template <bool CLAMP, typename LinkT>
+__device__ __forceinline__ int first_match(const RowTablesT<LinkT> &t, float v)
 {
     int best = INT_MAX;
-    int n = t.head[window_bucket<CLAMP>(v) & (2 * t.T - 1)];
+    int n = t.head[window_bucket<CLAMP>(v) & (t.HB - 1)];
     while (n >= 0) {
         const uint2 e = t.ent[n & (t.T - 1)];
         n = t.nxt[n];

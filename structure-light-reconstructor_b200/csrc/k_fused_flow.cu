@@ -1,0 +1,311 @@
+// k_fused_flow.cu — the fused multi-frequency pipeline as a barrier-free dataflow kernel.
+// Same work and the same device arithmetic as k_fused_mf (k_fused.cu: shadow mask + phase decode + heterodyne +
+// per-row first-k phase match + Q triangulation, Duke/mfreconstruct.cpp:160-334); what changes is the schedule.
+//
+// k_fused_mf runs a row in CTA-wide phases (clear | decode + insert | query + emit) separated by __syncthreads();
+// its profile shows a quarter of the resident warps parked at those barriers and the issue slots 67 % busy.
+// Here one persistent CTA per SM keeps THREE rows in flight and no CTA-wide barrier in steady state:
+//
+//   row r+1   TMA bulk copies of its image rows in flight      (stage buffer (r+1) % 2)
+//   row r     decode jobs: image bytes -> phases, right phases filed in the tables, left phases parked
+//             (context r % 3, stage buffer r % 2)
+//   row r-1   query jobs: first-k match of 32 left pixels + Q reprojection + stores   (context (r-1) % 3)
+//   row r-2   its tables being cleared by the warp that finished its last query job  (context (r-2) % 3)
+//
+// Work is cut into warp-sized jobs; every warp draws the next job from ONE shared counter whose order lists, per
+// step, the decode jobs of row r and then the query jobs of row r-1, so table-lookup-bound, latency-bound and
+// fp64-bound instruction streams share the SM at all times.  A job waits only on per-context completion counters
+// (release/acquire in shared memory) of jobs that precede it in the global order, which makes the schedule
+// deadlock-free: decode(r) needs the clear after query(r-3) and the stage re-armed after decode(r-2); query(r)
+// needs decode(r).  The warp that completes the last decode job of a row re-arms that row's stage buffer with the
+// TMA copies of row r+2.
+#include <limits.h>
+#include <stdlib.h>
+
+#include "k_fused_common.cuh"
+
+namespace {
+
+using namespace slr_fused;
+
+constexpr int FLOW_CTX = 3;        // row contexts (tables + parked left phases)
+constexpr int FLOW_STAGES = 2;     // TMA stage buffers
+constexpr int FLOW_HEADER = 1024;  // mbarriers, counters, job map
+constexpr int FLOW_MAX_JOBS = 448; // jobs per step the header's job map can hold
+
+using FlowTables = RowTablesT<int16_t>;
+
+__device__ __forceinline__ int ld_acquire_s32(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(slr::smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ int add_acq_rel_s32(int *p, int v)
+{
+    int old;
+    asm volatile("atom.acq_rel.cta.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(slr::smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
+// the calling warp continues once *ctr >= target (lane 0 polls; the others are held by the warp barrier)
+__device__ __forceinline__ void wait_count(const int *ctr, int target, int lane)
+{
+    if (lane == 0)
+        while (ld_acquire_s32(ctr) < target) {
+        }
+    __syncwarp();
+}
+
+// shared-memory bytes of one row context: ent[T] (8 B) + head[T] (4 B) + nxt[2T] (2 B) + left phases [W] (4 B)
+__host__ __device__ inline size_t flow_ctx_bytes(int W, int T) { return (size_t)16 * T + (size_t)4 * W; }
+
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1)
+k_fused_flow(const FusedParams p, const int n_d, const int n_q)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr bool CLAMP = MODE == MODE_PHASE_INPUT;
+    const int W = p.W, N = p.N, T = p.T;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+
+    // this CTA's contiguous range of rows rg = i * batch + b (scan index b fastest)
+    const long long rows = (long long)p.batch * p.H;
+    const long long r_begin = rows * blockIdx.x / gridDim.x, r_end = rows * (blockIdx.x + 1) / gridDim.x;
+    const int R = (int)(r_end - r_begin);
+    if (R <= 0) return;
+
+    // ---- shared memory carve-up ----
+    uint64_t *bar_stage = reinterpret_cast<uint64_t *>(smem);              // [FLOW_STAGES]
+    int *job_ctr = reinterpret_cast<int *>(smem + 32);
+    int *done_d = job_ctr + 1;                                             // [FLOW_CTX] decode jobs completed
+    int *done_q = done_d + FLOW_CTX;                                       // [FLOW_CTX] query jobs completed
+    int *cleared = done_q + FLOW_CTX;                                      // [FLOW_CTX] table clears completed
+    uint16_t *jobmap = reinterpret_cast<uint16_t *>(smem + 96);            // [n_d + n_q]: bit 15 = query job
+    const size_t stage_bytes = (MODE == MODE_PHASE_INPUT) ? (size_t)10 * W : (size_t)2 * N * W;
+    unsigned char *stage0 = smem + FLOW_HEADER;
+    unsigned char *ctx0 = stage0 + FLOW_STAGES * stage_bytes;
+    const size_t ctx_bytes = flow_ctx_bytes(W, T);
+    int *s_ptab = reinterpret_cast<int *>(ctx0 + FLOW_CTX * ctx_bytes);       // [SLR_PTAB_SIZE] (strict)
+    uint32_t *s_btab = reinterpret_cast<uint32_t *>(s_ptab + SLR_PTAB_SIZE);  // [SLR_BTAB_SIZE] (strict)
+
+    auto tables_of = [&](int c, float *&s_pl) {
+        FlowTables t;
+        unsigned char *base = ctx0 + (size_t)c * ctx_bytes;
+        t.T = T;
+        t.logT = p.logT;
+        t.HB = T;
+        t.ent = reinterpret_cast<uint2 *>(base);
+        t.head = reinterpret_cast<int *>(t.ent + T);
+        t.nxt = reinterpret_cast<int16_t *>(t.head + T);
+        s_pl = reinterpret_cast<float *>(t.nxt + 2 * T);
+        return t;
+    };
+    // slice `part` of `parts` of a context's tables: keys = EMPTY, min column = INT_MAX, heads = -1
+    auto clear_slice = [&](int c, int part, int parts, int lane_or_tid, int stride) {
+        float *unused;
+        const FlowTables t = tables_of(c, unused);
+        uint4 *e4p = reinterpret_cast<uint4 *>(t.ent);   // two entries per vector
+        uint4 *h4 = reinterpret_cast<uint4 *>(t.head);   // four heads per vector
+        const uint4 e4 = make_uint4(KEY_EMPTY, 0x7fffffffu, KEY_EMPTY, 0x7fffffffu);
+        const uint4 m4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        for (int q = part * stride + lane_or_tid; q < (T >> 1); q += parts * stride) e4p[q] = e4;
+        for (int q = part * stride + lane_or_tid; q < (T >> 2); q += parts * stride) h4[q] = m4;
+    };
+
+    const int JS = n_d + n_q;
+    if (MODE == SLR_MODE_STRICT) {
+        for (int k = tid; k < SLR_PTAB_SIZE; k += nthr) s_ptab[k] = p.ptab[k];
+        for (int k = tid; k < SLR_BTAB_SIZE; k += nthr) s_btab[k] = p.btab[k];
+    }
+    for (int c = 0; c < FLOW_CTX; c++) clear_slice(c, 0, 1, tid, nthr);
+    // job order inside a step: the decode jobs first (the next step's query jobs wait for all of them, and a job
+    // takes most of a step from draw to completion with 8 warps per scheduler), then the query jobs
+    for (int s = tid; s < JS; s += nthr) jobmap[s] = (s < n_d) ? (uint16_t)s : (uint16_t)(0x8000u | (unsigned)(s - n_d));
+    if (tid < 1 + 3 * FLOW_CTX) job_ctr[tid] = 0;
+    uint64_t policy = 0;
+    if (tid == 0) {
+        for (int s = 0; s < FLOW_STAGES; s++) slr::mbar_init(&bar_stage[s], 1);
+        slr::mbar_fence_init();
+    }
+    policy = make_evict_first_policy();
+    __syncthreads();
+
+    // TMA bulk copies of row r (CTA-local index) into stage r % FLOW_STAGES, issued by one whole warp
+    auto issue_row = [&](int r) {
+        const long long rg = r_begin + r;
+        const int i = (int)(rg / p.batch), b = (int)(rg - (long long)i * p.batch);
+        uint64_t *bar = &bar_stage[r % FLOW_STAGES];
+        unsigned char *stage = stage0 + (size_t)(r % FLOW_STAGES) * stage_bytes;
+        if (lane == 0) slr::mbar_expect_tx(bar, (uint32_t)stage_bytes);
+        __syncwarp();
+        if (MODE == MODE_PHASE_INPUT) {  // stage = pL f32[W] | pR f32[W] | mL u8[W] | mR u8[W]
+            const size_t offL = ((size_t)(b * 2 + 0) * p.H + i) * W, offR = ((size_t)(b * 2 + 1) * p.H + i) * W;
+            if (lane == 0) tma_load_1d_hint(stage, p.phase + offL, 4u * W, bar, policy);
+            if (lane == 1) tma_load_1d_hint(stage + 4 * W, p.phase + offR, 4u * W, bar, policy);
+            if (lane == 2) tma_load_1d_hint(stage + 8 * W, p.mask + offL, (uint32_t)W, bar, policy);
+            if (lane == 3) tma_load_1d_hint(stage + 9 * W, p.mask + offR, (uint32_t)W, bar, policy);
+            return;
+        }
+        const uint8_t *src = p.stack + ((size_t)b * 2 * N * p.H + i) * W;
+        for (int v = lane; v < 2 * N; v += 32)   // plane v of this scan (cam-major, then image index)
+            tma_load_1d_hint(stage + (size_t)v * W, src + (size_t)v * p.H * W, (uint32_t)W, bar, policy);
+    };
+    if (tid < 32) {
+        issue_row(0);
+        if (R > 1) issue_row(1);
+    }
+
+    const int ntasks = W >> 1;   // 4-pixel chunks, right and left chunk of the same columns on neighbouring lanes
+    const int total_jobs = (R + 2) * JS;
+    const size_t scan_px = (size_t)p.H * W;
+    unsigned n_local = 0;
+
+    // per-warp cursor: step t of the job last drawn, and (i, b) of CTA-local row t
+    int t = 0, t_base = 0;
+    int row_i = (int)(r_begin / p.batch), row_b = (int)(r_begin - (long long)row_i * p.batch);
+
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = atomicAdd(job_ctr, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= total_jobs) break;
+        while (g >= t_base + JS) {
+            t_base += JS;
+            ++t;
+            if (++row_b == p.batch) row_b = 0, ++row_i;
+        }
+        const unsigned code = jobmap[g - t_base];
+        const int idx = (int)(code & 0x7fffu);
+
+        if (!(code & 0x8000u)) {
+            // ================= decode job idx of row r = t - 1 (+ clear slice idx of row r + 1's context) =================
+            const int r = t - 1;
+            if (r < 0 || r >= R) continue;
+            const int c = r % FLOW_CTX, u = r / FLOW_CTX;
+            // this row's tables were cleared by the last query job of row r - 3 (rows 0..2: by the prologue)
+            wait_count(&cleared[c], u, lane);
+            slr::mbar_wait(&bar_stage[r % FLOW_STAGES], (uint32_t)((r / FLOW_STAGES) & 1));
+            float *s_pl;
+            const FlowTables tab = tables_of(c, s_pl);
+            const unsigned char *stage = stage0 + (size_t)(r % FLOW_STAGES) * stage_bytes;
+            {
+                const int task = idx * 32 + lane;
+                const bool live = task < ntasks;
+                const int x0 = live ? 4 * (task >> 1) : 0;
+                const bool right = (task & 1) == 0;
+                float ph[4];
+                bool ok[4];
+                load_phases<MODE, 4>(stage, W, N, x0, right, p, s_ptab, s_btab, ph, ok);
+                // the right lane hands its upper two phases to the left lane: every lane decodes 4 pixels and files 2
+                const float n2 = __shfl_xor_sync(0xffffffffu, ph[2], 1), n3 = __shfl_xor_sync(0xffffffffu, ph[3], 1);
+                const unsigned okb = __shfl_xor_sync(0xffffffffu, (ok[2] ? 1u : 0u) | (ok[3] ? 2u : 0u), 1);
+                float ip[2] = {right ? ph[0] : n2, right ? ph[1] : n3};
+                bool io[2] = {live && (right ? ok[0] : (okb & 1u) != 0), live && (right ? ok[1] : (okb & 2u) != 0)};
+                insert_right<2, CLAMP>(tab, ip, io, right ? x0 : x0 + 2);
+                if (live && !right)
+                    reinterpret_cast<float4 *>(s_pl)[x0 >> 2] =
+                        make_float4(ok[0] ? ph[0] : slr::qnan(), ok[1] ? ph[1] : slr::qnan(), ok[2] ? ph[2] : slr::qnan(),
+                                    ok[3] ? ph[3] : slr::qnan());
+            }
+            __syncwarp();
+            int last = 0;
+            if (lane == 0) last = add_acq_rel_s32(&done_d[c], 1) + 1 == (u + 1) * n_d;
+            last = __shfl_sync(0xffffffffu, last, 0);
+            // the stage buffer of row r is consumed: stream row r + 2 into it
+            if (last && r + FLOW_STAGES < R) issue_row(r + FLOW_STAGES);
+        } else {
+            // ================= query + emit job idx (32 left pixels) of row r = t - 2 =================
+            const int r = t - 2;
+            if (r < 0 || r >= R) continue;
+            const int c = r % FLOW_CTX, u = r / FLOW_CTX;
+            // (i, b) of row r from the cursor of row t
+            int b = row_b - 2, i = row_i;
+            while (b < 0) b += p.batch, --i;
+            const size_t orow = ((size_t)b * p.H + i) * W;
+            const size_t mrow = (size_t)i * W;
+            const int j = idx * 32 + lane;
+            const bool inside = j < W;
+            // undistortPoints maps of the left pixel (L2-resident, coalesced); issued before the table walk
+            float ulx = 0.0f, uly = 0.0f;
+            if (inside) {
+                ulx = __ldg(p.lx + mrow + j);
+                uly = __ldg(p.ly + mrow + j);
+            }
+            wait_count(&done_d[c], (u + 1) * n_d, lane);
+            float *s_pl;
+            const FlowTables tab = tables_of(c, s_pl);
+            const float v = inside ? s_pl[j] : slr::qnan();
+            const int best = (v != v) ? INT_MAX : first_match<CLAMP>(tab, v);
+            const bool hit = best != INT_MAX;
+            const float urx = hit ? __ldg(p.rx + mrow + best) : 0.0f;
+            if (!hit) ulx = 0.0f, uly = 0.0f;
+            // every pixel is reprojected unconditionally (dummy inputs where there is no match); misses become NaN
+            float X, Y, Z;
+            slr::reproject_q(p.calib, (double)ulx, (double)uly, (double)__fsub_rn(ulx, urx), X, Y, Z);
+            n_local += hit ? 1u : 0u;
+            if (inside) {
+                float *dst = p.xyz + (orow + j) * 3;
+                dst[0] = hit ? X : slr::qnan();
+                dst[1] = hit ? Y : slr::qnan();
+                dst[2] = hit ? Z : slr::qnan();
+                p.valid[orow + j] = hit ? 1 : 0;
+                if (p.match_k) p.match_k[orow + j] = hit ? best : -1;
+            }
+            __syncwarp();
+            int last = 0;
+            if (lane == 0) last = add_acq_rel_s32(&done_q[c], 1) + 1 == (u + 1) * n_q;
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {  // nobody reads this row's tables any more: clear them for row r + 3
+                clear_slice(c, 0, 1, lane, 32);
+                __syncwarp();
+                if (lane == 0) add_acq_rel_s32(&cleared[c], 1);
+            }
+        }
+    }
+    if (p.n_points) {
+        const unsigned long long s = slr::warp_sum_u32(n_local);
+        if (lane == 0 && s) atomicAdd(p.n_points, s);
+    }
+    (void)scan_px;
+}
+
+}  // namespace
+
+// Launch the dataflow kernel when the shape fits (three row contexts + two stage buffers in one SM's shared memory);
+// *handled = false sends the caller to k_fused_mf / the un-fused kernels.
+slr_status slr_launch_fused_flow(slr_engine *e, int mode, const FusedParams &p_in, bool *handled)
+{
+    *handled = false;
+    if (const char *ev = getenv("SLR_FUSED_FLOW"))
+        if (atoi(ev) == 0) return SLR_OK;
+    FusedParams p = p_in;
+    const int W = p.W;
+    const size_t stage_bytes = (mode == MODE_PHASE_INPUT) ? (size_t)10 * W : (size_t)2 * p.N * W;
+    const size_t smem = FLOW_HEADER + FLOW_STAGES * stage_bytes + FLOW_CTX * flow_ctx_bytes(W, p.T) +
+                        SLR_PTAB_SIZE * 4 + SLR_BTAB_SIZE * 4;
+    const int n_d = (W / 2 + 31) / 32, n_q = (W + 31) / 32;
+    if (smem > 227 * 1024 || 2 * p.T > 32768 || n_d + n_q > FLOW_MAX_JOBS || (stage_bytes % 16) != 0) return SLR_OK;
+    // rows per CTA must keep the job counter inside int32
+    const long long rows = (long long)p.batch * p.H;
+    if ((rows / e->num_sms + 4) * (n_d + n_q) >= (1LL << 30)) return SLR_OK;
+    *handled = true;
+
+    // one CTA per SM, up to 32 warps; narrow rows (few jobs per step) run two smaller CTAs per SM when they fit
+    const int ctas = (2 * (smem + 1024) <= 228 * 1024) ? 2 : 1;
+    int warps = 32 / ctas;
+    while (warps > 2 && warps * 2 > n_d + n_q) warps >>= 1;
+    if (const char *ev = getenv("SLR_FLOW_WARPS")) {
+        const int w = atoi(ev);
+        if (w >= 1 && w <= 32 / ctas) warps = w;
+    }
+    void (*kern)(const FusedParams, int, int) = (mode == SLR_MODE_STRICT)      ? k_fused_flow<SLR_MODE_STRICT>
+                                                : (mode == SLR_MODE_CORRECTED) ? k_fused_flow<SLR_MODE_CORRECTED>
+                                                                               : k_fused_flow<MODE_PHASE_INPUT>;
+    SLR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = (long long)e->num_sms * ctas;
+    if (grid > rows) grid = rows;
+    if (grid < 1) return SLR_OK;
+    kern<<<(unsigned)grid, warps * 32, smem, e->stream>>>(p, n_d, n_q);
+    SLR_CHECK_LAUNCH(e);
+    return SLR_OK;
+}
