@@ -231,7 +231,7 @@ k_fused_mf(const FusedParams p)
 #pragma unroll
             for (int u = 0; u < QPX; u++) {
                 const bool hit = best[u] != INT_MAX;
-                const float ulx = hit ? s_lx[j[u]] : 0.0f, uly = hit ? s_ly[j[u]] : 0.0f, urx = hit ? s_rx[best[u]] : 0.0f;
+                const float ulx = hit ? s_lx[j[u]] : 0.0f, uly = hit ? s_ly[j[u]] : 0.0f, urx = hit ? s_rx[best[u]] : -1.0f;  // misses: disparity 1
                 if (SLR_ABLATE(1))
                     X[u] = ulx, Y[u] = uly, Z[u] = urx;
                 else

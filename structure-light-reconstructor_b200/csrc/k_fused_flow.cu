@@ -4,19 +4,20 @@
 //
 // k_fused_mf runs a row in CTA-wide phases (clear | decode + insert | query + emit) separated by __syncthreads();
 // its profile shows a quarter of the resident warps parked at those barriers and the issue slots 67 % busy.
-// Here one persistent CTA per SM keeps THREE rows in flight and no CTA-wide barrier in steady state:
+// Here one persistent CTA per SM keeps FOUR row contexts in flight and no CTA-wide barrier in steady state:
 //
 //   row r+1   TMA bulk copies of its image rows in flight      (stage buffer (r+1) % 2)
 //   row r     decode jobs: image bytes -> phases, right phases filed in the tables, left phases parked
-//             (context r % 3, stage buffer r % 2)
-//   row r-1   query jobs: first-k match of 32 left pixels + Q reprojection + stores   (context (r-1) % 3)
-//   row r-2   its tables being cleared by the warp that finished its last query job  (context (r-2) % 3)
+//             (context r % 4, stage buffer r % 2)
+//   row r-1   decoded, waiting (its last decode jobs may still be running)
+//   row r-2   query jobs: first-k match of 32 left pixels + Q reprojection + stores   (context (r-2) % 4)
+//   row r-3   its tables being cleared by the warp that finished its last query job  (context (r-3) % 4)
 //
 // Work is cut into warp-sized jobs; every warp draws the next job from ONE shared counter whose order lists, per
 // step, the decode jobs of row r and then the query jobs of row r-1, so table-lookup-bound, latency-bound and
 // fp64-bound instruction streams share the SM at all times.  A job waits only on per-context completion counters
 // (release/acquire in shared memory) of jobs that precede it in the global order, which makes the schedule
-// deadlock-free: decode(r) needs the clear after query(r-3) and the stage re-armed after decode(r-2); query(r)
+// deadlock-free: decode(r) needs the clear after query(r-4) and the stage re-armed after decode(r-2); query(r)
 // needs decode(r).  The warp that completes the last decode job of a row re-arms that row's stage buffer with the
 // TMA copies of row r+2.
 #include <limits.h>
@@ -28,10 +29,10 @@ namespace {
 
 using namespace slr_fused;
 
-constexpr int FLOW_CTX = 3;        // row contexts (tables + parked left phases)
+constexpr int FLOW_CTX = 4;        // row contexts (tables + parked left phases); a power of two
+constexpr int FLOW_LAG = 2;        // steps between a row's decode jobs and its query jobs
 constexpr int FLOW_STAGES = 2;     // TMA stage buffers
-constexpr int FLOW_HEADER = 1024;  // mbarriers, counters, job map
-constexpr int FLOW_MAX_JOBS = 448; // jobs per step the header's job map can hold
+constexpr int FLOW_HEADER = 1024;  // mbarriers, counters, row descriptors
 
 using FlowTables = RowTablesT<int16_t>;
 
@@ -51,13 +52,17 @@ __device__ __forceinline__ int add_acq_rel_s32(int *p, int v)
 __device__ __forceinline__ void wait_count(const int *ctr, int target, int lane)
 {
     if (lane == 0)
-        while (ld_acquire_s32(ctr) < target) {
-        }
+        while (ld_acquire_s32(ctr) < target) __nanosleep(32);
     __syncwarp();
 }
 
 // shared-memory bytes of one row context: ent[T] (8 B) + head[T] (4 B) + nxt[2T] (2 B) + left phases [W] (4 B)
 __host__ __device__ inline size_t flow_ctx_bytes(int W, int T) { return (size_t)16 * T + (size_t)4 * W; }
+
+// first pixel of a row in the outputs / in the undistort maps, written by the warp that issues the row's TMA copies
+struct RowInfo {
+    unsigned out_px, map_px;
+};
 
 template <int MODE>
 __global__ void __launch_bounds__(1024, 1)
@@ -80,17 +85,17 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q)
     int *done_d = job_ctr + 1;                                             // [FLOW_CTX] decode jobs completed
     int *done_q = done_d + FLOW_CTX;                                       // [FLOW_CTX] query jobs completed
     int *cleared = done_q + FLOW_CTX;                                      // [FLOW_CTX] table clears completed
-    uint16_t *jobmap = reinterpret_cast<uint16_t *>(smem + 96);            // [n_d + n_q]: bit 15 = query job
+    RowInfo *rowinfo = reinterpret_cast<RowInfo *>(smem + 128);            // [8] ring, indexed by row & 7
     const size_t stage_bytes = (MODE == MODE_PHASE_INPUT) ? (size_t)10 * W : (size_t)2 * N * W;
     unsigned char *stage0 = smem + FLOW_HEADER;
     unsigned char *ctx0 = stage0 + FLOW_STAGES * stage_bytes;
-    const size_t ctx_bytes = flow_ctx_bytes(W, T);
-    int *s_ptab = reinterpret_cast<int *>(ctx0 + FLOW_CTX * ctx_bytes);       // [SLR_PTAB_SIZE] (strict)
-    uint32_t *s_btab = reinterpret_cast<uint32_t *>(s_ptab + SLR_PTAB_SIZE);  // [SLR_BTAB_SIZE] (strict)
+    const unsigned ctx_bytes = (unsigned)flow_ctx_bytes(W, T);
+    int *s_ptab = reinterpret_cast<int *>(ctx0 + (size_t)FLOW_CTX * ctx_bytes);  // [SLR_PTAB_SIZE] (strict)
+    uint32_t *s_btab = reinterpret_cast<uint32_t *>(s_ptab + SLR_PTAB_SIZE);     // [SLR_BTAB_SIZE] (strict)
 
     auto tables_of = [&](int c, float *&s_pl) {
         FlowTables t;
-        unsigned char *base = ctx0 + (size_t)c * ctx_bytes;
+        unsigned char *base = ctx0 + (unsigned)c * ctx_bytes;
         t.T = T;
         t.logT = p.logT;
         t.HB = T;
@@ -100,16 +105,16 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q)
         s_pl = reinterpret_cast<float *>(t.nxt + 2 * T);
         return t;
     };
-    // slice `part` of `parts` of a context's tables: keys = EMPTY, min column = INT_MAX, heads = -1
-    auto clear_slice = [&](int c, int part, int parts, int lane_or_tid, int stride) {
+    // a context's tables: keys = EMPTY, min column = INT_MAX, heads = -1
+    auto clear_tables = [&](int c, int first, int stride) {
         float *unused;
         const FlowTables t = tables_of(c, unused);
         uint4 *e4p = reinterpret_cast<uint4 *>(t.ent);   // two entries per vector
         uint4 *h4 = reinterpret_cast<uint4 *>(t.head);   // four heads per vector
         const uint4 e4 = make_uint4(KEY_EMPTY, 0x7fffffffu, KEY_EMPTY, 0x7fffffffu);
         const uint4 m4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        for (int q = part * stride + lane_or_tid; q < (T >> 1); q += parts * stride) e4p[q] = e4;
-        for (int q = part * stride + lane_or_tid; q < (T >> 2); q += parts * stride) h4[q] = m4;
+        for (int q = first; q < (T >> 1); q += stride) e4p[q] = e4;
+        for (int q = first; q < (T >> 2); q += stride) h4[q] = m4;
     };
 
     const int JS = n_d + n_q;
@@ -117,17 +122,13 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q)
         for (int k = tid; k < SLR_PTAB_SIZE; k += nthr) s_ptab[k] = p.ptab[k];
         for (int k = tid; k < SLR_BTAB_SIZE; k += nthr) s_btab[k] = p.btab[k];
     }
-    for (int c = 0; c < FLOW_CTX; c++) clear_slice(c, 0, 1, tid, nthr);
-    // job order inside a step: the decode jobs first (the next step's query jobs wait for all of them, and a job
-    // takes most of a step from draw to completion with 8 warps per scheduler), then the query jobs
-    for (int s = tid; s < JS; s += nthr) jobmap[s] = (s < n_d) ? (uint16_t)s : (uint16_t)(0x8000u | (unsigned)(s - n_d));
+    for (int c = 0; c < FLOW_CTX; c++) clear_tables(c, tid, nthr);
     if (tid < 1 + 3 * FLOW_CTX) job_ctr[tid] = 0;
-    uint64_t policy = 0;
     if (tid == 0) {
         for (int s = 0; s < FLOW_STAGES; s++) slr::mbar_init(&bar_stage[s], 1);
         slr::mbar_fence_init();
     }
-    policy = make_evict_first_policy();
+    const uint64_t policy = make_evict_first_policy();
     __syncthreads();
 
     // TMA bulk copies of row r (CTA-local index) into stage r % FLOW_STAGES, issued by one whole warp
@@ -136,7 +137,11 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q)
         const int i = (int)(rg / p.batch), b = (int)(rg - (long long)i * p.batch);
         uint64_t *bar = &bar_stage[r % FLOW_STAGES];
         unsigned char *stage = stage0 + (size_t)(r % FLOW_STAGES) * stage_bytes;
-        if (lane == 0) slr::mbar_expect_tx(bar, (uint32_t)stage_bytes);
+        if (lane == 0) {
+            rowinfo[r & 7].out_px = (unsigned)(((size_t)b * p.H + i) * W);
+            rowinfo[r & 7].map_px = (unsigned)((size_t)i * W);
+            slr::mbar_expect_tx(bar, (uint32_t)stage_bytes);   // release: the descriptor is visible to every waiter
+        }
         __syncwarp();
         if (MODE == MODE_PHASE_INPUT) {  // stage = pL f32[W] | pR f32[W] | mL u8[W] | mR u8[W]
             const size_t offL = ((size_t)(b * 2 + 0) * p.H + i) * W, offR = ((size_t)(b * 2 + 1) * p.H + i) * W;
@@ -156,40 +161,34 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q)
     }
 
     const int ntasks = W >> 1;   // 4-pixel chunks, right and left chunk of the same columns on neighbouring lanes
-    const int total_jobs = (R + 2) * JS;
-    const size_t scan_px = (size_t)p.H * W;
+    const int total_jobs = (R + 1 + FLOW_LAG) * JS;
     unsigned n_local = 0;
+    int t = 0, t_base = 0;       // per-warp cursor: step of the job last drawn
 
-    // per-warp cursor: step t of the job last drawn, and (i, b) of CTA-local row t
-    int t = 0, t_base = 0;
-    int row_i = (int)(r_begin / p.batch), row_b = (int)(r_begin - (long long)row_i * p.batch);
-
+    // Step t lists the n_d decode jobs of row t - 1, then the n_q query jobs of row t - 1 - FLOW_LAG: a job takes most
+    // of a step from draw to completion (8 warps share a scheduler), so a row's queries are drawn two steps after
+    // its decode jobs and practically never wait.
     for (;;) {
         int g = 0;
         if (lane == 0) g = atomicAdd(job_ctr, 1);
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= total_jobs) break;
-        while (g >= t_base + JS) {
-            t_base += JS;
-            ++t;
-            if (++row_b == p.batch) row_b = 0, ++row_i;
-        }
-        const unsigned code = jobmap[g - t_base];
-        const int idx = (int)(code & 0x7fffu);
+        while (g >= t_base + JS) t_base += JS, ++t;
+        const int s = g - t_base;
 
-        if (!(code & 0x8000u)) {
-            // ================= decode job idx of row r = t - 1 (+ clear slice idx of row r + 1's context) =================
+        if (s < n_d) {
+            // ================= decode job s of row r = t - 1 =================
             const int r = t - 1;
             if (r < 0 || r >= R) continue;
-            const int c = r % FLOW_CTX, u = r / FLOW_CTX;
-            // this row's tables were cleared by the last query job of row r - 3 (rows 0..2: by the prologue)
+            const int c = r & (FLOW_CTX - 1), u = r / FLOW_CTX;
+            // this row's tables were cleared by the last query job of row r - FLOW_CTX (first rows: by the prologue)
             wait_count(&cleared[c], u, lane);
             slr::mbar_wait(&bar_stage[r % FLOW_STAGES], (uint32_t)((r / FLOW_STAGES) & 1));
             float *s_pl;
             const FlowTables tab = tables_of(c, s_pl);
             const unsigned char *stage = stage0 + (size_t)(r % FLOW_STAGES) * stage_bytes;
             {
-                const int task = idx * 32 + lane;
+                const int task = s * 32 + lane;
                 const bool live = task < ntasks;
                 const int x0 = live ? 4 * (task >> 1) : 0;
                 const bool right = (task & 1) == 0;
@@ -214,49 +213,49 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q)
             // the stage buffer of row r is consumed: stream row r + 2 into it
             if (last && r + FLOW_STAGES < R) issue_row(r + FLOW_STAGES);
         } else {
-            // ================= query + emit job idx (32 left pixels) of row r = t - 2 =================
-            const int r = t - 2;
+            // ================= query + emit job (32 left pixels) of row r = t - 1 - FLOW_LAG =================
+            const int r = t - 1 - FLOW_LAG;
             if (r < 0 || r >= R) continue;
-            const int c = r % FLOW_CTX, u = r / FLOW_CTX;
-            // (i, b) of row r from the cursor of row t
-            int b = row_b - 2, i = row_i;
-            while (b < 0) b += p.batch, --i;
-            const size_t orow = ((size_t)b * p.H + i) * W;
-            const size_t mrow = (size_t)i * W;
-            const int j = idx * 32 + lane;
+            const int c = r & (FLOW_CTX - 1), u = r / FLOW_CTX;
+            const int j = (s - n_d) * 32 + lane;
             const bool inside = j < W;
-            // undistortPoints maps of the left pixel (L2-resident, coalesced); issued before the table walk
+            wait_count(&done_d[c], (u + 1) * n_d, lane);
+            const RowInfo ri = rowinfo[r & 7];
+            // undistortPoints maps of the left pixel (L2-resident, coalesced): in flight during the table walk
             float ulx = 0.0f, uly = 0.0f;
             if (inside) {
-                ulx = __ldg(p.lx + mrow + j);
-                uly = __ldg(p.ly + mrow + j);
+                ulx = __ldg(p.lx + ri.map_px + j);
+                uly = __ldg(p.ly + ri.map_px + j);
             }
-            wait_count(&done_d[c], (u + 1) * n_d, lane);
             float *s_pl;
             const FlowTables tab = tables_of(c, s_pl);
             const float v = inside ? s_pl[j] : slr::qnan();
             const int best = (v != v) ? INT_MAX : first_match<CLAMP>(tab, v);
             const bool hit = best != INT_MAX;
-            const float urx = hit ? __ldg(p.rx + mrow + best) : 0.0f;
-            if (!hit) ulx = 0.0f, uly = 0.0f;
-            // every pixel is reprojected unconditionally (dummy inputs where there is no match); misses become NaN
+            // every pixel is reprojected unconditionally; misses get harmless inputs (disparity 1) and become NaN
+            float d = 1.0f;
+            if (hit)
+                d = __fsub_rn(ulx, __ldg(p.rx + ri.map_px + best));
+            else
+                ulx = 0.0f, uly = 0.0f;
             float X, Y, Z;
-            slr::reproject_q(p.calib, (double)ulx, (double)uly, (double)__fsub_rn(ulx, urx), X, Y, Z);
+            slr::reproject_q(p.calib, (double)ulx, (double)uly, (double)d, X, Y, Z);
             n_local += hit ? 1u : 0u;
             if (inside) {
-                float *dst = p.xyz + (orow + j) * 3;
+                const size_t o = (size_t)ri.out_px + j;
+                float *dst = p.xyz + o * 3;
                 dst[0] = hit ? X : slr::qnan();
                 dst[1] = hit ? Y : slr::qnan();
                 dst[2] = hit ? Z : slr::qnan();
-                p.valid[orow + j] = hit ? 1 : 0;
-                if (p.match_k) p.match_k[orow + j] = hit ? best : -1;
+                p.valid[o] = hit ? 1 : 0;
+                if (p.match_k) p.match_k[o] = hit ? best : -1;
             }
             __syncwarp();
             int last = 0;
             if (lane == 0) last = add_acq_rel_s32(&done_q[c], 1) + 1 == (u + 1) * n_q;
             last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) {  // nobody reads this row's tables any more: clear them for row r + 3
-                clear_slice(c, 0, 1, lane, 32);
+            if (last) {  // nobody reads this row's tables any more: clear them for row r + FLOW_CTX
+                clear_tables(c, lane, 32);
                 __syncwarp();
                 if (lane == 0) add_acq_rel_s32(&cleared[c], 1);
             }
@@ -266,7 +265,6 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q)
         const unsigned long long s = slr::warp_sum_u32(n_local);
         if (lane == 0 && s) atomicAdd(p.n_points, s);
     }
-    (void)scan_px;
 }
 
 }  // namespace
@@ -284,16 +282,16 @@ slr_status slr_launch_fused_flow(slr_engine *e, int mode, const FusedParams &p_i
     const size_t smem = FLOW_HEADER + FLOW_STAGES * stage_bytes + FLOW_CTX * flow_ctx_bytes(W, p.T) +
                         SLR_PTAB_SIZE * 4 + SLR_BTAB_SIZE * 4;
     const int n_d = (W / 2 + 31) / 32, n_q = (W + 31) / 32;
-    if (smem > 227 * 1024 || 2 * p.T > 32768 || n_d + n_q > FLOW_MAX_JOBS || (stage_bytes % 16) != 0) return SLR_OK;
-    // rows per CTA must keep the job counter inside int32
+    if (smem > 227 * 1024 || 2 * p.T > 32768 || (stage_bytes % 16) != 0) return SLR_OK;
+    // rows per CTA must keep the job counter inside int32, pixel offsets inside uint32
     const long long rows = (long long)p.batch * p.H;
-    if ((rows / e->num_sms + 4) * (n_d + n_q) >= (1LL << 30)) return SLR_OK;
+    if ((rows / e->num_sms + 8) * (n_d + n_q) >= (1LL << 30) || rows * W >= (1LL << 32)) return SLR_OK;
     *handled = true;
 
     // one CTA per SM, up to 32 warps; narrow rows (few jobs per step) run two smaller CTAs per SM when they fit
     const int ctas = (2 * (smem + 1024) <= 228 * 1024) ? 2 : 1;
     int warps = 32 / ctas;
-    while (warps > 2 && warps * 2 > n_d + n_q) warps >>= 1;
+    while (warps > 2 && warps > n_d + n_q) warps >>= 1;
     if (const char *ev = getenv("SLR_FLOW_WARPS")) {
         const int w = atoi(ev);
         if (w >= 1 && w <= 32 / ctas) warps = w;

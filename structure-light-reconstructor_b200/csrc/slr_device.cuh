@@ -319,6 +319,42 @@ __device__ __forceinline__ int phase_bucket(float p) { return __float2int_rd(__f
 // ------------------------------------------------------------------------------------------------
 // emitters
 // ------------------------------------------------------------------------------------------------
+// float(RN(a0 / w)), float(RN(a1 / w)), float(RN(a2 / w)) — the three double divisions of the reprojection narrowed
+// to float, bit-identical to IEEE division followed by the cast (Duke/mfreconstruct.cpp:303-309 on cv::Mat doubles).
+// One shared reciprocal (MUFU seed + two Newton steps), one correction step per quotient: q is then within one
+// double ulp of a / w, so (float)q equals (float)RN(a / w) unless q sits within a few double ulps of a float
+// rounding boundary (the 29 dropped mantissa bits read 0x10000000 +- 8) — those lanes, and any operand or result
+// outside the normal range (zero disparity with Q[3][3] == 0 gives w = 0), take the IEEE divisions.
+__device__ __forceinline__ void div3_narrow(double a0, double a1, double a2, double w, float &f0, float &f1, float &f2)
+{
+    const unsigned ew = ((unsigned)__double2hiint(w) >> 20) & 0x7ffu;
+    bool slow = (ew - 523u) > 1000u;                       // |w| outside [2^-500, 2^500], zero, inf, nan
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(w));
+    double e = fma(-w, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-w, r, 1.0);
+    r = fma(r, e, r);
+    auto one = [&](double a, float &f) {
+        double q = a * r;
+        const double rem = fma(-q, w, a);
+        q = fma(rem, r, q);
+        f = __double2float_rn(q);
+        const unsigned lo = (unsigned)__double2loint(q) & 0x1FFFFFFFu;
+        const unsigned ef = (__float_as_uint(f) >> 23) & 0xffu;
+        slow |= (lo - 0x0FFFFFF8u) < 17u;                  // float rounding boundary within 8 double ulps
+        slow |= (ef - 1u) > 253u;                          // zero, subnormal, inf or nan result
+    };
+    one(a0, f0);
+    one(a1, f1);
+    one(a2, f2);
+    if (slow) {
+        f0 = __double2float_rn(__ddiv_rn(a0, w));
+        f1 = __double2float_rn(__ddiv_rn(a1, w));
+        f2 = __double2float_rn(__ddiv_rn(a2, w));
+    }
+}
+
 // p = Q * [x y d 1]^T in double (sums left to right), /w, narrowed to float, then the optional
 // 3x4 rigid transform.  Duke/mfreconstruct.cpp:299-323, Duke/reconstruct.cpp:570-594.
 __device__ __forceinline__ void reproject_q(const slr_calib_dev &c, double x, double y, double d, float &ox,
@@ -344,9 +380,8 @@ __device__ __forceinline__ void reproject_q(const slr_calib_dev &c, double x, do
             r[i] = s;
         }
     }
-    float px = __double2float_rn(__ddiv_rn(r[0], r[3]));
-    float py = __double2float_rn(__ddiv_rn(r[1], r[3]));
-    float pz = __double2float_rn(__ddiv_rn(r[2], r[3]));
+    float px, py, pz;
+    div3_narrow(r[0], r[1], r[2], r[3], px, py, pz);
     if (c.has_rigid) {
         float o[3];
 #pragma unroll
