@@ -32,6 +32,7 @@ using namespace slr_fused;
 constexpr int FLOW_CTX = 4;        // row contexts (tables + parked left phases); a power of two
 constexpr int FLOW_LAG = 2;        // steps between a row's decode jobs and its query jobs
 constexpr int FLOW_STAGES = 2;     // TMA stage buffers
+constexpr int FLOW_QPX = 2;        // left pixels per lane in one query job
 constexpr int FLOW_HEADER = 1024;  // mbarriers, counters, row descriptors
 
 using FlowTables = RowTablesT<int16_t>;
@@ -66,7 +67,7 @@ struct RowInfo {
 
 template <int MODE>
 __global__ void __launch_bounds__(1024, 1)
-k_fused_flow(const FusedParams p, const int n_d, const int n_q)
+k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned js_magic)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool CLAMP = MODE == MODE_PHASE_INPUT;
@@ -163,7 +164,6 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q)
     const int ntasks = W >> 1;   // 4-pixel chunks, right and left chunk of the same columns on neighbouring lanes
     const int total_jobs = (R + 1 + FLOW_LAG) * JS;
     unsigned n_local = 0;
-    int t = 0, t_base = 0;       // per-warp cursor: step of the job last drawn
 
     // Step t lists the n_d decode jobs of row t - 1, then the n_q query jobs of row t - 1 - FLOW_LAG: a job takes most
     // of a step from draw to completion (8 warps share a scheduler), so a row's queries are drawn two steps after
@@ -173,8 +173,8 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q)
         if (lane == 0) g = atomicAdd(job_ctr, 1);
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= total_jobs) break;
-        while (g >= t_base + JS) t_base += JS, ++t;
-        const int s = g - t_base;
+        const int t = (int)__umulhi((unsigned)g, js_magic);   // g / JS (exact for g * JS < 2^32, checked by the launcher)
+        const int s = g - t * JS;
 
         if (s < n_d) {
             // ================= decode job s of row r = t - 1 =================
@@ -213,42 +213,54 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q)
             // the stage buffer of row r is consumed: stream row r + 2 into it
             if (last && r + FLOW_STAGES < R) issue_row(r + FLOW_STAGES);
         } else {
-            // ================= query + emit job (32 left pixels) of row r = t - 1 - FLOW_LAG =================
+            // ================= query + emit job (FLOW_QPX * 32 left pixels) of row r = t - 1 - FLOW_LAG =================
             const int r = t - 1 - FLOW_LAG;
             if (r < 0 || r >= R) continue;
             const int c = r & (FLOW_CTX - 1), u = r / FLOW_CTX;
-            const int j = (s - n_d) * 32 + lane;
-            const bool inside = j < W;
             wait_count(&done_d[c], (u + 1) * n_d, lane);
             const RowInfo ri = rowinfo[r & 7];
-            // undistortPoints maps of the left pixel (L2-resident, coalesced): in flight during the table walk
-            float ulx = 0.0f, uly = 0.0f;
-            if (inside) {
-                ulx = __ldg(p.lx + ri.map_px + j);
-                uly = __ldg(p.ly + ri.map_px + j);
-            }
             float *s_pl;
             const FlowTables tab = tables_of(c, s_pl);
-            const float v = inside ? s_pl[j] : slr::qnan();
-            const int best = (v != v) ? INT_MAX : first_match<CLAMP>(tab, v);
-            const bool hit = best != INT_MAX;
-            // every pixel is reprojected unconditionally; misses get harmless inputs (disparity 1) and become NaN
-            float d = 1.0f;
-            if (hit)
-                d = __fsub_rn(ulx, __ldg(p.rx + ri.map_px + best));
-            else
-                ulx = 0.0f, uly = 0.0f;
-            float X, Y, Z;
-            slr::reproject_q(p.calib, (double)ulx, (double)uly, (double)d, X, Y, Z);
-            n_local += hit ? 1u : 0u;
-            if (inside) {
-                const size_t o = (size_t)ri.out_px + j;
-                float *dst = p.xyz + o * 3;
-                dst[0] = hit ? X : slr::qnan();
-                dst[1] = hit ? Y : slr::qnan();
-                dst[2] = hit ? Z : slr::qnan();
-                p.valid[o] = hit ? 1 : 0;
-                if (p.match_k) p.match_k[o] = hit ? best : -1;
+            int j[FLOW_QPX], best[FLOW_QPX];
+            float ulx[FLOW_QPX], uly[FLOW_QPX], v[FLOW_QPX];
+#pragma unroll
+            for (int q = 0; q < FLOW_QPX; q++) {
+                j[q] = ((s - n_d) * FLOW_QPX + q) * 32 + lane;
+                const bool inside = j[q] < W;
+                // undistortPoints maps of the left pixel (L2-resident, coalesced): in flight during the table walk
+                ulx[q] = inside ? __ldg(p.lx + ri.map_px + j[q]) : 0.0f;
+                uly[q] = inside ? __ldg(p.ly + ri.map_px + j[q]) : 0.0f;
+                v[q] = inside ? s_pl[j[q]] : slr::qnan();
+            }
+#pragma unroll
+            for (int q = 0; q < FLOW_QPX; q++) best[q] = (v[q] != v[q]) ? INT_MAX : first_match<CLAMP>(tab, v[q]);
+            float d[FLOW_QPX], X[FLOW_QPX], Y[FLOW_QPX], Z[FLOW_QPX];
+#pragma unroll
+            for (int q = 0; q < FLOW_QPX; q++) {
+                // every pixel is reprojected unconditionally; misses get harmless inputs (disparity 1) and become NaN
+                const bool hit = best[q] != INT_MAX;
+                d[q] = 1.0f;
+                if (hit)
+                    d[q] = __fsub_rn(ulx[q], __ldg(p.rx + ri.map_px + best[q]));
+                else
+                    ulx[q] = 0.0f, uly[q] = 0.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < FLOW_QPX; q++)
+                slr::reproject_q(p.calib, (double)ulx[q], (double)uly[q], (double)d[q], X[q], Y[q], Z[q]);
+#pragma unroll
+            for (int q = 0; q < FLOW_QPX; q++) {
+                const bool hit = best[q] != INT_MAX;
+                n_local += hit ? 1u : 0u;
+                if (j[q] < W) {
+                    const size_t o = (size_t)ri.out_px + j[q];
+                    float *dst = p.xyz + o * 3;
+                    dst[0] = hit ? X[q] : slr::qnan();
+                    dst[1] = hit ? Y[q] : slr::qnan();
+                    dst[2] = hit ? Z[q] : slr::qnan();
+                    p.valid[o] = hit ? 1 : 0;
+                    if (p.match_k) p.match_k[o] = hit ? best[q] : -1;
+                }
             }
             __syncwarp();
             int last = 0;
@@ -281,11 +293,13 @@ slr_status slr_launch_fused_flow(slr_engine *e, int mode, const FusedParams &p_i
     const size_t stage_bytes = (mode == MODE_PHASE_INPUT) ? (size_t)10 * W : (size_t)2 * p.N * W;
     const size_t smem = FLOW_HEADER + FLOW_STAGES * stage_bytes + FLOW_CTX * flow_ctx_bytes(W, p.T) +
                         SLR_PTAB_SIZE * 4 + SLR_BTAB_SIZE * 4;
-    const int n_d = (W / 2 + 31) / 32, n_q = (W + 31) / 32;
+    const int n_d = (W / 2 + 31) / 32, n_q = (W + 32 * FLOW_QPX - 1) / (32 * FLOW_QPX);
     if (smem > 227 * 1024 || 2 * p.T > 32768 || (stage_bytes % 16) != 0) return SLR_OK;
     // rows per CTA must keep the job counter inside int32, pixel offsets inside uint32
     const long long rows = (long long)p.batch * p.H;
-    if ((rows / e->num_sms + 8) * (n_d + n_q) >= (1LL << 30) || rows * W >= (1LL << 32)) return SLR_OK;
+    const long long JS = n_d + n_q;
+    if ((rows / e->num_sms + 8) * JS * JS >= (1LL << 32) || rows * W >= (1LL << 32)) return SLR_OK;
+    const unsigned js_magic = (unsigned)(((1ULL << 32) + JS - 1) / JS);
     *handled = true;
 
     // one CTA per SM, up to 32 warps; narrow rows (few jobs per step) run two smaller CTAs per SM when they fit
@@ -296,14 +310,14 @@ slr_status slr_launch_fused_flow(slr_engine *e, int mode, const FusedParams &p_i
         const int w = atoi(ev);
         if (w >= 1 && w <= 32 / ctas) warps = w;
     }
-    void (*kern)(const FusedParams, int, int) = (mode == SLR_MODE_STRICT)      ? k_fused_flow<SLR_MODE_STRICT>
+    void (*kern)(const FusedParams, int, int, unsigned) = (mode == SLR_MODE_STRICT)      ? k_fused_flow<SLR_MODE_STRICT>
                                                 : (mode == SLR_MODE_CORRECTED) ? k_fused_flow<SLR_MODE_CORRECTED>
                                                                                : k_fused_flow<MODE_PHASE_INPUT>;
     SLR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = (long long)e->num_sms * ctas;
     if (grid > rows) grid = rows;
     if (grid < 1) return SLR_OK;
-    kern<<<(unsigned)grid, warps * 32, smem, e->stream>>>(p, n_d, n_q);
+    kern<<<(unsigned)grid, warps * 32, smem, e->stream>>>(p, n_d, n_q, js_magic);
     SLR_CHECK_LAUNCH(e);
     return SLR_OK;
 }
