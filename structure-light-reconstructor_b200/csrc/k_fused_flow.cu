@@ -18,7 +18,7 @@
 // fp64-bound instruction streams share the SM at all times.  A job waits only on per-context completion counters
 // (release/acquire in shared memory) of jobs that precede it in the global order, which makes the schedule
 // deadlock-free: decode(r) needs the clear after query(r-4) and the stage re-armed after decode(r-2); query(r)
-// needs decode(r).  The warp that completes the last decode job of a row re-arms that row's stage buffer with the
+// needs decode(r).  The warp whose decode job is the last to have read a row's stage buffer re-arms it with the
 // TMA copies of row r+2.
 #include <limits.h>
 #include <stdlib.h>
@@ -36,6 +36,26 @@ constexpr int FLOW_QPX = 2;        // left pixels per lane in one query job
 constexpr int FLOW_HEADER = 1024;  // mbarriers, counters, row descriptors
 
 using FlowTables = RowTablesT<int16_t>;
+
+#ifdef SLR_FLOW_TRACE   // debug build (csrc/Makefile TRACE=1): per-job clock stamps of CTA 0, read by profiles/flow_trace.py
+constexpr int TRACE_JOBS = 8192;
+__device__ long long g_flow_trace[TRACE_JOBS * 4];   // {type | row << 8 | warp << 40, t_draw, t_ready, t_end}
+#define FLOW_TRACE_DRAW() const long long trc_draw = clock64()
+#define FLOW_TRACE_READY() const long long trc_ready = clock64()
+#define FLOW_TRACE_END(type, row)                                                                               \
+    do {                                                                                                        \
+        if (blockIdx.x == 0 && lane == 0 && g < TRACE_JOBS) {                                                   \
+            g_flow_trace[4 * g + 0] = (long long)(type) | ((long long)(row) << 8) | ((long long)(tid >> 5) << 40); \
+            g_flow_trace[4 * g + 1] = trc_draw;                                                                 \
+            g_flow_trace[4 * g + 2] = trc_ready;                                                                \
+            g_flow_trace[4 * g + 3] = clock64();                                                                \
+        }                                                                                                       \
+    } while (0)
+#else
+#define FLOW_TRACE_DRAW() do { } while (0)
+#define FLOW_TRACE_READY() do { } while (0)
+#define FLOW_TRACE_END(type, row) do { } while (0)
+#endif
 
 __device__ __forceinline__ int ld_acquire_s32(const int *p)
 {
@@ -86,6 +106,7 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
     int *done_d = job_ctr + 1;                                             // [FLOW_CTX] decode jobs completed
     int *done_q = done_d + FLOW_CTX;                                       // [FLOW_CTX] query jobs completed
     int *cleared = done_q + FLOW_CTX;                                      // [FLOW_CTX] table clears completed
+    int *done_l = cleared + FLOW_CTX;                                      // [FLOW_CTX] decode jobs done reading the stage
     RowInfo *rowinfo = reinterpret_cast<RowInfo *>(smem + 128);            // [8] ring, indexed by row & 7
     const size_t stage_bytes = (MODE == MODE_PHASE_INPUT) ? (size_t)10 * W : (size_t)2 * N * W;
     unsigned char *stage0 = smem + FLOW_HEADER;
@@ -124,7 +145,7 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
         for (int k = tid; k < SLR_BTAB_SIZE; k += nthr) s_btab[k] = p.btab[k];
     }
     for (int c = 0; c < FLOW_CTX; c++) clear_tables(c, tid, nthr);
-    if (tid < 1 + 3 * FLOW_CTX) job_ctr[tid] = 0;
+    if (tid < 1 + 4 * FLOW_CTX) job_ctr[tid] = 0;
     if (tid == 0) {
         for (int s = 0; s < FLOW_STAGES; s++) slr::mbar_init(&bar_stage[s], 1);
         slr::mbar_fence_init();
@@ -155,6 +176,15 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
         const uint8_t *src = p.stack + ((size_t)b * 2 * N * p.H + i) * W;
         for (int v = lane; v < 2 * N; v += 32)   // plane v of this scan (cam-major, then image index)
             tma_load_1d_hint(stage + (size_t)v * W, src + (size_t)v * p.H * W, (uint32_t)W, bar, policy);
+        // pull the row that will follow into this stage buffer from HBM into L2 now: its bulk copies are issued the
+        // moment this row's decode jobs finish and must land within a step
+        if (r + FLOW_STAGES < R) {
+            int ni = i, nb = b + FLOW_STAGES;
+            while (nb >= p.batch) nb -= p.batch, ++ni;
+            const uint8_t *nsrc = p.stack + ((size_t)nb * 2 * N * p.H + ni) * W;
+            for (int v = lane; v < 2 * N; v += 32)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nsrc + (size_t)v * p.H * W), "r"((uint32_t)W) : "memory");
+        }
     };
     if (tid < 32) {
         issue_row(0);
@@ -173,6 +203,7 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
         if (lane == 0) g = atomicAdd(job_ctr, 1);
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= total_jobs) break;
+        FLOW_TRACE_DRAW();
         const int t = (int)__umulhi((unsigned)g, js_magic);   // g / JS (exact for g * JS < 2^32, checked by the launcher)
         const int s = g - t * JS;
 
@@ -184,6 +215,7 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
             // this row's tables were cleared by the last query job of row r - FLOW_CTX (first rows: by the prologue)
             wait_count(&cleared[c], u, lane);
             slr::mbar_wait(&bar_stage[r % FLOW_STAGES], (uint32_t)((r / FLOW_STAGES) & 1));
+            FLOW_TRACE_READY();
             float *s_pl;
             const FlowTables tab = tables_of(c, s_pl);
             const unsigned char *stage = stage0 + (size_t)(r % FLOW_STAGES) * stage_bytes;
@@ -195,6 +227,14 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
                 float ph[4];
                 bool ok[4];
                 load_phases<MODE, 4>(stage, W, N, x0, right, p, s_ptab, s_btab, ph, ok);
+                // this job has read its bytes of the stage buffer (the release orders the loads before the count).  The
+                // warp that counts the last reader streams row r + 2 into the buffer: a third of a decode job earlier
+                // than its completion, which is the slack the bulk copies need to land before row r + 2 is drawn.
+                __syncwarp();
+                int last_reader = 0;
+                if (lane == 0) last_reader = add_acq_rel_s32(&done_l[c], 1) + 1 == (u + 1) * n_d;
+                last_reader = __shfl_sync(0xffffffffu, last_reader, 0);
+                if (last_reader && r + FLOW_STAGES < R) issue_row(r + FLOW_STAGES);
                 // the right lane hands its upper two phases to the left lane: every lane decodes 4 pixels and files 2
                 const float n2 = __shfl_xor_sync(0xffffffffu, ph[2], 1), n3 = __shfl_xor_sync(0xffffffffu, ph[3], 1);
                 const unsigned okb = __shfl_xor_sync(0xffffffffu, (ok[2] ? 1u : 0u) | (ok[3] ? 2u : 0u), 1);
@@ -207,17 +247,18 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
                                     ok[3] ? ph[3] : slr::qnan());
             }
             __syncwarp();
-            int last = 0;
-            if (lane == 0) last = add_acq_rel_s32(&done_d[c], 1) + 1 == (u + 1) * n_d;
-            last = __shfl_sync(0xffffffffu, last, 0);
-            // the stage buffer of row r is consumed: stream row r + 2 into it
-            if (last && r + FLOW_STAGES < R) issue_row(r + FLOW_STAGES);
+            if (lane == 0) add_acq_rel_s32(&done_d[c], 1);
+            FLOW_TRACE_END(0, r);
         } else {
             // ================= query + emit job (FLOW_QPX * 32 left pixels) of row r = t - 1 - FLOW_LAG =================
+            // (measured with the trace build, profiles/flow_trace.py: jobs wait 5 % of their time in this order; drawing
+            // half of a row's queries half a step earlier made the ring's slack even on paper and the kernel 5 % slower)
             const int r = t - 1 - FLOW_LAG;
+            const int qidx = s - n_d;
             if (r < 0 || r >= R) continue;
             const int c = r & (FLOW_CTX - 1), u = r / FLOW_CTX;
             wait_count(&done_d[c], (u + 1) * n_d, lane);
+            FLOW_TRACE_READY();
             const RowInfo ri = rowinfo[r & 7];
             float *s_pl;
             const FlowTables tab = tables_of(c, s_pl);
@@ -225,7 +266,7 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
             float ulx[FLOW_QPX], uly[FLOW_QPX], v[FLOW_QPX];
 #pragma unroll
             for (int q = 0; q < FLOW_QPX; q++) {
-                j[q] = ((s - n_d) * FLOW_QPX + q) * 32 + lane;
+                j[q] = (qidx * FLOW_QPX + q) * 32 + lane;
                 const bool inside = j[q] < W;
                 // undistortPoints maps of the left pixel (L2-resident, coalesced): in flight during the table walk
                 ulx[q] = inside ? __ldg(p.lx + ri.map_px + j[q]) : 0.0f;
@@ -271,6 +312,7 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
                 __syncwarp();
                 if (lane == 0) add_acq_rel_s32(&cleared[c], 1);
             }
+            FLOW_TRACE_END(last ? 2 : 1, r);
         }
     }
     if (p.n_points) {
@@ -319,5 +361,18 @@ slr_status slr_launch_fused_flow(slr_engine *e, int mode, const FusedParams &p_i
     if (grid < 1) return SLR_OK;
     kern<<<(unsigned)grid, warps * 32, smem, e->stream>>>(p, n_d, n_q, js_magic);
     SLR_CHECK_LAUNCH(e);
+#ifdef SLR_FLOW_TRACE
+    if (const char *path = getenv("SLR_FLOW_TRACE_OUT")) {
+        static long long h[TRACE_JOBS * 4];
+        SLR_CHECK_CUDA(cudaStreamSynchronize(e->stream));
+        SLR_CHECK_CUDA(cudaMemcpyFromSymbol(h, g_flow_trace, sizeof(h)));
+        if (FILE *f = fopen(path, "wb")) {
+            int hdr[4] = {TRACE_JOBS, n_d, n_q, warps};
+            fwrite(hdr, sizeof(hdr), 1, f);
+            fwrite(h, sizeof(h), 1, f);
+            fclose(f);
+        }
+    }
+#endif
     return SLR_OK;
 }
