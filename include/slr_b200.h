@@ -203,6 +203,29 @@ SLR_API slr_status slr_nccl_unique_id(void *id128);
 SLR_API slr_status slr_nccl_comm_create(slr_engine *e, void **comm, int world, int rank, const void *id128);
 SLR_API slr_status slr_nccl_comm_destroy(void *comm);
 
+/* The same assembly without a collective call (preferred): every rank maps the assembled cloud buffers of all ranks
+ * (CUDA IPC over NVLink / NVSwitch peer access) and registers them as gather targets; slr_run_mf / slr_run_ge then
+ * store every output row into this rank's block of EVERY target straight from the kernel's registers, so the
+ * transfer overlaps the kernel that produces the data (k_fused_flow's epilogue; other routes copy the finished block
+ * to the peers on the engine's stream).  One process per GPU:
+ *   slr_peer_alloc   cudaMalloc + IPC handle (64 bytes) for the buffers this rank owns
+ *   slr_peer_open    map another rank's buffer from its handle (handles travel by any means, e.g. torch.distributed)
+ *   slr_set_gather_targets  d_xyz_all[t] = float [scans][H][W][3], d_valid_all[t] = uint8 [scans][H][W] of target t;
+ *                    target 0 MUST be this rank's own buffer; first_scan = index of this rank's first scan in the
+ *                    assembled cloud.  With targets set, slr_run_mf / slr_run_ge ignore their d_xyz / d_valid arguments.
+ *                    n_targets = 0 switches back.  After the call on every rank completes and the ranks have
+ *                    synchronised (any barrier), every target holds the whole cloud.
+ * Row bands: an engine of height H_band with slr_set_row_offset(first_row) treats its rows as rows first_row .. of
+ * the full image (undistortPoints maps, the Q reprojection of the Gray-EPI path), so ONE scan can be split over N
+ * GPUs by horizontal bands (each rank gets the same rows of both cameras; no halo) and assembled with the targets. */
+SLR_API slr_status slr_peer_alloc(slr_engine *e, size_t bytes, void **d_ptr, void *ipc_handle64);
+SLR_API slr_status slr_peer_open(slr_engine *e, const void *ipc_handle64, void **d_ptr);
+SLR_API slr_status slr_peer_close(slr_engine *e, void *d_ptr);
+SLR_API slr_status slr_peer_free(slr_engine *e, void *d_ptr);
+SLR_API slr_status slr_set_gather_targets(slr_engine *e, int n_targets, float *const *d_xyz_all,
+                                          uint8_t *const *d_valid_all, long long first_scan);
+SLR_API slr_status slr_set_row_offset(slr_engine *e, int first_row);
+
 /* ---- mesh indexing ---------------------------------------------------------- */
 /* The index passes of MeshCreator::exportPlyMesh / exportObjMesh, Duke/meshcreator.cpp:16-65, 67-166, on a
  * PointCloudImage stored as the reference stores it (Duke/pointcloudimage.cpp:3-13): d_sum = float [h][w][3]
@@ -221,6 +244,14 @@ SLR_API slr_status slr_mesh_index(slr_engine *e, const float *d_sum, const uint8
 SLR_API slr_status slr_mesh_index_host(slr_engine *e, const float *h_sum, const uint8_t *h_count, int w, int h,
                                        int first_vertex, float *h_vertices, int32_t *h_vertex_src, int32_t *h_faces,
                                        unsigned long long *h_counts);
+/* Utilities::autoContrast (Duke/utilities.cpp:340-355) as Reconstruct::loadCamImgs applies it to every loaded image
+ * when the "auto contrast" setting is on (Duke/reconstruct.cpp:182-183): per image, min/max stretch with OpenCV's
+ * saturating 8-bit arithmetic, in place.  d_images = n_images images of width*height bytes.  (The reference indexes
+ * channels 1 and 2 of a one-channel image — undefined behaviour; channel 0's arithmetic is what is restated.) */
+SLR_API slr_status slr_auto_contrast(slr_engine *e, uint8_t *d_images, int n_images);
+/* The host-buffer pipelines (slr_run_ge_host, slr_run_gray_host, slr_run_mf_host) stretch every image after upload
+ * (and rectification) when this is on: Reconstruct::getParameters' autocontrast flag. */
+SLR_API slr_status slr_set_auto_contrast(slr_engine *e, int on);
 SLR_API slr_status slr_host_alloc(void **out, size_t bytes); /* pinned */
 SLR_API slr_status slr_host_free(void *p);
 

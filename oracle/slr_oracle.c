@@ -925,6 +925,36 @@ void orc_remap_linear(const uint8_t *src, int W, int H, const int16_t *map1, con
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* Utilities::autoContrast, Duke/utilities.cpp:340-355, channel 0                                */
+/* ------------------------------------------------------------------------------------------ */
+/* cv::saturate_cast<uchar>(cvRound(x)): lrint (round half to even), then clamp to 0..255 */
+static uint8_t sat_round_u8(float x)
+{
+    long r = lrintf(x);
+    return (uint8_t)(r < 0 ? 0 : r > 255 ? 255 : r);
+}
+
+void orc_auto_contrast(uint8_t *img, int W, int H)
+{
+    const size_t P = (size_t)W * H;
+    int mn = 255, mx = 0;                                  /* cv::minMaxIdx, :346 */
+    for (size_t k = 0; k < P; k++) {
+        if (img[k] < mn) mn = img[k];
+        if (img[k] > mx) mx = img[k];
+    }
+    if (P == 0) return;
+    const double min = (double)mn + 255 * 0.05;            /* :347 */
+    const double a = 255 / ((double)mx - min);             /* :349 */
+    /* bgr[i] -= min (:350): cv::subtract with a non-integer scalar computes in CV_32F and saturates to 8 bits;
+     * bgr[i] *= a (:351): Mat::operator*= -> convertTo(alpha = a) -> cvtScale_<uchar, uchar, float> */
+    const float minf = (float)min, af = (float)a;
+    for (size_t k = 0; k < P; k++) {
+        const uint8_t t = sat_round_u8((float)img[k] - minf);
+        img[k] = sat_round_u8((float)t * af);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* whole MF pipeline for one scan (Duke/mfreconstruct.cpp:160-187 minus image IO)               */
 /* ------------------------------------------------------------------------------------------ */
 

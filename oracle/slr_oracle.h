@@ -130,6 +130,11 @@ void orc_pointcloud_add(int w, int h, const int32_t *iw, const int32_t *jh, cons
 /* Duke/stereorect.cpp:26-34: cv::remap(INTER_LINEAR) with CV_16SC2 maps (map1 = [H][W][2] int16, map2 = [H][W] u16) */
 void orc_remap_linear(const uint8_t *src, int W, int H, const int16_t *map1, const uint16_t *map2, uint8_t *dst);
 
+/* Duke/utilities.cpp:340-355 (Utilities::autoContrast) on one CV_8U image, in place, as Reconstruct::loadCamImgs
+ * calls it (Duke/reconstruct.cpp:182-183).  Channel 0 only: the reference indexes bgr[1], bgr[2] of a one-channel
+ * split, which is undefined behaviour, so this function has NO reference pin ("parity unpinned", oracle-only). */
+void orc_auto_contrast(uint8_t *img, int W, int H);
+
 /* ---- whole-pipeline conveniences used by bench.py's CPU legs ------------------------------ */
 /* MF pipeline on one scan: stacks = [2][14][H][W].  Returns points; *n_pixels unused. */
 int64_t orc_run_mf(const uint8_t *stacks, int W, int H, int F, int S, int black_thr, int mode,

@@ -59,7 +59,8 @@ EXPORTS = [
     "slr_version", "slr_gray_num_bits", "slr_gray_num_imgs", "slr_generate_gray_patterns",
     "slr_generate_mf_patterns", "slr_mf_decode", "slr_gray_decode", "slr_match_triangulate_phase",
     "slr_match_triangulate_code", "slr_bucket_triangulate", "slr_run_mf", "slr_run_ge", "slr_run_mf_host",
-    "slr_run_ge_host", "slr_host_alloc", "slr_host_free", "slr_synth_mf", "slr_synth_mf_fs", "slr_synth_gray",
+    "slr_run_ge_host", "slr_host_alloc", "slr_host_free", "slr_synth_mf", "slr_synth_mf_fs", "slr_auto_contrast", "slr_set_auto_contrast", "slr_peer_alloc", "slr_peer_open", "slr_peer_close",
+    "slr_peer_free", "slr_set_gather_targets", "slr_set_row_offset", "slr_synth_gray",
     "slr_kernel_launches", "slr_mesh_index", "slr_mesh_index_host", "slr_allgather", "slr_nccl_unique_id",
     "slr_nccl_comm_create", "slr_nccl_comm_destroy", "slr_set_rectify_maps", "slr_rectify_stack", "slr_set_host_input_raw", "slr_run_gray_host",
 ]
@@ -101,6 +102,8 @@ def capi():
     lib.slr_synth_mf.argtypes = [vp, vp, i32, i32, u32, i32, C.c_float]
     lib.slr_synth_mf_fs.argtypes = [vp, vp, i32, i32, i32, i32, u32, i32, C.c_float]
     lib.slr_synth_gray.argtypes = [vp, vp, i32, i32, u32, i32, C.c_float]
+    lib.slr_auto_contrast.argtypes = [vp, vp, i32]
+    lib.slr_set_auto_contrast.argtypes = [vp, i32]
     lib.slr_set_rectify_maps.argtypes = [vp, vp, vp]
     lib.slr_rectify_stack.argtypes = [vp, vp, i32, i32, vp]
     lib.slr_set_host_input_raw.argtypes = [vp, i32]
@@ -111,6 +114,12 @@ def capi():
     lib.slr_nccl_unique_id.argtypes = [vp]
     lib.slr_nccl_comm_create.argtypes = [vp, C.POINTER(vp), i32, i32, vp]
     lib.slr_nccl_comm_destroy.argtypes = [vp]
+    lib.slr_peer_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp), vp]
+    lib.slr_peer_open.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.slr_peer_close.argtypes = [vp, vp]
+    lib.slr_peer_free.argtypes = [vp, vp]
+    lib.slr_set_gather_targets.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.c_longlong]
+    lib.slr_set_row_offset.argtypes = [vp, i32]
     lib.slr_kernel_launches.argtypes = [vp]
     lib.slr_kernel_launches.restype = C.c_ulonglong
     _lib = lib
@@ -228,6 +237,16 @@ class Engine:
         self._bind_stream()
         _check(self.lib.slr_rectify_stack(self.h, self._p(raw), B, N, self._p(out)), "slr_rectify_stack")
         return out
+
+    def auto_contrast(self, images):
+        """Utilities::autoContrast on every [H, W] image of a uint8 device tensor [..., H, W], in place."""
+        assert images.is_contiguous() and tuple(images.shape[-2:]) == (self.H, self.W)
+        self._bind_stream()
+        _check(self.lib.slr_auto_contrast(self.h, self._p(images), images.numel() // (self.H * self.W)), "slr_auto_contrast")
+        return images
+
+    def set_auto_contrast(self, on: bool):
+        _check(self.lib.slr_set_auto_contrast(self.h, int(on)), "slr_set_auto_contrast")
 
     def set_host_input_raw(self, raw: bool):
         _check(self.lib.slr_set_host_input_raw(self.h, int(raw)), "slr_set_host_input_raw")
@@ -365,6 +384,36 @@ class Engine:
         self._bind_stream()
         _check(self.lib.slr_allgather(self.h, comm, world, rank, scans_per_rank, self._p(xyz_all), self._p(valid_all)),
                "slr_allgather")
+
+    # ---- multi-GPU assembly by peer stores (CUDA IPC mappings over NVLink; see slr_b200.parallel.PeerAssembly) ----
+    def peer_alloc(self, nbytes: int):
+        """-> (device pointer, 64-byte IPC handle) of a buffer other ranks can map"""
+        ptr, handle = C.c_void_p(0), C.create_string_buffer(64)
+        _check(self.lib.slr_peer_alloc(self.h, nbytes, C.byref(ptr), handle), "slr_peer_alloc")
+        return ptr.value, handle.raw
+
+    def peer_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p(0)
+        _check(self.lib.slr_peer_open(self.h, C.create_string_buffer(handle, 64), C.byref(ptr)), "slr_peer_open")
+        return ptr.value
+
+    def peer_close(self, ptr: int):
+        _check(self.lib.slr_peer_close(self.h, C.c_void_p(ptr)), "slr_peer_close")
+
+    def peer_free(self, ptr: int):
+        _check(self.lib.slr_peer_free(self.h, C.c_void_p(ptr)), "slr_peer_free")
+
+    def set_gather_targets(self, xyz_ptrs, valid_ptrs, first_scan: int = 0):
+        """Device pointers of every rank's assembled cloud, this rank's own first; [] switches the targets off."""
+        n = len(xyz_ptrs)
+        assert n == len(valid_ptrs)
+        xa = (C.c_void_p * max(n, 1))(*xyz_ptrs)
+        va = (C.c_void_p * max(n, 1))(*valid_ptrs)
+        _check(self.lib.slr_set_gather_targets(self.h, n, xa, va, first_scan), "slr_set_gather_targets")
+
+    def set_row_offset(self, first_row: int):
+        self._bind_stream()
+        _check(self.lib.slr_set_row_offset(self.h, first_row), "slr_set_row_offset")
 
     def mesh_index(self, sums, counts, first_vertex=0):
         """slr_mesh_index on device tensors sums [h,w,3] f32 / counts [h,w] u8 -> (vertices [nv,3], vertex_src [nv],

@@ -161,7 +161,7 @@ k3b_code_match(const K3bParams p)
             float X = slr::qnan(), Y = slr::qnan(), Z = slr::qnan();
             uint8_t colr = 0;
             if (k >= 0) {
-                slr::reproject_q(p.calib, (double)j, (double)i, (double)(j - k), X, Y, Z);  // :570
+                slr::reproject_q(p.calib, (double)j, (double)(i + p.calib.row0), (double)(j - k), X, Y, Z);  // :570
                 if (p.color) {
                     const size_t vL = (size_t)(b * 2 + 0) * p.white_stride + (size_t)i * W;
                     const size_t vR = (size_t)(b * 2 + 1) * p.white_stride + (size_t)i * W;

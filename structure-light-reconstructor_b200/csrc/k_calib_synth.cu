@@ -34,15 +34,15 @@ __device__ __forceinline__ void undistort_point(float px, float py, const slr_ca
     oy = __double2float_rn(__dadd_rn((double)__double2float_rn(__dmul_rn(y, fy)), cy));
 }
 
-__global__ void k_undistort_maps(slr_camera camL, slr_camera camR, int W, int H, float *__restrict__ lx,
+__global__ void k_undistort_maps(slr_camera camL, slr_camera camR, int W, int H, int row0, float *__restrict__ lx,
                                  float *__restrict__ ly, float *__restrict__ rx)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     if (j >= W || i >= H) return;
     float ax, ay, bx, by;
-    undistort_point((float)j, (float)i, camL, ax, ay);
-    undistort_point((float)j, (float)i, camR, bx, by);
+    undistort_point((float)j, (float)(i + row0), camL, ax, ay);   // row0: first image row of a row band
+    undistort_point((float)j, (float)(i + row0), camR, bx, by);
     const size_t o = (size_t)i * W + j;
     lx[o] = ax;
     ly[o] = ay;
@@ -185,7 +185,7 @@ __global__ void k_synth_gray(uint8_t *__restrict__ stack, int W, int H, int batc
 slr_status slr_launch_undistort_maps(slr_engine *e)
 {
     dim3 block(128), grid((e->W + 127) / 128, e->H);
-    k_undistort_maps<<<grid, block, 0, e->stream>>>(e->cams[0], e->cams[1], e->W, e->H, e->d_undist_lx,
+    k_undistort_maps<<<grid, block, 0, e->stream>>>(e->cams[0], e->cams[1], e->W, e->H, e->calib.row0, e->d_undist_lx,
                                                     e->d_undist_ly, e->d_undist_rx);
     SLR_CHECK_LAUNCH(e);
     return SLR_OK;

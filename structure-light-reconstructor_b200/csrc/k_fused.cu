@@ -370,6 +370,21 @@ static slr_status launch_fused(slr_engine *e, int mode, const uint8_t *d_stack, 
     }
     p.xyz = d_xyz;
     p.valid = d_valid;
+    p.n_t = 1;
+    p.xyz_t[0] = d_xyz;
+    p.valid_t[0] = d_valid;
+    {
+        // writing this engine's block of its own assembled cloud with peers registered: the dataflow kernel stores
+        // every row to the same block on all of them (an all-gather folded into the epilogue)
+        const size_t off = (size_t)e->target_first_scan * e->W * e->H;
+        if (e->n_targets > 1 && mode != MODE_PHASE_INPUT && d_xyz == e->xyz_t[0] + off * 3 && d_valid == e->valid_t[0] + off) {
+            p.n_t = e->n_targets;
+            for (int t = 1; t < e->n_targets; t++) {
+                p.xyz_t[t] = e->xyz_t[t] + off * 3;
+                p.valid_t[t] = e->valid_t[t] + off;
+            }
+        }
+    }
     p.match_k = d_match_k;
     p.n_points = d_n_points;
     p.calib = e->calib;
@@ -377,6 +392,7 @@ static slr_status launch_fused(slr_engine *e, int mode, const uint8_t *d_stack, 
     {
         bool flow = false;
         const slr_status st = slr_launch_fused_flow(e, mode, p, &flow);
+        if (st == SLR_OK && flow && p.n_t > 1) e->targets_written = true;
         if (st != SLR_OK || flow) return st;
     }
 #endif

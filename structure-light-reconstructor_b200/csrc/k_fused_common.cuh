@@ -27,6 +27,11 @@ struct FusedParams {
     float cs[16], sn[16];  // corrected: cos/sin(2 pi s / S)
     float *xyz;
     uint8_t *valid;
+    // k_fused_flow: the clouds every output row is stored to — [0] = xyz / valid above, [1..] = the same block of the
+    // assembled cloud on every peer GPU (NVLink peer mappings, slr_set_gather_targets)
+    int n_t;
+    float *xyz_t[SLR_MAX_TARGETS];
+    uint8_t *valid_t[SLR_MAX_TARGETS];
     int32_t *match_k;
     unsigned long long *n_points;
     slr_calib_dev calib;

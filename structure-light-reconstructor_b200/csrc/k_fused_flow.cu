@@ -295,11 +295,17 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
                 n_local += hit ? 1u : 0u;
                 if (j[q] < W) {
                     const size_t o = (size_t)ri.out_px + j[q];
-                    float *dst = p.xyz + o * 3;
-                    dst[0] = hit ? X[q] : slr::qnan();
-                    dst[1] = hit ? Y[q] : slr::qnan();
-                    dst[2] = hit ? Z[q] : slr::qnan();
-                    p.valid[o] = hit ? 1 : 0;
+                    const float ox = hit ? X[q] : slr::qnan(), oy = hit ? Y[q] : slr::qnan(), oz = hit ? Z[q] : slr::qnan();
+                    // target 0 is this GPU's cloud; further targets are the peers' assembled clouds (NVLink stores
+                    // straight from registers: the all-gather overlaps the kernel that produces the data)
+#pragma unroll 1
+                    for (int tg = 0; tg < p.n_t; tg++) {
+                        float *dst = p.xyz_t[tg] + o * 3;
+                        dst[0] = ox;
+                        dst[1] = oy;
+                        dst[2] = oz;
+                        p.valid_t[tg][o] = hit ? 1 : 0;
+                    }
                     if (p.match_k) p.match_k[o] = hit ? best[q] : -1;
                 }
             }

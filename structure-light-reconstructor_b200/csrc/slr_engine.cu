@@ -68,6 +68,8 @@ static void free_engine(slr_engine *e)
     }
     cudaFree(e->d_counter);
     cudaFree(e->d_bucket_scratch);
+    cudaFree(e->d_minmax);
+    for (void *g : e->d_gray) cudaFree(g);
     cudaFree(e->d_map1);
     cudaFree(e->d_map2);
     cudaFree(e->d_stage_rect[0]);
@@ -100,6 +102,7 @@ extern "C" slr_status slr_create(slr_engine **out, int device, int width, int he
         return SLR_ERR_NOMEM;
     }
     e->device = device;
+    e->calib.row0 = 0;
     e->W = width;
     e->H = height;
     e->max_batch = max_batch;
@@ -278,6 +281,100 @@ extern "C" slr_status slr_generate_mf_patterns(uint8_t *h_out, int projW, int pr
 }
 
 // ------------------------------------------------------------------------------------------------
+// multi-GPU assembly over NVLink: peer-mapped cloud buffers, gather targets, row bands
+// ------------------------------------------------------------------------------------------------
+extern "C" slr_status slr_set_row_offset(slr_engine *e, int first_row)
+{
+    SLR_REQUIRE(e != nullptr && first_row >= 0, "slr_set_row_offset: bad argument");
+    SLR_CHECK_CUDA(cudaSetDevice(e->device));
+    if (e->calib.row0 == first_row) return SLR_OK;
+    e->calib.row0 = first_row;
+    if (!e->calib_set) return SLR_OK;
+    e->calib_version++;                     // the undistort maps (and a padded child's) depend on the absolute row
+    return slr_launch_undistort_maps(e);
+}
+
+extern "C" slr_status slr_peer_alloc(slr_engine *e, size_t bytes, void **d_ptr, void *ipc_handle64)
+{
+    SLR_REQUIRE(e && d_ptr && ipc_handle64 && bytes > 0, "slr_peer_alloc: bad argument");
+    SLR_CHECK_CUDA(cudaSetDevice(e->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    SLR_CHECK_CUDA(cudaMalloc(d_ptr, bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t err = cudaIpcGetMemHandle(&h, *d_ptr);
+    if (err != cudaSuccess) {
+        cudaFree(*d_ptr);
+        *d_ptr = nullptr;
+        slr_set_error("slr_peer_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(err));
+        return SLR_ERR_CUDA;
+    }
+    memcpy(ipc_handle64, &h, 64);
+    return SLR_OK;
+}
+
+extern "C" slr_status slr_peer_open(slr_engine *e, const void *ipc_handle64, void **d_ptr)
+{
+    SLR_REQUIRE(e && d_ptr && ipc_handle64, "slr_peer_open: bad argument");
+    SLR_CHECK_CUDA(cudaSetDevice(e->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle64, 64);
+    SLR_CHECK_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SLR_OK;
+}
+
+extern "C" slr_status slr_peer_close(slr_engine *e, void *d_ptr)
+{
+    SLR_REQUIRE(e != nullptr, "slr_peer_close: engine is NULL");
+    SLR_CHECK_CUDA(cudaSetDevice(e->device));
+    if (d_ptr) SLR_CHECK_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return SLR_OK;
+}
+
+extern "C" slr_status slr_peer_free(slr_engine *e, void *d_ptr)
+{
+    SLR_REQUIRE(e != nullptr, "slr_peer_free: engine is NULL");
+    SLR_CHECK_CUDA(cudaSetDevice(e->device));
+    if (d_ptr) SLR_CHECK_CUDA(cudaFree(d_ptr));
+    return SLR_OK;
+}
+
+extern "C" slr_status slr_set_gather_targets(slr_engine *e, int n_targets, float *const *d_xyz_all,
+                                             uint8_t *const *d_valid_all, long long first_scan)
+{
+    SLR_REQUIRE(e != nullptr && n_targets >= 0 && n_targets <= SLR_MAX_TARGETS && first_scan >= 0,
+                "slr_set_gather_targets: bad argument (at most %d targets)", SLR_MAX_TARGETS);
+    SLR_REQUIRE(n_targets == 0 || (d_xyz_all && d_valid_all), "slr_set_gather_targets: NULL target arrays");
+    for (int t = 0; t < n_targets; t++) {
+        SLR_REQUIRE(d_xyz_all[t] && d_valid_all[t], "slr_set_gather_targets: target %d is NULL", t);
+        e->xyz_t[t] = d_xyz_all[t];
+        e->valid_t[t] = d_valid_all[t];
+    }
+    e->n_targets = n_targets;
+    e->target_first_scan = first_scan;
+    return SLR_OK;
+}
+
+// this engine's block of its own assembled cloud (target 0): where the kernels write when targets are set
+static void slr_own_target_block(slr_engine *e, float **d_xyz, uint8_t **d_valid)
+{
+    const size_t off = (size_t)e->target_first_scan * e->W * e->H;
+    *d_xyz = e->xyz_t[0] + off * 3;
+    *d_valid = e->valid_t[0] + off;
+}
+
+// routes whose kernels do not store to the peers themselves: copy the finished block over NVLink (stream ordered)
+static slr_status slr_copy_to_targets(slr_engine *e, int batch)
+{
+    if (e->n_targets <= 1 || e->targets_written) return SLR_OK;
+    const size_t off = (size_t)e->target_first_scan * e->W * e->H, px = (size_t)batch * e->W * e->H;
+    for (int t = 1; t < e->n_targets; t++) {
+        SLR_CHECK_CUDA(cudaMemcpyAsync(e->xyz_t[t] + off * 3, e->xyz_t[0] + off * 3, px * 3 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+        SLR_CHECK_CUDA(cudaMemcpyAsync(e->valid_t[t] + off, e->valid_t[0] + off, px, cudaMemcpyDeviceToDevice, e->stream));
+    }
+    return SLR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // device-pointer entry points
 // ------------------------------------------------------------------------------------------------
 #define SLR_ENTER(e)                                                     \
@@ -354,6 +451,8 @@ extern "C" slr_status slr_bucket_triangulate(slr_engine *e, const int32_t *d_col
         slr_set_error("slr_bucket_triangulate: call slr_set_calib first");
         return SLR_ERR_STATE;
     }
+    SLR_REQUIRE(e->calib.row0 == 0, "slr_bucket_triangulate: the Gray-only path does not partition by row bands "
+                                    "(projector-cell buckets span the image); row offset must be 0");
     return slr_launch_bucket_triangulate(e, d_col, d_row, d_mask, batch, scan_w, scan_h, d_sum, d_cnt, d_n_cells);
 }
 
@@ -362,12 +461,15 @@ extern "C" slr_status slr_run_mf(slr_engine *e, const uint8_t *d_stack, int batc
                                  unsigned long long *d_n_points)
 {
     SLR_ENTER(e);
-    SLR_REQUIRE(d_stack && d_xyz && d_valid && batch > 0, "slr_run_mf: bad argument");
+    SLR_REQUIRE(d_stack && batch > 0 && (e->n_targets > 0 || (d_xyz && d_valid)), "slr_run_mf: bad argument");
     if (!e->calib_set) {
         slr_set_error("slr_run_mf: call slr_set_calib first");
         return SLR_ERR_STATE;
     }
-    return slr_launch_fused_mf(e, d_stack, batch, F, S, black_thr, mode, d_xyz, d_valid, d_match_k, d_n_points);
+    if (e->n_targets > 0) slr_own_target_block(e, &d_xyz, &d_valid);
+    e->targets_written = false;
+    const slr_status st = slr_launch_fused_mf(e, d_stack, batch, F, S, black_thr, mode, d_xyz, d_valid, d_match_k, d_n_points);
+    return st == SLR_OK ? slr_copy_to_targets(e, batch) : st;
 }
 
 extern "C" slr_status slr_run_ge(slr_engine *e, const uint8_t *d_stack, int batch, int nbits_col, int black_thr,
@@ -375,14 +477,17 @@ extern "C" slr_status slr_run_ge(slr_engine *e, const uint8_t *d_stack, int batc
                                  int32_t *d_match_k, uint8_t *d_color, unsigned long long *d_n_points)
 {
     SLR_ENTER(e);
-    SLR_REQUIRE(d_stack && d_xyz && d_valid && batch > 0, "slr_run_ge: bad argument");
+    SLR_REQUIRE(d_stack && batch > 0 && (e->n_targets > 0 || (d_xyz && d_valid)), "slr_run_ge: bad argument");
     SLR_REQUIRE(!have_color || d_color, "slr_run_ge: have_color set but d_color is NULL");
     if (!e->calib_set) {
         slr_set_error("slr_run_ge: call slr_set_calib first");
         return SLR_ERR_STATE;
     }
-    return slr_launch_fused_ge(e, d_stack, batch, nbits_col, black_thr, white_thr, scan_w, have_color, d_xyz,
-                               d_valid, d_match_k, d_color, d_n_points);
+    if (e->n_targets > 0) slr_own_target_block(e, &d_xyz, &d_valid);
+    e->targets_written = false;
+    const slr_status st = slr_launch_fused_ge(e, d_stack, batch, nbits_col, black_thr, white_thr, scan_w, have_color, d_xyz,
+                                              d_valid, d_match_k, d_color, d_n_points);
+    return st == SLR_OK ? slr_copy_to_targets(e, batch) : st;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -415,6 +520,7 @@ slr_status slr_padded_run(slr_engine *e, int kind, const void *d_in0, const uint
     slr_engine *c = e->child;
     c->stream = e->stream;
     if (c->calib_version == 0 || e->child_calib_version != e->calib_version) {
+        c->calib.row0 = e->calib.row0;
         slr_status st = slr_set_calib(c, e->cams, e->calib.Q, e->calib.has_rigid ? e->calib.rigid : nullptr);
         if (st != SLR_OK) return st;
         e->child_calib_version = e->calib_version;
@@ -613,6 +719,20 @@ extern "C" slr_status slr_set_host_input_raw(slr_engine *e, int raw)
     return SLR_OK;
 }
 
+extern "C" slr_status slr_auto_contrast(slr_engine *e, uint8_t *d_images, int n_images)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(d_images && n_images > 0, "slr_auto_contrast: bad argument");
+    return slr_launch_auto_contrast(e, d_images, n_images);
+}
+
+extern "C" slr_status slr_set_auto_contrast(slr_engine *e, int on)
+{
+    SLR_ENTER(e);
+    e->auto_contrast = on != 0;
+    return SLR_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host-buffer pipelines
 // ------------------------------------------------------------------------------------------------
@@ -658,9 +778,9 @@ static slr_status ensure_stage(slr_engine *e, size_t in_bytes_per_scan, bool wan
 // Scan-by-scan software pipeline over three streams: H2D of scan s+1 overlaps the kernels of scan s
 // and the D2H of scan s-1 (PCIe is full duplex; the kernels take microseconds, the copies ~1 ms).
 template <typename LaunchFn>
-static slr_status host_pipeline(slr_engine *e, const uint8_t *h_stack, size_t in_bytes, int batch, bool color,
-                                float *h_xyz, uint8_t *h_valid, int32_t *h_match_k, uint8_t *h_color,
-                                unsigned long long *h_n_points, LaunchFn launch)
+static slr_status host_pipeline_body(slr_engine *e, const uint8_t *h_stack, size_t in_bytes, int batch, bool color,
+                                     float *h_xyz, uint8_t *h_valid, int32_t *h_match_k, uint8_t *h_color,
+                                     unsigned long long *h_n_points, LaunchFn launch)
 {
     const size_t P = (size_t)e->W * e->H;
     slr_status st = ensure_stage(e, in_bytes, color);
@@ -682,6 +802,10 @@ static slr_status host_pipeline(slr_engine *e, const uint8_t *h_stack, size_t in
             st = slr_launch_rectify(e, d_in, 1, (int)(in_bytes / (2 * P)), e->d_stage_rect[b]);
             if (st != SLR_OK) return st;
             d_in = e->d_stage_rect[b];
+        }
+        if (e->auto_contrast) {   // Utilities::autoContrast on every loaded image (Duke/reconstruct.cpp:182-183), in place
+            st = slr_launch_auto_contrast(e, d_in, (int)(in_bytes / P));
+            if (st != SLR_OK) return st;
         }
         st = launch(d_in, e->d_stage_xyz[b], e->d_stage_valid[b], e->d_stage_k[b], e->d_stage_color[b]);
         if (st != SLR_OK) return st;
@@ -705,6 +829,27 @@ static slr_status host_pipeline(slr_engine *e, const uint8_t *h_stack, size_t in
     SLR_CHECK_CUDA(cudaStreamSynchronize(e->copy_in));
     if (h_n_points) *h_n_points = *e->h_counter;
     return SLR_OK;
+}
+
+// On an error in the middle of a batch, asynchronous copies from h_stack / into the caller's output buffers may still
+// be in flight: drain all three streams before the caller gets the (first) error back and frees or reuses them.
+template <typename LaunchFn>
+static slr_status host_pipeline(slr_engine *e, const uint8_t *h_stack, size_t in_bytes, int batch, bool color,
+                                float *h_xyz, uint8_t *h_valid, int32_t *h_match_k, uint8_t *h_color,
+                                unsigned long long *h_n_points, LaunchFn launch)
+{
+    const slr_status st = host_pipeline_body(e, h_stack, in_bytes, batch, color, h_xyz, h_valid, h_match_k, h_color,
+                                             h_n_points, launch);
+    if (st != SLR_OK) {
+        char first[512];
+        snprintf(first, sizeof(first), "%s", slr_last_error());
+        cudaStreamSynchronize(e->copy_in);
+        cudaStreamSynchronize(e->stream);
+        cudaStreamSynchronize(e->copy_out);
+        cudaGetLastError();
+        slr_set_error("%s", first);
+    }
+    return st;
 }
 
 extern "C" slr_status slr_run_mf_host(slr_engine *e, const uint8_t *h_stack, int batch, int F, int S,
@@ -765,38 +910,39 @@ extern "C" slr_status slr_run_gray_host(slr_engine *e, const uint8_t *h_stack, i
     }
     const size_t P = (size_t)e->W * e->H, ncell = (size_t)scan_w * scan_h;
     const size_t N = (size_t)(2 + 2 * nbits_col + 2 * nbits_row);
-    uint8_t *d_stack = nullptr, *d_mask = nullptr, *d_cnt = nullptr;
-    int32_t *d_col = nullptr, *d_row = nullptr;
-    float *d_sum = nullptr;
+    // engine-owned scratch, grown on demand and kept for the next call
+    const size_t want[6] = {2 * N * P, 2 * P, 2 * P * sizeof(int32_t), 2 * P * sizeof(int32_t), ncell * 3 * sizeof(float), ncell};
+    for (int k = 0; k < 6; k++) {
+        if (e->gray_bytes[k] >= want[k]) continue;
+        cudaFree(e->d_gray[k]);
+        e->d_gray[k] = nullptr;
+        e->gray_bytes[k] = 0;
+        SLR_CHECK_CUDA(cudaMalloc(&e->d_gray[k], want[k]));
+        e->gray_bytes[k] = want[k];
+    }
+    uint8_t *d_stack = (uint8_t *)e->d_gray[0], *d_mask = (uint8_t *)e->d_gray[1], *d_cnt = (uint8_t *)e->d_gray[5];
+    int32_t *d_col = (int32_t *)e->d_gray[2], *d_row = (int32_t *)e->d_gray[3];
+    float *d_sum = (float *)e->d_gray[4];
     slr_status st = SLR_OK;
-    cudaError_t ce = cudaMalloc(&d_stack, 2 * N * P);
-    if (ce == cudaSuccess) ce = cudaMalloc(&d_mask, 2 * P);
-    if (ce == cudaSuccess) ce = cudaMalloc(&d_col, 2 * P * sizeof(int32_t));
-    if (ce == cudaSuccess) ce = cudaMalloc(&d_row, 2 * P * sizeof(int32_t));
-    if (ce == cudaSuccess) ce = cudaMalloc(&d_sum, ncell * 3 * sizeof(float));
-    if (ce == cudaSuccess) ce = cudaMalloc(&d_cnt, ncell);
-    if (ce == cudaSuccess) ce = cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream);
+    cudaError_t ce = cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream);
     for (int b = 0; b < batch && ce == cudaSuccess && st == SLR_OK; b++) {
+        // one scan at a time: upload, decode, triangulate, download on the engine's stream (stream order makes the
+        // scratch reusable without a host synchronisation per scan)
         ce = cudaMemcpyAsync(d_stack, h_stack + (size_t)b * 2 * N * P, 2 * N * P, cudaMemcpyHostToDevice, e->stream);
         if (ce != cudaSuccess) break;
-        st = slr_launch_gray_decode(e, d_stack, 2, nbits_col, nbits_row, black_thr, white_thr, scan_w, scan_h, d_col, d_row, d_mask);
+        if (e->auto_contrast) st = slr_launch_auto_contrast(e, d_stack, (int)(2 * N));
+        if (st == SLR_OK)
+            st = slr_launch_gray_decode(e, d_stack, 2, nbits_col, nbits_row, black_thr, white_thr, scan_w, scan_h, d_col, d_row, d_mask);
         if (st == SLR_OK) st = slr_launch_bucket_triangulate(e, d_col, d_row, d_mask, 1, scan_w, scan_h, d_sum, d_cnt, e->d_counter);
         if (st != SLR_OK) break;
         ce = cudaMemcpyAsync(h_sum + (size_t)b * ncell * 3, d_sum, ncell * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_cnt + (size_t)b * ncell, d_cnt, ncell, cudaMemcpyDeviceToHost, e->stream);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
     }
-    if (ce == cudaSuccess && st == SLR_OK) {
+    if (ce == cudaSuccess && st == SLR_OK)
         ce = cudaMemcpyAsync(e->h_counter, e->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
-        if (ce == cudaSuccess && h_n_cells) *h_n_cells = *e->h_counter;
-    }
-    cudaFree(d_stack);
-    cudaFree(d_mask);
-    cudaFree(d_col);
-    cudaFree(d_row);
-    cudaFree(d_sum);
-    cudaFree(d_cnt);
+    const cudaError_t cs = cudaStreamSynchronize(e->stream);   // also on errors: no copy may outlive the call
+    if (ce == cudaSuccess) ce = cs;
+    if (ce == cudaSuccess && st == SLR_OK && h_n_cells) *h_n_cells = *e->h_counter;
     if (ce != cudaSuccess) {
         slr_set_error("slr_run_gray_host: %s", cudaGetErrorString(ce));
         return SLR_ERR_CUDA;

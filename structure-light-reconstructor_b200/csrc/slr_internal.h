@@ -9,6 +9,7 @@
 #include "slr_b200.h"
 
 #define SLR_QNAN_BITS 0x7FC00000u
+#define SLR_MAX_TARGETS 8
 
 // Reference constants.  Duke/mfreconstruct.cpp:5 `float PI = 3.1416;`
 #define SLR_PI_DEC 3.1416f
@@ -19,6 +20,7 @@ struct slr_calib_dev {
     float rigid[12];
     int has_rigid;
     int q_std;  // Q has the cv::stereoRectify sparsity pattern (see reproject_q)
+    int row0;   // image row of the engine's row 0 (row-band partition of a scan over several GPUs; 0 otherwise)
 };
 
 struct slr_engine {
@@ -60,6 +62,12 @@ struct slr_engine {
     uint16_t *d_map2 = nullptr;
     bool maps_set = false;
     bool host_input_raw = false;     // host entry points rectify the uploaded stacks first
+    bool auto_contrast = false;      // host entry points stretch every image (Utilities::autoContrast) before decoding
+    void *d_minmax = nullptr;        // K_contrast: int2 {min, max} per image
+    int minmax_images = 0;
+    // slr_run_gray_host scratch (one scan): stack, mask, col, row, cell sums, cell counts
+    void *d_gray[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t gray_bytes[6] = {0, 0, 0, 0, 0, 0};
     uint8_t *d_stage_rect[2] = {nullptr, nullptr};
     size_t stage_rect_bytes = 0;
 
@@ -83,6 +91,14 @@ struct slr_engine {
     unsigned calib_version = 0, child_calib_version = 0;
     void *d_pad[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t pad_bytes[6] = {0, 0, 0, 0, 0, 0};
+
+    // gather targets (slr_set_gather_targets): the assembled clouds of all ranks, [0] = this GPU's own, the others
+    // peer mappings; the MF / GE pipelines write every output row into each of them
+    int n_targets = 0;
+    float *xyz_t[SLR_MAX_TARGETS] = {};
+    uint8_t *valid_t[SLR_MAX_TARGETS] = {};
+    long long target_first_scan = 0;
+    bool targets_written = false;   // set by a launcher whose kernel stored to all targets itself
 
     unsigned long long launches = 0;
 };
@@ -145,6 +161,7 @@ slr_status slr_launch_fused_ge(slr_engine *e, const uint8_t *d_stack, int batch,
 slr_status slr_launch_undistort_maps(slr_engine *e);
 slr_status slr_launch_rectify(slr_engine *e, const uint8_t *d_raw, int batch, int N, uint8_t *d_out);
 slr_status slr_build_strict_tables(slr_engine *e);
+slr_status slr_launch_auto_contrast(slr_engine *e, uint8_t *d_images, int n_images);
 // padded route for e->W % 16 != 0 (slr_engine.cu); kind: 0 = image stacks (MF), 1 = image stacks (GE),
 // 2 = phase + mask rows, 3 = code + mask rows
 slr_status slr_padded_run(slr_engine *e, int kind, const void *d_in0, const uint8_t *d_in1, int batch, int planes,

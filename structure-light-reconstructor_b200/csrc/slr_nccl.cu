@@ -8,6 +8,8 @@
 #include <dlfcn.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "slr_internal.h"
 
 namespace {
@@ -23,33 +25,41 @@ struct NcclApi {
     int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
 
-NcclApi *nccl_api()
+static NcclApi g_api;
+
+static void nccl_bind()
 {
-    static NcclApi api;
-    static bool tried = false;
-    if (tried) return api.lib ? &api : nullptr;
-    tried = true;
+    NcclApi &api = g_api;
     const char *names[] = {getenv("SLR_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     for (const char *n : names) {
         if (!n || !*n) continue;
         api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
         if (api.lib) break;
     }
-    if (!api.lib) return nullptr;
+    if (!api.lib) return;
     api.GetUniqueId = (int (*)(ncclUniqueId *))dlsym(api.lib, "ncclGetUniqueId");
     api.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(api.lib, "ncclCommInitRank");
     api.CommDestroy = (int (*)(ncclComm_t))dlsym(api.lib, "ncclCommDestroy");
     api.AllGather = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t))dlsym(api.lib, "ncclAllGather");
+    api.GroupStart = (int (*)())dlsym(api.lib, "ncclGroupStart");
+    api.GroupEnd = (int (*)())dlsym(api.lib, "ncclGroupEnd");
     api.GetErrorString = (const char *(*)(int))dlsym(api.lib, "ncclGetErrorString");
-    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather) {
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.GroupStart || !api.GroupEnd) {
         dlclose(api.lib);
         api.lib = nullptr;
-        return nullptr;
     }
-    return &api;
+}
+
+NcclApi *nccl_api()   // thread-safe one-time binding (slr_last_error is per thread, so callers may be too)
+{
+    static std::once_flag once;
+    std::call_once(once, nccl_bind);
+    return g_api.lib ? &g_api : nullptr;
 }
 
 #define SLR_CHECK_NCCL(api, expr)                                                                              \
@@ -100,10 +110,13 @@ extern "C" slr_status slr_allgather(slr_engine *e, void *nccl_comm, int world, i
     SLR_REQUIRE(a != nullptr, "NCCL is not available (libnccl.so.2 not found; set SLR_NCCL_LIB)");
     SLR_CHECK_CUDA(cudaSetDevice(e->device));
     const size_t px = (size_t)scans_per_rank * e->W * e->H;
-    // in place: this rank's block already sits at rank * count of the receive buffer
-    SLR_CHECK_NCCL(a, a->AllGather(d_xyz_all + (size_t)rank * px * 3, d_xyz_all, px * 3, ncclFloat32V, (ncclComm_t)nccl_comm,
-                                   e->stream));
-    SLR_CHECK_NCCL(a, a->AllGather(d_valid_all + (size_t)rank * px, d_valid_all, px, ncclUint8V, (ncclComm_t)nccl_comm,
-                                   e->stream));
+    // in place: this rank's block already sits at rank * count of the receive buffer.  Both tensors travel in ONE
+    // NCCL group: a single communication call (one launch) per step
+    SLR_CHECK_NCCL(a, a->GroupStart());
+    const int r1 = a->AllGather(d_xyz_all + (size_t)rank * px * 3, d_xyz_all, px * 3, ncclFloat32V, (ncclComm_t)nccl_comm, e->stream);
+    const int r2 = a->AllGather(d_valid_all + (size_t)rank * px, d_valid_all, px, ncclUint8V, (ncclComm_t)nccl_comm, e->stream);
+    SLR_CHECK_NCCL(a, a->GroupEnd());
+    SLR_CHECK_NCCL(a, r1);
+    SLR_CHECK_NCCL(a, r2);
     return SLR_OK;
 }

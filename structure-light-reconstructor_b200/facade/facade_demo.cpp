@@ -84,7 +84,8 @@ int main(int argc, char **argv)
     } else {
         Reconstruct *r = new Reconstruct(kind == "ge");
         r->scanSN = sn;
-        r->getParameters(scanw, scanh, camw, camh, false, havecolor != 0, project);
+        const bool autocontrast = getenv("DUKE_AUTOCONTRAST") && atoi(getenv("DUKE_AUTOCONTRAST")) != 0;   // Set dialog flag
+        r->getParameters(scanw, scanh, camw, camh, autocontrast, havecolor != 0, project);
         r->setCalibPath(project + "/calib/left/", 0);
         r->setCalibPath(project + "/calib/right/", 1);
         if (!r->loadCameras()) return 1;

@@ -96,6 +96,7 @@ bool MFReconstruct::runReconstruction()
         if (slr_set_calib(eng, cams, sr->Q.v.data(), rg) != SLR_OK) break;
         if (slr_set_rectify_maps(eng, sr->map1().data(), sr->map2().data()) != SLR_OK) break;
         if (slr_set_host_input_raw(eng, 1) != SLR_OK) break;
+        if (slr_set_auto_contrast(eng, 0) != SLR_OK) break;   // MFReconstruct has no such setting; the engine is shared
         if (!(h_stack = duke::pinned_scratch(0, 2 * (size_t)numberOfImgs * P))) break;
         if (!(h_xyz = duke::pinned_scratch(1, P * 3 * sizeof(float)))) break;
         if (!(h_valid = duke::pinned_scratch(2, P))) break;

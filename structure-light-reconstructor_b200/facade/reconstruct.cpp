@@ -94,10 +94,6 @@ bool Reconstruct::runReconstruction_GE()
         fprintf(stderr, "Reconstruct: stereo calibration is not loaded\n");
         return false;
     }
-    if (autoContrast_) {
-        fprintf(stderr, "Reconstruct: autoContrast is not supported by the B200 path\n");
-        return false;
-    }
     const int W = cameraWidth, H = cameraHeight;
     const size_t P = (size_t)W * H;
     const int nbits = slr_gray_num_bits(scan_w);       // GrayCodes(scan_w, scan_h, true)
@@ -124,6 +120,8 @@ bool Reconstruct::runReconstruction_GE()
         if (slr_set_calib(eng, cams, sr->Q.v.data(), rg) != SLR_OK) break;
         if (slr_set_rectify_maps(eng, sr->map1().data(), sr->map2().data()) != SLR_OK) break;
         if (slr_set_host_input_raw(eng, 1) != SLR_OK) break;
+        // Utilities::autoContrast on every rectified image (Duke/reconstruct.cpp:182-183), on the GPU after K0
+        if (slr_set_auto_contrast(eng, autoContrast_ ? 1 : 0) != SLR_OK) break;
         if (!(h_stack = duke::pinned_scratch(0, 2 * (size_t)nimg * P))) break;
         if (!(h_xyz = duke::pinned_scratch(1, P * 3 * sizeof(float)))) break;
         if (!(h_valid = duke::pinned_scratch(2, P))) break;
@@ -147,10 +145,6 @@ bool Reconstruct::runReconstruction_GE()
 
 bool Reconstruct::runReconstruction()
 {
-    if (autoContrast_) {
-        fprintf(stderr, "Reconstruct: autoContrast is not supported by the B200 path\n");
-        return false;
-    }
     const int W = cameraWidth, H = cameraHeight;
     const size_t P = (size_t)W * H;
     const int nc = slr_gray_num_bits(scan_w), nr = slr_gray_num_bits(scan_h);   // GrayCodes(scan_w, scan_h, false)
@@ -178,6 +172,7 @@ bool Reconstruct::runReconstruction()
         if (scanSN > 0 && duke::load_rigid(savePath_ + "/scan/transfer_mat" + std::to_string(scanSN) + ".txt", rigid)) rg = rigid;
         if (slr_set_calib(eng, cams, Qid, rg) != SLR_OK) break;
         if (slr_set_host_input_raw(eng, 0) != SLR_OK) break;   // the shared engine may have rectified for a GE / MF scan
+        if (slr_set_auto_contrast(eng, autoContrast_ ? 1 : 0) != SLR_OK) break;
         bool loaded = true;
         for (int i = 0; i < 2 && loaded; i++)
             loaded = duke::load_stack(scanFolder[i], imgPrefix[i], imgSuffix, nimg, W, H, stack.data() + (size_t)i * nimg * P);
@@ -187,7 +182,9 @@ bool Reconstruct::runReconstruction()
                               cnt.data(), &n) != SLR_OK)
             break;
         delete points3DProjView;
-        points3DProjView = new PointCloudImage(scan_w, scan_h, false);
+        // colour storage as in Duke/reconstruct.cpp:262; the Gray-only triangulation never sets a colour (:417-481),
+        // so with haveColor the export shows "0 0 0" columns, exactly as the reference's
+        points3DProjView = new PointCloudImage(scan_w, scan_h, haveColor);
         // cells arrive in the reference's ac(i, j) = i*scan_h + j order; the accumulated state (sum, wrapped count)
         // is reproduced by one setPoint plus count-1 zero additions
         for (int i = 0; i < scan_w; i++)

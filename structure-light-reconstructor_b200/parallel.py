@@ -1,6 +1,8 @@
-"""Multi-GPU plumbing (host side only).  Scans are independent, so ranks own contiguous blocks of the batch and
-no collective is needed on the data path; the optional all-gather assembles every rank's cloud on every rank
-(`torch.distributed.all_gather_into_tensor`: NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+"""Multi-GPU plumbing (host side only).  Scans are independent, so ranks own contiguous blocks of the batch (or, for
+one scan, contiguous row bands) and no collective is needed on the data path.  Assembling every rank's cloud on every
+rank is done either by `PeerAssembly` (the kernels store their output rows straight into every peer's buffer over
+NVLink: no collective call at all) or by `CloudAssembly` / `gather_clouds` (an all-gather: NCCL on GPUs, gloo in the
+CPU tests)."""
 from __future__ import annotations
 
 
@@ -12,6 +14,79 @@ def scan_shard(n_scans: int, rank: int, world: int):
     base, extra = divmod(n_scans, world)
     lo = rank * base + min(rank, extra)
     return lo, lo + base + (1 if rank < extra else 0)
+
+
+def row_band(height: int, rank: int, world: int):
+    """Rows [lo, hi) of ONE scan owned by `rank`: both cameras' rows lo..hi-1 (the match runs along rectified rows, so
+    bands need no halo; SURVEY.md §8e unit 2).  Same contiguous split as scan_shard."""
+    return scan_shard(height, rank, world)
+
+
+class _DevicePtr:
+    """Zero-copy torch view of raw device memory through the CUDA array interface."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerAssembly:
+    """The assembled cloud of all ranks WITHOUT a collective: every rank allocates [world * b_local, H, W, 3] xyz +
+    [world * b_local, H, W] valid with `slr_peer_alloc`, maps every other rank's buffers through their CUDA IPC
+    handles, and registers all of them as gather targets of its engine.  `slr_run_mf` then stores each output row
+    into block `rank` of EVERY rank's buffer from the kernel's epilogue (peer stores over NVLink / NVSwitch), so the
+    transfer overlaps the kernel that produces the data.  After the kernels of all ranks have completed and the
+    ranks have synchronised (`dist.barrier()`), `views(slot)` holds the whole cloud on every rank.
+    For row bands, pass the band height as H: block r is then band r of the scan and the assembled tensor, viewed as
+    [b_local, world * H, W, ...] for b_local == 1, is the full image.  Equal shards only."""
+
+    def __init__(self, eng, b_local: int, H: int, W: int, slots: int = 2, group=None):
+        import torch
+        import torch.distributed as dist
+        self.eng, self.b, self.slots = eng, b_local, slots
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        n = self.world * b_local
+        px = n * H * W
+        self.own, self.peers, self._views = [], [], []
+        handles = []
+        for _ in range(slots):
+            xp, xh = eng.peer_alloc(px * 12)
+            vp, vh = eng.peer_alloc(px)
+            self.own.append((xp, vp))
+            handles.append((xh, vh))
+            self._views.append((torch.as_tensor(_DevicePtr(xp, (n, H, W, 3), "<f4"), device=eng.dev),
+                                torch.as_tensor(_DevicePtr(vp, (n, H, W), "|u1"), device=eng.dev)))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, handles, group=group)
+        for slot in range(slots):
+            mapped = []
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                xh, vh = everyone[r][slot]
+                mapped.append((eng.peer_open(xh), eng.peer_open(vh)))
+            self.peers.append(mapped)
+        dist.barrier(group=group)
+
+    def views(self, slot: int):
+        """(xyz_all, valid_all) of this rank's own assembled buffers"""
+        return self._views[slot]
+
+    def select(self, slot: int):
+        """Make slot the destination of the engine's next slr_run_mf / slr_run_ge calls."""
+        targets = [self.own[slot]] + self.peers[slot]
+        self.eng.set_gather_targets([t[0] for t in targets], [t[1] for t in targets], self.rank * self.b)
+
+    def close(self):
+        self.eng.set_gather_targets([], [])
+        for mapped in self.peers:
+            for xp, vp in mapped:
+                self.eng.peer_close(xp)
+                self.eng.peer_close(vp)
+        self._views = []
+        for xp, vp in self.own:
+            self.eng.peer_free(xp)
+            self.eng.peer_free(vp)
+        self.peers, self.own = [], []
 
 
 def gather_clouds(xyz_local, valid_local, n_scans: int, group=None):

@@ -217,6 +217,13 @@ class Oracle:
                                   C.c_void_p(dst.ctypes.data))
         return dst
 
+    def auto_contrast(self, img):
+        """Utilities::autoContrast (channel 0) on a copy of a uint8 [H, W] image"""
+        out = np.ascontiguousarray(img, np.uint8).copy()
+        H, W = out.shape
+        self.lib.orc_auto_contrast(C.c_void_p(out.ctypes.data), W, H)
+        return out
+
     def max_threads(self):
         return self.lib.orc_max_threads()
 

@@ -73,9 +73,10 @@ def make_project(tmp, W, H, sn, stacks, rigid=None):
     return [cams["left"], cams["right"]]
 
 
-def run_demo(kind, tmp, sn, scan_w, scan_h, W, H, black, white, color, ply=None):
+def run_demo(kind, tmp, sn, scan_w, scan_h, W, H, black, white, color, ply=None, autocontrast=False):
     out = os.path.join(tmp, "out.bin")
     env = dict(os.environ)
+    env["DUKE_AUTOCONTRAST"] = "1" if autocontrast else "0"
     if ply:
         env["DUKE_EXPORT_PLY"] = ply      # the caller's export step (MeshCreator, mainwindow.cpp:637-646)
     r = subprocess.run([DEMO, kind, tmp, str(sn), str(scan_w), str(scan_h), str(W), str(H), str(black), str(white),
@@ -148,6 +149,43 @@ def test_reconstruct_ge_facade_end_to_end(tmp_path, oracle):
     pts_o, cnt_o = oracle.pointcloud_from_dense(xyz, valid, W, 400)
     assert n > 1000 and (cnt == cnt_o).all()
     assert (bits(sums[cnt > 0]) == bits(pts_o[cnt_o > 0])).all()
+
+
+def test_reconstruct_ge_facade_with_auto_contrast(tmp_path, oracle):
+    """Reconstruct::getParameters(autocontrast = true): loadCamImgs stretches every rectified image with
+    Utilities::autoContrast before the decode (Duke/reconstruct.cpp:182-183).  Oracle-only (the reference's own
+    autoContrast reads channels 1, 2 of a one-channel image: undefined behaviour)."""
+    W, H = 320, 48
+    stacks = synth.synth_gray(W, H, seed=64, noise_dn=2.0)
+    stacks = (stacks.astype(np.float32) * 0.6 + 20).astype(np.uint8)      # a dim scan: the stretch matters
+    nc = oracle.gray_num_bits(W)
+    make_project(str(tmp_path), W, H, 0, stacks)
+    sums, cnt, Q, m1, m2, _ = run_demo("ge", str(tmp_path), 0, W, 400, W, H, 40, 4, True, autocontrast=True)
+    rect = np.stack([[oracle.auto_contrast(oracle.remap_linear(stacks[c, i], m1[c], m2[c])) for i in range(stacks.shape[1])]
+                     for c in range(2)])
+    dec = [oracle.gray_decode(rect[c], nc, 0, 40, 4, W, 400) for c in range(2)]
+    xyz, valid, k, color, n = oracle.ge_triangulate(dec[0][0], dec[0][2], dec[1][0], dec[1][2], Q,
+                                                    whiteL=rect[0, 0], whiteR=rect[1, 0])
+    pts_o, cnt_o = oracle.pointcloud_from_dense(xyz, valid, W, 400)
+    assert n > 300 and (cnt == cnt_o).all()
+    assert (bits(sums[cnt > 0]) == bits(pts_o[cnt_o > 0])).all()
+    # without the stretch the same dim scan decodes to a different cloud (the flag is not a no-op)
+    sums0, cnt0, *_ = run_demo("ge", str(tmp_path), 0, W, 400, W, H, 40, 4, True, autocontrast=False)
+    assert (cnt0 != cnt).any()
+
+
+def test_auto_contrast_kernel_vs_oracle(oracle):
+    import torch
+    import slr_b200
+    rng = np.random.default_rng(9)
+    for W, H in ((320, 48), (37, 5)):                       # 128-bit path and the byte path (W*H % 16 != 0)
+        eng = slr_b200.Engine(W, H, max_batch=1)
+        imgs = np.stack([rng.integers(0, 256, (H, W)), rng.integers(90, 101, (H, W)), np.full((H, W), 77),
+                         rng.integers(30, 200, (H, W)), np.clip(rng.normal(60, 10, (H, W)), 0, 255)]).astype(np.uint8)
+        got = eng.auto_contrast(torch.from_numpy(imgs).cuda()).cpu().numpy()
+        for q in range(len(imgs)):
+            assert (got[q] == oracle.auto_contrast(imgs[q])).all(), (W, H, q)
+        eng.close()
 
 
 def test_reconstruct_gray_only_facade_end_to_end(tmp_path, oracle):

@@ -212,3 +212,29 @@ def test_unaligned_device_pointers_match_the_oracle(cuda_engine_factory, oracle)
     gm = np.stack(mks)[None]
     xyz, valid, k, _, n = eng.match_triangulate_code(_offset_like(_t(col), 4), _offset_like(_t(gm), 5))
     _assert_cloud_equal(xyz[0], valid[0], k[0], int(n.item()), xyz_g, valid_g, k_g, n_g, "unaligned code match")
+
+
+# ------------------------------------------------------------------------------------------------
+# row bands: an engine of the band's height with slr_set_row_offset == the same rows of the full image
+# ------------------------------------------------------------------------------------------------
+def test_row_band_engines_reproduce_the_full_image(cuda_engine_factory):
+    import torch
+    W, H = 640, 60
+    full = cuda_engine_factory(W, H, 1)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    full.set_calib(cams, Q)
+    mf = full.synth_mf(1, seed=81, integer_disparity=False, noise_dn=1.0)
+    ge = full.synth_gray(1, seed=82, integer_disparity=False, noise_dn=2.0)
+    nb = slr_b200.gray_num_bits(W)
+    xyz_f, valid_f, k_f, _ = full.run_mf(mf, black_thr=40)
+    gx_f, gv_f, gk_f, _, _ = full.run_ge(ge, nb, black_thr=40, white_thr=3)
+    for lo, hi in ((0, 20), (20, 47), (47, 60)):
+        band = cuda_engine_factory(W, hi - lo, 1)
+        band.set_calib(cams, Q)
+        band.set_row_offset(lo)
+        xyz, valid, k, _ = band.run_mf(mf[:, :, :, lo:hi].contiguous(), black_thr=40)
+        assert torch.equal(k, k_f[:, lo:hi]) and torch.equal(valid, valid_f[:, lo:hi])
+        assert (bits(xyz.cpu().numpy()) == bits(xyz_f[:, lo:hi].cpu().numpy())).all()
+        gx, gv, gk, _, _ = band.run_ge(ge[:, :, :, lo:hi].contiguous(), nb, black_thr=40, white_thr=3)
+        assert torch.equal(gk, gk_f[:, lo:hi]) and torch.equal(gv, gv_f[:, lo:hi])
+        assert (bits(gx.cpu().numpy()) == bits(gx_f[:, lo:hi].cpu().numpy())).all()

@@ -272,3 +272,14 @@ def test_gray_decode_kat(oracle):
     assert mk2[0, 7] == 0 and col2[0, 7] == -1 and mk2[1, 3] == 0
     col3, _, mk3 = oracle.gray_decode(stack, nb, black_thr=40, white_thr=0, scan_w=20)
     assert mk3[0, :21].all() and not mk3[0, 21:].any()                # xDec > scan_w is strict (:403)
+
+
+def test_auto_contrast_known_answers(oracle):
+    """Utilities::autoContrast (Duke/utilities.cpp:340-355), channel 0, by hand: min = 20 + 12.75 = 32.75,
+    a = 255 / (220 - 32.75) = 1.36181...; v = 20 -> 0 (saturated), v = 33 -> round(0.25) = 0 -> 0,
+    v = 34 -> round(1.25) = 1 -> round(1.3618) = 1, v = 120 -> round(87.25) = 87 -> round(118.48) = 118,
+    v = 220 -> round(187.25) = 187 -> round(254.66) = 255."""
+    img = np.array([[20, 33, 34, 120, 220]], np.uint8)
+    assert oracle.auto_contrast(img).tolist() == [[0, 0, 1, 118, 255]]
+    # a flat image: max - (min + 12.75) < 0, every pixel saturates to 0 in the subtraction
+    assert (oracle.auto_contrast(np.full((3, 4), 99, np.uint8)) == 0).all()

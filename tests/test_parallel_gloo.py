@@ -24,6 +24,14 @@ def test_scan_shard_partitions_the_batch():
         parallel.scan_shard(4, 2, 2)
 
 
+def test_row_band_partitions_one_scan():
+    for h in (1, 48, 1024, 1536, 3000):
+        for world in (1, 2, 4, 8):
+            bands = [parallel.row_band(h, r, world) for r in range(world)]
+            assert bands[0][0] == 0 and bands[-1][1] == h
+            assert all(bands[i][1] == bands[i + 1][0] for i in range(world - 1))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
