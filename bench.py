@@ -97,6 +97,20 @@ def bind_to_gpu_numa_node(index):
     return None
 
 
+class stdout_to_stderr:
+    """NCCL prints its version banner on stdout when a communicator is created; the bench's stdout is ONE JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -329,7 +343,9 @@ def main():
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
 
     cfg = CONFIGS[args.config]
     W, H, F, S = cfg["W"], cfg["H"], cfg["F"], cfg["S"]
@@ -441,7 +457,8 @@ def main():
         # (b) one NCCL all-gather per step (xyz and valid of a slot in one group call), on a side stream
         ids = [slr_b200.Engine.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
-        comm = eng.nccl_comm_create(world, rank, ids[0])
+        with stdout_to_stderr():
+            comm = eng.nccl_comm_create(world, rank, ids[0])
         casm = parallel.CloudAssembly(B, H, W, dev, slots=2, native=(eng, comm))
         outs = []
         for slot in range(2):

@@ -293,21 +293,39 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
             for (int q = 0; q < FLOW_QPX; q++) {
                 const bool hit = best[q] != INT_MAX;
                 n_local += hit ? 1u : 0u;
-                if (j[q] < W) {
-                    const size_t o = (size_t)ri.out_px + j[q];
-                    const float ox = hit ? X[q] : slr::qnan(), oy = hit ? Y[q] : slr::qnan(), oz = hit ? Z[q] : slr::qnan();
-                    // target 0 is this GPU's cloud; further targets are the peers' assembled clouds (NVLink stores
-                    // straight from registers: the all-gather overlaps the kernel that produces the data)
-#pragma unroll 1
-                    for (int tg = 0; tg < p.n_t; tg++) {
-                        float *dst = p.xyz_t[tg] + o * 3;
+                const float ox = hit ? X[q] : slr::qnan(), oy = hit ? Y[q] : slr::qnan(), oz = hit ? Z[q] : slr::qnan();
+                const size_t o = (size_t)ri.out_px + j[q];
+                if (p.n_t == 1) {
+                    if (j[q] < W) {
+                        float *dst = p.xyz + o * 3;
                         dst[0] = ox;
                         dst[1] = oy;
                         dst[2] = oz;
-                        p.valid_t[tg][o] = hit ? 1 : 0;
+                        p.valid[o] = hit ? 1 : 0;
                     }
-                    if (p.match_k) p.match_k[o] = hit ? best[q] : -1;
+                } else {
+                    // Assembly on every GPU: target 0 is this GPU's cloud, the others are the peers' (NVLink stores
+                    // straight from registers, so the all-gather overlaps the kernel that produces the data).  The 32
+                    // float3 of the group are transposed across the warp (4 x select + shuffle) into 24 float4, so
+                    // that every peer store is a full 16-byte write instead of three 4-byte writes 12 bytes apart:
+                    // a third of the NVLink packets, each with a full payload.
+                    float4 v4;
+                    float *o4 = &v4.x;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int cmp = (k - 3 * lane) & 3;            // the component lane `lane` exposes in round k
+                        const float sel = (cmp == 0) ? ox : (cmp == 1) ? oy : oz;
+                        o4[k] = __shfl_sync(0xffffffffu, sel, min((4 * lane + k) / 3, 31));
+                    }
+                    const int j0 = j[q] - lane, n_f = 3 * min(32, W - j0);   // floats of this group inside the row
+                    const size_t f0 = ((size_t)ri.out_px + j0) * 3;
+#pragma unroll 1
+                    for (int tg = 0; tg < p.n_t; tg++) {
+                        if (4 * lane + 3 < n_f) *reinterpret_cast<float4 *>(p.xyz_t[tg] + f0 + 4 * lane) = v4;
+                        if (j[q] < W) p.valid_t[tg][o] = hit ? 1 : 0;
+                    }
                 }
+                if (j[q] < W && p.match_k) p.match_k[o] = hit ? best[q] : -1;
             }
             __syncwarp();
             int last = 0;
