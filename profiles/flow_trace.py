@@ -40,6 +40,16 @@ def report(path):
         w, run = (ready - draw)[sel], (end - ready)[sel]
         print(f"{name:7s} jobs {sel.sum():5d}  wait mean {w.mean():7.0f} p50 {np.median(w):6.0f} p90 {np.percentile(w, 90):6.0f} max {w.max():6d}"
               f"   run mean {run.mean():7.0f} p90 {np.percentile(run, 90):6.0f}   share of warp time waiting {w.sum() / (w.sum() + run.sum()):.3f}")
+    # where a warp's time goes: running a job, waiting for its dependencies, or between jobs (draw + loop overhead)
+    warp = (d[:, 0] >> 40) & 0xff
+    tot_run = (end - ready).sum()
+    tot_wait = (ready - draw).sum()
+    span = 0
+    for w in np.unique(warp):
+        sel = warp == w
+        span += end[sel].max() - draw[sel].min()
+    print(f"warp time: run {tot_run / span:.3f}  wait {tot_wait / span:.3f}  between jobs {(span - tot_run - tot_wait) / span:.3f}"
+          f"   (decode run {((end - ready)[typ == 0]).sum() / span:.3f}, query run {((end - ready)[typ >= 1]).sum() / span:.3f})")
     print("per-row timeline (cycles from the row's first decode draw), rows 20..25:")
     for r in range(20, min(26, rows)):
         dsel, qsel = (typ == 0) & (row == r), (typ >= 1) & (row == r)

@@ -286,14 +286,14 @@ slr_status slr_build_strict_tables(slr_engine *e)
     };
     for (int q = 0; q <= 255; q++) {
         const float atp = atanf((float)q), atn = atanf((float)(-q));
-        ptab[0 * 256 + q] = fx(atn);                       // b > 0, a <= 0 (:261 / :246)
-        ptab[1 * 256 + q] = fx(atp + 2 * PI);              // b > 0, a > 0  (:259)
-        ptab[2 * 256 + q] = fx(atp + PI);                  // b < 0, a <= 0 (:257 / :248)
-        ptab[3 * 256 + q] = fx(atn + PI);                  // b < 0, a > 0  (:257)
-        ptab[4 * 256 + q] = fx(PI / 2);                    // b == 0, a < 0 (:252)
-        ptab[5 * 256 + q] = fx(3 * PI / 2);                // b == 0, a > 0 (:250)
+        ptab[0 * SLR_PTAB_STRIDE + q] = fx(atn);                       // b > 0, a <= 0 (:261 / :246)
+        ptab[1 * SLR_PTAB_STRIDE + q] = fx(atp + 2 * PI);              // b > 0, a > 0  (:259)
+        ptab[2 * SLR_PTAB_STRIDE + q] = fx(atp + PI);                  // b < 0, a <= 0 (:257 / :248)
+        ptab[3 * SLR_PTAB_STRIDE + q] = fx(atn + PI);                  // b < 0, a > 0  (:257)
+        ptab[4 * SLR_PTAB_STRIDE + q] = fx(PI / 2);                    // b == 0, a < 0 (:252)
+        ptab[5 * SLR_PTAB_STRIDE + q] = fx(3 * PI / 2);                // b == 0, a > 0 (:250)
     }
-    ptab[4 * 256 + 0] = SLR_PTAB_DEGENERATE;               // a == 0 and b == 0 (:254)
+    ptab[4 * SLR_PTAB_STRIDE + 0] = SLR_PTAB_DEGENERATE;               // a == 0 and b == 0 (:254)
     if (!exact) {
         slr_set_error("strict tables: a wrapped phase is not a multiple of 2^-24 (host libm atanf out of spec?)");
         return SLR_ERR_INVALID;
@@ -302,7 +302,7 @@ slr_status slr_build_strict_tables(slr_engine *e)
         const uint32_t ub = (uint32_t)abs(b);
         const uint32_t M = ub ? 65536u / ub + 1u : 65536u;  // b == 0: q = |a| selects within rows 4/5
         const uint32_t row = (b > 0) ? 0u : (b < 0) ? 2u : 4u;
-        btab[b + 256] = M | ((row * 256u) << 17);
+        btab[b + 256] = M | ((row * (uint32_t)SLR_PTAB_STRIDE) << 17);
     }
     btab[0] = 0;
     if (!e->d_ptab) SLR_CHECK_CUDA(cudaMalloc(&e->d_ptab, sizeof(ptab)));

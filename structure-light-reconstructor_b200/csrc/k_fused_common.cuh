@@ -191,10 +191,11 @@ __device__ __forceinline__ void decode_px(const uint8_t *__restrict__ rows, int 
 }
 
 // phases of PX pixels of the right or left row, from the staged image rows (or the staged phase + mask rows)
+// cam_pad = bytes between the end of the left camera's planes and the start of the right camera's in the stage buffer
 template <int MODE, int PX>
 __device__ __forceinline__ void load_phases(const unsigned char *stage, int W, int N, int x0, bool right,
                                             const FusedParams &p, const int *s_ptab, const uint32_t *s_btab,
-                                            float (&ph)[PX], bool (&ok)[PX])
+                                            float (&ph)[PX], bool (&ok)[PX], int cam_pad = 0)
 {
     if (MODE == MODE_PHASE_INPUT) {  // stage = pL f32[W] | pR f32[W] | mL u8[W] | mR u8[W]
         const float *src = reinterpret_cast<const float *>(stage + (right ? 4 * W : 0)) + x0;
@@ -205,11 +206,11 @@ __device__ __forceinline__ void load_phases(const unsigned char *stage, int W, i
             ok[q] = m[q] != 0 && (!right || ph[q] == ph[q]);  // a NaN on the right never matches
         }
     } else if (SLR_ABLATE(8)) {
-        const unsigned char *r0 = stage + (right ? (size_t)N * W : 0) + x0;
+        const unsigned char *r0 = stage + (right ? (size_t)N * W + cam_pad : 0) + x0;
 #pragma unroll
         for (int q = 0; q < PX; q++) ph[q] = (float)r0[2 * W + q] + 0.01f * (float)r0[6 * W + q], ok[q] = r0[q] > r0[W + q];
     } else {
-        decode_px<MODE, PX>(stage + (right ? (size_t)N * W : 0), W, x0, p, s_ptab, s_btab, ph, ok);
+        decode_px<MODE, PX>(stage + (right ? (size_t)N * W + cam_pad : 0), W, x0, p, s_ptab, s_btab, ph, ok);
     }
 }
 
@@ -303,5 +304,25 @@ __device__ __forceinline__ int first_match(const RowTablesT<LinkT> &t, float v)
     return best;
 }
 
+// The same for two left pixels at once (NaN = no pixel): both chains advance in one loop, so a warp iterates
+// max(len0, len1) over its lanes instead of max(len0) + max(len1), and the two walks' shared-memory round trips overlap.
+// The smallest-column word of an entry is loaded only where the value matches.
+template <bool CLAMP, typename LinkT>
+__device__ __forceinline__ void first_match_x2(const RowTablesT<LinkT> &t, float v0, float v1, int &best0, int &best1)
+{
+    best0 = best1 = INT_MAX;
+    int n0 = (v0 == v0) ? t.head[window_bucket<CLAMP>(v0) & (t.HB - 1)] : -1;
+    int n1 = (v1 == v1) ? t.head[window_bucket<CLAMP>(v1) & (t.HB - 1)] : -1;
+    while ((n0 & n1) >= 0) {   // at least one chain has a node left
+        const int e0 = max(n0, 0) & (t.T - 1), e1 = max(n1, 0) & (t.T - 1);
+        const bool a0 = n0 >= 0, a1 = n1 >= 0;
+        const uint32_t k0 = a0 ? t.ent[e0].x : 0u, k1 = a1 ? t.ent[e1].x : 0u;
+        const int m0 = a0 ? (int)t.nxt[n0] : -1, m1 = a1 ? (int)t.nxt[n1] : -1;
+        if (a0 && slr::phase_match(v0, __uint_as_float(k0))) best0 = min(best0, (int)t.ent[e0].y);
+        if (a1 && slr::phase_match(v1, __uint_as_float(k1))) best1 = min(best1, (int)t.ent[e1].y);
+        n0 = m0;
+        n1 = m1;
+    }
+}
 
 }  // namespace slr_fused

@@ -15,11 +15,11 @@
 //
 // Work is cut into warp-sized jobs; every warp draws the next job from ONE shared counter whose order lists, per
 // step, the decode jobs of row r and then the query jobs of row r-1, so table-lookup-bound, latency-bound and
-// fp64-bound instruction streams share the SM at all times.  A job waits only on per-context completion counters
-// (release/acquire in shared memory) of jobs that precede it in the global order, which makes the schedule
-// deadlock-free: decode(r) needs the clear after query(r-4) and the stage re-armed after decode(r-2); query(r)
-// needs decode(r).  The warp whose decode job is the last to have read a row's stage buffer re-arms it with the
-// TMA copies of row r+2.
+// fp64-bound instruction streams share the SM at all times.  A job waits only on per-context mbarriers that jobs
+// preceding it in the global order arrive on, which makes the schedule deadlock-free: decode(r) needs the clear after
+// query(r-4) and the stage re-armed after decode(r-2); query(r) needs decode(r).  A waiting warp sleeps in
+// mbarrier.try_wait (no issue slots, no shared-memory polling).  The warp whose decode job is the last to have read a
+// row's stage buffer re-arms it with the TMA copies of row r+2.
 #include <limits.h>
 #include <stdlib.h>
 
@@ -33,7 +33,10 @@ constexpr int FLOW_CTX = 4;        // row contexts (tables + parked left phases)
 constexpr int FLOW_LAG = 2;        // steps between a row's decode jobs and its query jobs
 constexpr int FLOW_STAGES = 2;     // TMA stage buffers
 constexpr int FLOW_QPX = 2;        // left pixels per lane in one query job
-constexpr int FLOW_HEADER = 1024;  // mbarriers, counters, row descriptors
+constexpr int FLOW_HEADER = 256;   // mbarriers, counters, row descriptors
+constexpr int FLOW_CAM_PAD = 64;   // bytes between the two cameras' planes in a stage buffer: N * W is a multiple of 128
+                                   // for the usual widths, and the left and the right lane of a pair read the same
+                                   // columns, i.e. the same banks, of their cameras in one load
 
 using FlowTables = RowTablesT<int16_t>;
 
@@ -57,24 +60,16 @@ __device__ long long g_flow_trace[TRACE_JOBS * 4];   // {type | row << 8 | warp 
 #define FLOW_TRACE_END(type, row) do { } while (0)
 #endif
 
-__device__ __forceinline__ int ld_acquire_s32(const int *p)
-{
-    int v;
-    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(slr::smem_u32(p)) : "memory");
-    return v;
-}
 __device__ __forceinline__ int add_acq_rel_s32(int *p, int v)
 {
     int old;
     asm volatile("atom.acq_rel.cta.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(slr::smem_u32(p)), "r"(v) : "memory");
     return old;
 }
-// the calling warp continues once *ctr >= target (lane 0 polls; the others are held by the warp barrier)
-__device__ __forceinline__ void wait_count(const int *ctr, int target, int lane)
+// one arrival (release) on an mbarrier that counts jobs
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
-    if (lane == 0)
-        while (ld_acquire_s32(ctr) < target) __nanosleep(32);
-    __syncwarp();
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(slr::smem_u32(bar)) : "memory");
 }
 
 // shared-memory bytes of one row context: ent[T] (8 B) + head[T] (4 B) + nxt[2T] (2 B) + left phases [W] (4 B)
@@ -101,14 +96,16 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
     if (R <= 0) return;
 
     // ---- shared memory carve-up ----
-    uint64_t *bar_stage = reinterpret_cast<uint64_t *>(smem);              // [FLOW_STAGES]
-    int *job_ctr = reinterpret_cast<int *>(smem + 32);
-    int *done_d = job_ctr + 1;                                             // [FLOW_CTX] decode jobs completed
-    int *done_q = done_d + FLOW_CTX;                                       // [FLOW_CTX] query jobs completed
-    int *cleared = done_q + FLOW_CTX;                                      // [FLOW_CTX] table clears completed
-    int *done_l = cleared + FLOW_CTX;                                      // [FLOW_CTX] decode jobs done reading the stage
+    uint64_t *bar_stage = reinterpret_cast<uint64_t *>(smem);              // [FLOW_STAGES] a row's bulk copies have landed
+    uint64_t *bar_dec = bar_stage + FLOW_STAGES;                           // [FLOW_CTX] phase u: row 4u+c is decoded (n_d arrivals)
+    uint64_t *bar_clr = bar_dec + FLOW_CTX;                                // [FLOW_CTX] phase u: tables cleared after row 4u+c
+    int *job_ctr = reinterpret_cast<int *>(bar_clr + FLOW_CTX);
+    int *done_q = job_ctr + 1;                                             // [FLOW_CTX] query jobs completed
+    int *done_l = done_q + FLOW_CTX;                                       // [FLOW_CTX] decode jobs done reading the stage
     RowInfo *rowinfo = reinterpret_cast<RowInfo *>(smem + 128);            // [8] ring, indexed by row & 7
-    const size_t stage_bytes = (MODE == MODE_PHASE_INPUT) ? (size_t)10 * W : (size_t)2 * N * W;
+    const size_t tx_bytes = (MODE == MODE_PHASE_INPUT) ? (size_t)10 * W : (size_t)2 * N * W;   // bytes a row's copies bring
+    const int cam_pad = (MODE == MODE_PHASE_INPUT) ? 0 : FLOW_CAM_PAD;
+    const size_t stage_bytes = tx_bytes + cam_pad;
     unsigned char *stage0 = smem + FLOW_HEADER;
     unsigned char *ctx0 = stage0 + FLOW_STAGES * stage_bytes;
     const unsigned ctx_bytes = (unsigned)flow_ctx_bytes(W, T);
@@ -145,9 +142,10 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
         for (int k = tid; k < SLR_BTAB_SIZE; k += nthr) s_btab[k] = p.btab[k];
     }
     for (int c = 0; c < FLOW_CTX; c++) clear_tables(c, tid, nthr);
-    if (tid < 1 + 4 * FLOW_CTX) job_ctr[tid] = 0;
+    if (tid < 1 + 2 * FLOW_CTX) job_ctr[tid] = 0;
     if (tid == 0) {
         for (int s = 0; s < FLOW_STAGES; s++) slr::mbar_init(&bar_stage[s], 1);
+        for (int c = 0; c < FLOW_CTX; c++) slr::mbar_init(&bar_dec[c], (uint32_t)n_d), slr::mbar_init(&bar_clr[c], 1);
         slr::mbar_fence_init();
     }
     const uint64_t policy = make_evict_first_policy();
@@ -162,7 +160,7 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
         if (lane == 0) {
             rowinfo[r & 7].out_px = (unsigned)(((size_t)b * p.H + i) * W);
             rowinfo[r & 7].map_px = (unsigned)((size_t)i * W);
-            slr::mbar_expect_tx(bar, (uint32_t)stage_bytes);   // release: the descriptor is visible to every waiter
+            slr::mbar_expect_tx(bar, (uint32_t)tx_bytes);   // release: the descriptor is visible to every waiter
         }
         __syncwarp();
         if (MODE == MODE_PHASE_INPUT) {  // stage = pL f32[W] | pR f32[W] | mL u8[W] | mR u8[W]
@@ -175,7 +173,7 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
         }
         const uint8_t *src = p.stack + ((size_t)b * 2 * N * p.H + i) * W;
         for (int v = lane; v < 2 * N; v += 32)   // plane v of this scan (cam-major, then image index)
-            tma_load_1d_hint(stage + (size_t)v * W, src + (size_t)v * p.H * W, (uint32_t)W, bar, policy);
+            tma_load_1d_hint(stage + (size_t)v * W + (v >= N ? cam_pad : 0), src + (size_t)v * p.H * W, (uint32_t)W, bar, policy);
         // pull the row that will follow into this stage buffer from HBM into L2 now: its bulk copies are issued the
         // moment this row's decode jobs finish and must land within a step
         if (r + FLOW_STAGES < R) {
@@ -213,7 +211,7 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
             if (r < 0 || r >= R) continue;
             const int c = r & (FLOW_CTX - 1), u = r / FLOW_CTX;
             // this row's tables were cleared by the last query job of row r - FLOW_CTX (first rows: by the prologue)
-            wait_count(&cleared[c], u, lane);
+            if (u > 0) slr::mbar_wait(&bar_clr[c], (uint32_t)((u - 1) & 1));
             slr::mbar_wait(&bar_stage[r % FLOW_STAGES], (uint32_t)((r / FLOW_STAGES) & 1));
             FLOW_TRACE_READY();
             float *s_pl;
@@ -226,7 +224,7 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
                 const bool right = (task & 1) == 0;
                 float ph[4];
                 bool ok[4];
-                load_phases<MODE, 4>(stage, W, N, x0, right, p, s_ptab, s_btab, ph, ok);
+                load_phases<MODE, 4>(stage, W, N, x0, right, p, s_ptab, s_btab, ph, ok, cam_pad);
                 // this job has read its bytes of the stage buffer (the release orders the loads before the count).  The
                 // warp that counts the last reader streams row r + 2 into the buffer: a third of a decode job earlier
                 // than its completion, which is the slack the bulk copies need to land before row r + 2 is drawn.
@@ -247,7 +245,7 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
                                     ok[3] ? ph[3] : slr::qnan());
             }
             __syncwarp();
-            if (lane == 0) add_acq_rel_s32(&done_d[c], 1);
+            if (lane == 0) mbar_arrive(&bar_dec[c]);
             FLOW_TRACE_END(0, r);
         } else {
             // ================= query + emit job (FLOW_QPX * 32 left pixels) of row r = t - 1 - FLOW_LAG =================
@@ -257,7 +255,7 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
             const int qidx = s - n_d;
             if (r < 0 || r >= R) continue;
             const int c = r & (FLOW_CTX - 1), u = r / FLOW_CTX;
-            wait_count(&done_d[c], (u + 1) * n_d, lane);
+            slr::mbar_wait(&bar_dec[c], (uint32_t)(u & 1));
             FLOW_TRACE_READY();
             const RowInfo ri = rowinfo[r & 7];
             float *s_pl;
@@ -273,8 +271,8 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
                 uly[q] = inside ? __ldg(p.ly + ri.map_px + j[q]) : 0.0f;
                 v[q] = inside ? s_pl[j[q]] : slr::qnan();
             }
-#pragma unroll
-            for (int q = 0; q < FLOW_QPX; q++) best[q] = (v[q] != v[q]) ? INT_MAX : first_match<CLAMP>(tab, v[q]);
+            static_assert(FLOW_QPX == 2, "the query job walks two chains per lane");
+            first_match_x2<CLAMP>(tab, v[0], v[1], best[0], best[1]);
             float d[FLOW_QPX], X[FLOW_QPX], Y[FLOW_QPX], Z[FLOW_QPX];
 #pragma unroll
             for (int q = 0; q < FLOW_QPX; q++) {
@@ -334,7 +332,7 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
             if (last) {  // nobody reads this row's tables any more: clear them for row r + FLOW_CTX
                 clear_tables(c, lane, 32);
                 __syncwarp();
-                if (lane == 0) add_acq_rel_s32(&cleared[c], 1);
+                if (lane == 0) mbar_arrive(&bar_clr[c]);
             }
             FLOW_TRACE_END(last ? 2 : 1, r);
         }
@@ -356,7 +354,7 @@ slr_status slr_launch_fused_flow(slr_engine *e, int mode, const FusedParams &p_i
         if (atoi(ev) == 0) return SLR_OK;
     FusedParams p = p_in;
     const int W = p.W;
-    const size_t stage_bytes = (mode == MODE_PHASE_INPUT) ? (size_t)10 * W : (size_t)2 * p.N * W;
+    const size_t stage_bytes = (mode == MODE_PHASE_INPUT) ? (size_t)10 * W : (size_t)2 * p.N * W + FLOW_CAM_PAD;
     const size_t smem = FLOW_HEADER + FLOW_STAGES * stage_bytes + FLOW_CTX * flow_ctx_bytes(W, p.T) +
                         SLR_PTAB_SIZE * 4 + SLR_BTAB_SIZE * 4;
     const int n_d = (W / 2 + 31) / 32, n_q = (W + 32 * FLOW_QPX - 1) / (32 * FLOW_QPX);
@@ -372,9 +370,11 @@ slr_status slr_launch_fused_flow(slr_engine *e, int mode, const FusedParams &p_i
     const int ctas = (2 * (smem + 1024) <= 228 * 1024) ? 2 : 1;
     int warps = 32 / ctas;
     while (warps > 2 && warps > n_d + n_q) warps >>= 1;
+    // (the mbarrier phases stay unambiguous only while a CTA has no more warps than one step has jobs: a stuck row then
+    // blocks every warp before any of them can reach the jobs of the row that reuses its context)
     if (const char *ev = getenv("SLR_FLOW_WARPS")) {
         const int w = atoi(ev);
-        if (w >= 1 && w <= 32 / ctas) warps = w;
+        if (w >= 1 && w <= 32 / ctas && w <= (n_d + n_q > 2 ? n_d + n_q : 2)) warps = w;
     }
     void (*kern)(const FusedParams, int, int, unsigned) = (mode == SLR_MODE_STRICT)      ? k_fused_flow<SLR_MODE_STRICT>
                                                 : (mode == SLR_MODE_CORRECTED) ? k_fused_flow<SLR_MODE_CORRECTED>

@@ -193,7 +193,7 @@ __device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return __byte_p
 // integer arithmetic followed by ONE rounding (I2F), which is what narrowing the exact double to float does.
 //
 //   btab[b + 256], b = G1-G3 in [-255, 255]:  bits 0..16  M = floor(65536/|b|) + 1   (b == 0: 65536)
-//                                             bits 17..   first ptab row of this sign of b, times 256
+//                                             bits 17..   first ptab entry of the first row of this sign of b
 //   q = (|a| * M) >> 16 == floor(|a| / |b|) for 0 <= |a|, |b| <= 255 (b == 0: q = |a|): the excess |a|/65536 < 1/256
 //       <= 1/|b| can never reach the next integer because a non-integer quotient has a fractional part <= 1 - 1/|b|.
 //   ptab rows (256 entries, index q; C++ int division truncates toward zero, so the signed quotient is +-q):
@@ -203,8 +203,12 @@ __device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return __byte_p
 //     3: b < 0, a >  0   atan(float(-q)) + PI       (:257)
 //     4: b == 0, a <= 0  PI/2 (:252); entry 0 (a == 0: the degenerate branch :254) = SLR_PTAB_DEGENERATE
 //     5: b == 0, a >  0  3*PI/2 (:250)
+// Rows start SLR_PTAB_STRIDE = 256 + 8 words apart: the quotient is 0..7 for nine pixels in ten, and with the skew the
+// entries q = 0..7 of rows 0..3 (the four sign cases a warp mixes freely) occupy 32 distinct shared-memory banks instead
+// of four words each in banks 0..7.
 #define SLR_PTAB_ROWS 6
-#define SLR_PTAB_SIZE (SLR_PTAB_ROWS * 256)
+#define SLR_PTAB_STRIDE 264
+#define SLR_PTAB_SIZE (SLR_PTAB_ROWS * SLR_PTAB_STRIDE)
 #define SLR_BTAB_SIZE 512
 #define SLR_PTAB_DEGENERATE INT_MIN
 
@@ -213,7 +217,7 @@ __device__ __forceinline__ int wrapped_strict_fx(int a, int b, const int *__rest
 {
     const uint32_t t = btab[b + 256];
     const uint32_t q = ((uint32_t)abs(a) * (t & 0x1FFFFu)) >> 16;
-    return ptab[(t >> 17) + q + ((a > 0) ? 256u : 0u)];
+    return ptab[(t >> 17) + q + ((a > 0) ? (unsigned)SLR_PTAB_STRIDE : 0u)];
 }
 
 // Heterodyne of :265-268 on fixed-point wrapped phases.  I0 - I1 (+ 2*PI) is exact in int32 (|I| < 2^27), and
