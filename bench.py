@@ -175,6 +175,26 @@ def make_host_inputs(n_scans, rank, noise_dn=0.0, integer_disparity=True):
                                     noise_dn=noise_dn) for s in range(n_scans)])
 
 
+def rectify_maps_numpy(W, H):
+    """CV_16SC2 maps as cv::convertMaps / cv::initUndistortRectifyMap produce them (integer source pixel + 5+5 fractional
+    bits), for a small rotation + scale + lens-like bow of each camera: int16 [2][H][W][2], uint16 [2][H][W]."""
+    import numpy as np
+    xs, ys = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64))
+    m1, m2 = [], []
+    for cam in range(2):
+        th = (0.4 - 0.8 * cam) * np.pi / 180
+        cx, cy = W / 2, H / 2
+        dx, dy = xs - cx, ys - cy
+        r2 = (dx * dx + dy * dy) / (cx * cx + cy * cy)
+        sc = 1.004 + 0.01 * r2
+        mx = cx + sc * (np.cos(th) * dx - np.sin(th) * dy) + 1.5
+        my = cy + sc * (np.sin(th) * dx + np.cos(th) * dy) - 0.75
+        ix, iy = np.rint(mx * 32).astype(np.int64), np.rint(my * 32).astype(np.int64)
+        m1.append(np.stack([ix >> 5, iy >> 5], -1).astype(np.int16))
+        m2.append(((iy & 31) * 32 + (ix & 31)).astype(np.uint16))
+    return np.stack(m1), np.stack(m2)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU arms: the reference's own code (oracle/_ref/libref.so = Duke/*.cpp compiled unmodified against oracle/ref_shim)
 # and the oracle port of the same loops.  Only bench legs that are reported as baselines call into oracle/.
@@ -423,12 +443,37 @@ def main():
                              "ms_per_step": ms / v_steps, "points_per_step": pts,
                              "roofline_frac": alg / (statistics.mean(per) * 1e-3) / 1e9 / peak})
         del noisy
+        # RAW camera stacks: rectification inside the fused kernel's stage fill (slr_run_mf_raw, one
+        # kernel) against K0 into HBM followed by the fused kernel (two kernels, the stack written and read once more)
+        m1, m2 = rectify_maps_numpy(W, H)
+        eng.set_rectify_maps(m1, m2)
+        raw_leg = {}
+        for name, fn in (("fused", lambda: eng.run_mf_raw(stack, F, S, BLACK_THR, mode, out=out)),
+                         ("k0_then_fused", lambda: eng.run_mf(eng.rectify_stack(stack, out=rect_buf), F, S, BLACK_THR, mode, out=out))):
+            if name == "k0_then_fused":
+                rect_buf = torch.empty_like(stack)
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            l0 = eng.launches()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(v_steps):
+                out[4].zero_()
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / v_steps
+            raw_leg[name] = {"ms_per_step": ms, "value": int(out[4].item()) / (ms * 1e-3) / 1e6, "unit": UNIT,
+                             "kernels_per_step": (eng.launches() - l0) / v_steps,
+                             "roofline_frac": (alg + 2 * W * H * 6) / (ms * 1e-3) / 1e9 / peak}
+        del rect_buf
         # single-scan latency (one scan is launch- and tail-bound, far below the L2 size)
         one = eng._outputs(1, want_k=False)
         ms, per, _, _ = timed_steps(stack[:1], 20, mode, one)
         single_scan_ms = statistics.median(per)
     else:
-        single_scan_ms = None
+        single_scan_ms, raw_leg = None, None
 
     # ---- N > 1: assemble every rank's cloud on every rank ----
     gather = {}
@@ -576,6 +621,10 @@ def main():
             config["variants"] = variants
         if single_scan_ms is not None:
             config["single_scan_latency_ms"] = single_scan_ms
+            config["raw_input"] = dict(raw_leg, note="the same stacks taken as RAW camera images: stereoRect::doStereoRectify "
+                                       "(cv::remap, CV_16SC2 maps of a 0.4 degree / 0.4 % warp) inside the fused kernel's "
+                                       "stage fill vs as a separate pass; algorithmic bytes = the step's + 6 map bytes per "
+                                       "pixel and camera")
         result = {
             "metric": METRIC, "value": points_all / (ms_per_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -162,6 +162,13 @@ SLR_API slr_status slr_bucket_triangulate(slr_engine *e, const int32_t *d_col, c
 SLR_API slr_status slr_run_mf(slr_engine *e, const uint8_t *d_stack, int batch, int F, int S,
                               int black_thr, int mode, float *d_xyz, uint8_t *d_valid,
                               int32_t *d_match_k, unsigned long long *d_n_points);
+/* The same on RAW (un-rectified) camera stacks: stereoRect::doStereoRectify of every image (Duke/stereorect.cpp:26-34,
+ * called per image by MFReconstruct::loadCamImgs, Duke/mfreconstruct.cpp:127-134) happens while the fused kernel fills
+ * its shared-memory stage — raw bytes are read once, the rectified images never exist in HBM, one kernel per call
+ * (SURVEY.md 8f row N1).  Needs slr_set_rectify_maps.  d_raw_stack = [batch][2][2+F*S][H][W]. */
+SLR_API slr_status slr_run_mf_raw(slr_engine *e, const uint8_t *d_raw_stack, int batch, int F, int S,
+                                  int black_thr, int mode, float *d_xyz, uint8_t *d_valid,
+                                  int32_t *d_match_k, unsigned long long *d_n_points);
 /* Reconstruct::runReconstruction_GE minus image IO, Duke/reconstruct.cpp:271-307 (K2 then K3b through engine
  * scratch; integer codes make the intermediate cheap: 5 bytes per pixel). */
 SLR_API slr_status slr_run_ge(slr_engine *e, const uint8_t *d_stack, int batch, int nbits_col,
@@ -181,6 +188,29 @@ SLR_API slr_status slr_run_ge_host(slr_engine *e, const uint8_t *h_stack, int ba
                                    int black_thr, int white_thr, int scan_w, int have_color,
                                    float *h_xyz, uint8_t *h_valid, int32_t *h_match_k, uint8_t *h_color,
                                    unsigned long long *h_n_points);
+/* ---- PNG ingest ---------------------------------------------------------------
+ * MFReconstruct::loadCamImgs' cv::imread(path, 0) of every scan image (Duke/mfreconstruct.cpp:119-134) split where the
+ * work stops being sequential: the caller inflates each image's zlib stream on a host thread (one stream per thread) and
+ * hands over the bytes exactly as the stream holds them; copy, PNG unfiltering, rectification, decode, match and
+ * triangulation run on the GPU while the remaining images are still being inflated.
+ *   slr_ingest_begin   start a scan of n_images = 2 * (2 + F*S) images (index = cam * N + i)
+ *   slr_ingest_image   one image, from pinned host memory, asynchronously.  filtered != 0: h_data = H scanlines of
+ *                      [filter type byte][W filtered bytes] (8-bit grey, filter types 0 / 1 / 2 only; has_up_rows != 0 when
+ *                      a row uses type 2); filtered == 0: h_data = H*W finished pixels (other formats, or images with
+ *                      Average / Paeth rows, decoded by the caller).  h_data must stay valid until slr_run_mf_ingested
+ *                      returns.  Calls may come from any host thread, one at a time.
+ *   slr_run_mf_ingested  run the MF pipeline on the ingested scan (raw input + rectification in the fused kernel when
+ *                      slr_set_host_input_raw is on) and return the cloud as h_xyz / h_valid (as slr_run_mf_host) and /
+ *                      or in the storage layout of the reference's PointCloudImage(scan_w, scan_h) after
+ *                      MFReconstruct::triangulation's addPoint(i, j, p) calls (Duke/mfreconstruct.cpp:326,
+ *                      Duke/pointcloudimage.cpp:86-97): h_sum = float [scan_h][scan_w][3], h_cnt = uint8 [scan_h][scan_w],
+ *                      cell (i_w = image row, j_h = image column), points with i_w >= scan_w or j_h >= scan_h dropped.
+ *                      Either output pair may be NULL.  Synchronous. */
+SLR_API slr_status slr_ingest_begin(slr_engine *e, int n_images);
+SLR_API slr_status slr_ingest_image(slr_engine *e, int index, const uint8_t *h_data, int filtered, int has_up_rows);
+SLR_API slr_status slr_run_mf_ingested(slr_engine *e, int F, int S, int black_thr, int mode, int scan_w, int scan_h,
+                                       float *h_sum, uint8_t *h_cnt, float *h_xyz, uint8_t *h_valid,
+                                       unsigned long long *h_n_points);
 /* Reconstruct::runReconstruction minus image IO (Gray-only: column + row codes on UN-rectified images, ray-ray
  * triangulation), Duke/reconstruct.cpp:230-265.  h_stack = [batch][2][2+2*nbits_col+2*nbits_row][H][W];
  * h_sum = float [batch][scan_w*scan_h][3], h_cnt = uint8 [batch][scan_w*scan_h], indexed ac(x,y) = x*scan_h + y. */

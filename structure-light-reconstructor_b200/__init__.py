@@ -63,6 +63,7 @@ EXPORTS = [
     "slr_peer_free", "slr_set_gather_targets", "slr_set_row_offset", "slr_synth_gray",
     "slr_kernel_launches", "slr_mesh_index", "slr_mesh_index_host", "slr_allgather", "slr_nccl_unique_id",
     "slr_nccl_comm_create", "slr_nccl_comm_destroy", "slr_set_rectify_maps", "slr_rectify_stack", "slr_set_host_input_raw", "slr_run_gray_host",
+    "slr_run_mf_raw", "slr_ingest_begin", "slr_ingest_image", "slr_run_mf_ingested",
 ]
 
 
@@ -93,6 +94,10 @@ def capi():
     lib.slr_match_triangulate_code.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, u64p]
     lib.slr_bucket_triangulate.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, u64p]
     lib.slr_run_mf.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, u64p]
+    lib.slr_run_mf_raw.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, u64p]
+    lib.slr_ingest_begin.argtypes = [vp, i32]
+    lib.slr_ingest_image.argtypes = [vp, i32, vp, i32, i32]
+    lib.slr_run_mf_ingested.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(C.c_ulonglong)]
     lib.slr_run_ge.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, u64p]
     lib.slr_run_mf_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, C.POINTER(C.c_ulonglong)]
     lib.slr_run_ge_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp,
@@ -231,8 +236,8 @@ class Engine:
         _check(self.lib.slr_set_rectify_maps(self.h, C.c_void_p(m1.ctypes.data), C.c_void_p(m2.ctypes.data)),
                "slr_set_rectify_maps")
 
-    def rectify_stack(self, raw):
-        out = self._torch.empty_like(raw)
+    def rectify_stack(self, raw, out=None):
+        out = self._torch.empty_like(raw) if out is None else out
         B, _, N = raw.shape[:3]
         self._bind_stream()
         _check(self.lib.slr_rectify_stack(self.h, self._p(raw), B, N, self._p(out)), "slr_rectify_stack")
@@ -324,6 +329,15 @@ class Engine:
                                    self._p(k), self._p(n)), "slr_run_mf")
         return xyz, valid, k, n
 
+    def run_mf_raw(self, raw_stack, F=3, S=4, black_thr=40, mode=MODE_STRICT, want_k=True, out=None):
+        """slr_run_mf_raw: RAW camera stacks in, rectification inside the fused kernel's stage fill."""
+        B = raw_stack.shape[0]
+        xyz, valid, k, _, n = out if out is not None else self._outputs(B, want_k)
+        self._bind_stream()
+        _check(self.lib.slr_run_mf_raw(self.h, self._p(raw_stack), B, F, S, black_thr, mode, self._p(xyz),
+                                       self._p(valid), self._p(k), self._p(n)), "slr_run_mf_raw")
+        return xyz, valid, k, n
+
     def run_ge(self, stack, nbits_col, black_thr=40, white_thr=0, scan_w=None, have_color=False, want_k=True,
                out=None):
         B = stack.shape[0]
@@ -350,6 +364,23 @@ class Engine:
         _check(self.lib.slr_run_mf_host(self.h, self._hp(h_stack), B, F, S, black_thr, mode, self._hp(h_xyz),
                                         self._hp(h_valid), self._hp(h_k), C.byref(n)), "slr_run_mf_host")
         return int(n.value)
+
+    def run_mf_ingested(self, images, filtered, h_sum=None, h_cnt=None, h_xyz=None, h_valid=None, scan_w=0, scan_h=0,
+                        F=3, S=4, black_thr=40, mode=MODE_STRICT) -> int:
+        """slr_ingest_begin + slr_ingest_image per image + slr_run_mf_ingested.  images[k] = numpy uint8 host array of
+        image k (cam * N + i): [H, 1 + W] PNG scanlines when filtered[k], else [H, W] pixels."""
+        self._bind_stream()
+        _check(self.lib.slr_ingest_begin(self.h, len(images)), "slr_ingest_begin")
+        keep = []
+        for k, (img, f) in enumerate(zip(images, filtered)):
+            a = np.ascontiguousarray(img, np.uint8)
+            keep.append(a)
+            up = int(bool(f) and bool((a[:, 0] == 2).any()))
+            _check(self.lib.slr_ingest_image(self.h, k, C.c_void_p(a.ctypes.data), int(bool(f)), up), "slr_ingest_image")
+        n = C.c_ulonglong(0)
+        _check(self.lib.slr_run_mf_ingested(self.h, F, S, black_thr, mode, scan_w, scan_h, self._hp(h_sum), self._hp(h_cnt),
+                                            self._hp(h_xyz), self._hp(h_valid), C.byref(n)), "slr_run_mf_ingested")
+        return n.value
 
     def run_ge_host(self, h_stack, h_xyz, h_valid, h_k=None, h_color=None, nbits_col=11, black_thr=40, white_thr=0,
                     scan_w=None) -> int:

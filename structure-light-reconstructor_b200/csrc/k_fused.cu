@@ -320,7 +320,8 @@ static size_t fused_smem_bytes(size_t stage_bytes, int W, int T)
 // shared launcher: mode = SLR_MODE_STRICT | SLR_MODE_CORRECTED (image stacks) or MODE_PHASE_INPUT (phase + mask rows)
 static slr_status launch_fused(slr_engine *e, int mode, const uint8_t *d_stack, const float *d_phase,
                                const uint8_t *d_mask, int batch, int F, int S, int black_thr, float *d_xyz,
-                               uint8_t *d_valid, int32_t *d_match_k, unsigned long long *d_n_points, bool *handled)
+                               uint8_t *d_valid, int32_t *d_match_k, unsigned long long *d_n_points, bool *handled,
+                               bool raw = false)
 {
     *handled = false;
     const int W = e->W, N = 2 + F * S;
@@ -348,6 +349,8 @@ static slr_status launch_fused(slr_engine *e, int mode, const uint8_t *d_stack, 
     if (const char *ev = getenv("SLR_FUSED_QPX")) qpx = atoi(ev) == 2 ? 2 : 1;
     FusedParams p;
     p.stack = d_stack;
+    p.map1 = raw ? reinterpret_cast<const short2 *>(e->d_map1) : nullptr;
+    p.map2 = raw ? e->d_map2 : nullptr;
     p.phase = d_phase;
     p.mask = d_mask;
     p.W = W;
@@ -396,6 +399,10 @@ static slr_status launch_fused(slr_engine *e, int mode, const uint8_t *d_stack, 
         if (st != SLR_OK || flow) return st;
     }
 #endif
+    if (raw) {   // only the dataflow kernel rectifies on load
+        *handled = false;
+        return SLR_OK;
+    }
 
     void (*kern)(const FusedParams);
 #define SLR_PICK_Q(MAXT, MINB, Q)                                                                                 \
@@ -474,6 +481,38 @@ slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch,
                                  d_n_points, &handled);
     if (st != SLR_OK || handled) return st;
     return slr_unfused_mf(e, d_stack, batch, F, S, black_thr, mode, d_xyz, d_valid, d_match_k, d_n_points);
+}
+
+// RAW camera stacks in, XYZ out: stereoRect::doStereoRectify folded into the fused kernel's stage fill (k_fused_flow<RAW>).
+// Shapes that kernel does not take are rectified by K0 into engine scratch, scan by scan, and then run as usual.
+slr_status slr_launch_fused_mf_raw(slr_engine *e, const uint8_t *d_raw, int batch, int F, int S, int black_thr, int mode,
+                                   float *d_xyz, uint8_t *d_valid, int32_t *d_match_k, unsigned long long *d_n_points)
+{
+    const size_t P = (size_t)e->W * e->H, in_bytes = (size_t)2 * (2 + F * S) * P;
+    const bool shape_ok = (mode == SLR_MODE_STRICT) ? (F == 3 && S == 4)
+                                                     : (mode == SLR_MODE_CORRECTED && F >= 1 && F <= 8 && S >= 3 && S <= 16);
+    if (shape_ok && e->W % 16 == 0 && !slr_misaligned16(d_raw, d_xyz, d_valid, d_match_k)) {
+        bool handled = false;
+        const slr_status st = launch_fused(e, mode, d_raw, nullptr, nullptr, batch, F, S, black_thr, d_xyz, d_valid,
+                                           d_match_k, d_n_points, &handled, true);
+        if (st != SLR_OK || handled) return st;
+    }
+    if (e->stage_rect_bytes < in_bytes) {
+        for (int k = 0; k < 2; k++) {
+            if (e->d_stage_rect[k]) SLR_CHECK_CUDA(cudaFree(e->d_stage_rect[k]));
+            e->d_stage_rect[k] = nullptr;
+            SLR_CHECK_CUDA(cudaMalloc(&e->d_stage_rect[k], in_bytes));
+        }
+        e->stage_rect_bytes = in_bytes;
+    }
+    for (int b = 0; b < batch; b++) {
+        slr_status st = slr_launch_rectify(e, d_raw + (size_t)b * in_bytes, 1, 2 + F * S, e->d_stage_rect[0]);
+        if (st != SLR_OK) return st;
+        st = slr_launch_fused_mf(e, e->d_stage_rect[0], 1, F, S, black_thr, mode, d_xyz + (size_t)b * P * 3,
+                                 d_valid + (size_t)b * P, d_match_k ? d_match_k + (size_t)b * P : nullptr, d_n_points);
+        if (st != SLR_OK) return st;
+    }
+    return SLR_OK;
 }
 
 // K3a through the same kernel: rows of decoded phase + mask in, XYZ out (slr_match_triangulate_phase).

@@ -16,6 +16,10 @@ constexpr int MODE_PHASE_INPUT = 2;  // rows of already decoded phase + mask (sl
 
 struct FusedParams {
     const uint8_t *stack;  // [batch][2][N][H][W]
+    // k_fused_flow<RAW>: `stack` holds the RAW camera images and is rectified on the way into shared memory with the
+    // CV_16SC2 maps of cv::initUndistortRectifyMap, [cam][H][W] each (NULL: the stack is rectified already)
+    const short2 *map1;
+    const uint16_t *map2;
     const float *phase;    // MODE_PHASE_INPUT: [batch][2][H][W]
     const uint8_t *mask;   // MODE_PHASE_INPUT: [batch][2][H][W]
     int W, H, batch, F, S, N;

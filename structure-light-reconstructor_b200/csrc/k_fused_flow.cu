@@ -20,6 +20,14 @@
 // query(r-4) and the stage re-armed after decode(r-2); query(r) needs decode(r).  A waiting warp sleeps in
 // mbarrier.try_wait (no issue slots, no shared-memory polling).  The warp whose decode job is the last to have read a
 // row's stage buffer re-arms it with the TMA copies of row r+2.
+//
+// RAW = true (slr_run_mf_raw): the stack holds the RAW camera images and the stage buffer is not
+// filled by bulk copies but by a third kind of job, listed one step ahead of the row's decode jobs: rectify jobs
+// evaluate stereoRect::doStereoRectify = cv::remap(INTER_LINEAR, CV_16SC2 maps) (Duke/stereorect.cpp:26-34) for 128
+// pixels of one camera's row and all N planes — map entries read once, four aligned 32-bit loads per plane for the
+// 2 x 8-byte tap window of four pixels, OpenCV's fixed-point blend as two DP2A — straight into the stage buffer, so the
+// rectified images never exist in HBM: raw bytes in, XYZ out, one kernel.  Rows are walked image-row-fastest there, so
+// that the two source rows an output row blends are still in L2 for the next output row.
 #include <limits.h>
 #include <stdlib.h>
 
@@ -34,6 +42,7 @@ constexpr int FLOW_LAG = 2;        // steps between a row's decode jobs and its 
 constexpr int FLOW_STAGES = 2;     // TMA stage buffers
 constexpr int FLOW_QPX = 2;        // left pixels per lane in one query job
 constexpr int FLOW_HEADER = 256;   // mbarriers, counters, row descriptors
+constexpr int FLOW_RAW_LEAD = 3;   // RAW: rows between the L2 prefetch of a source row and the row that blends it
 constexpr int FLOW_CAM_PAD = 64;   // bytes between the two cameras' planes in a stage buffer: N * W is a multiple of 128
                                    // for the usual widths, and the left and the right lane of a pair read the same
                                    // columns, i.e. the same banks, of their cameras in one load
@@ -80,16 +89,145 @@ struct RowInfo {
     unsigned out_px, map_px;
 };
 
-template <int MODE>
+// OpenCV's fixed-point bilinear weights of one CV_16SC2 map entry (5 + 5 fractional bits), as two pairs of 16-bit lanes
+// for DP2A: (32-fx)(32-fy)*32 ... = 2^15-scaled shorts; the (0,0) entry saturates to 32767 and cv::remap's table fix-up
+// gives the missing 1 to the diagonal tap.
+__device__ __forceinline__ void remap_weights(uint32_t m2, uint32_t &w01, uint32_t &w23)
+{
+    const int a = (int)(m2 & 1023u), fx = a & 31, fy = a >> 5;
+    int w0 = (32 - fx) * (32 - fy) * 32, w1 = fx * (32 - fy) * 32, w2 = (32 - fx) * fy * 32, w3 = fx * fy * 32;
+    if (a == 0) w0 = 32767, w3 = 1;
+    w01 = (uint32_t)w0 | ((uint32_t)w1 << 16);
+    w23 = (uint32_t)w2 | ((uint32_t)w3 << 16);
+}
+
+// A rectify job: cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) of 128 consecutive output pixels of row i of one camera, all
+// N planes, written to the stage rows; called by the whole warp, lane l owns the four pixels x .. x+3 (active = x < W),
+// dst = stage address of pixel x of plane 0.  Same arithmetic as k0_rectify.cu (the stand-alone K0).
+//
+// Rectification maps are smooth: a lane's four pixels almost always read the same two source rows and source columns
+// that fit one aligned 8-byte window, so a plane costs it four aligned 32-bit loads, a PRMT per pixel and row, two DP2A
+// per pixel and one 32-bit shared-memory store.  The source row of a slightly rotated camera changes every hundred
+// pixels or so, i.e. in about ONE lane of most warps; a per-lane fallback would make the whole warp sit through its
+// 14 x 4 x 4 byte loads, so the lanes that do not fit are served by the warp together afterwards: one (plane, pixel)
+// item per lane, the map entry re-read (it is in L1), four byte taps, one byte stored.
+__device__ __forceinline__ void rectify_job(const uint8_t *__restrict__ sv /* raw [N][H][W] of this scan + camera */,
+                                            const short2 *__restrict__ map1, const uint16_t *__restrict__ map2 /* this camera */,
+                                            int W, int H, int N, int i, int x, bool active, unsigned char *dst, int lane)
+{
+    const size_t P = (size_t)W * H;
+    const size_t o = (size_t)i * W + x;
+    bool fast = false;
+    int sx[4], sy[4], bx = 0;
+    uint32_t w01[4], w23[4];
+    if (active) {
+        const uint4 m1 = __ldg(reinterpret_cast<const uint4 *>(map1 + o));   // 4 x short2
+        const uint2 m2 = __ldg(reinterpret_cast<const uint2 *>(map2 + o));   // 4 x u16
+        const uint32_t m1w[4] = {m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            sx[k] = (int)(short)(m1w[k] & 0xffffu);
+            sy[k] = (int)(short)(m1w[k] >> 16);
+            remap_weights((k < 2 ? m2.x : m2.y) >> (16 * (k & 1)), w01[k], w23[k]);
+        }
+        bx = sx[0] & ~3;   // aligned window [bx, bx+8) x rows {sy0, sy0+1}
+        fast = bx >= 0 && bx + 8 <= W && sy[0] >= 0 && sy[0] + 1 < H;
+#pragma unroll
+        for (int k = 0; k < 4; k++) fast = fast && sy[k] == sy[0] && sx[k] >= bx && sx[k] + 1 < bx + 8;
+    }
+    const unsigned fmask = __ballot_sync(0xffffffffu, fast);             // the lanes on the fast path
+    {
+        if (fast) {
+            uint32_t sel[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t off = (uint32_t)(sx[k] - bx);            // 0..6
+                sel[k] = off | ((off + 1u) << 4) | 0x4400u;
+            }
+            const uint8_t *q = sv + (size_t)sy[0] * W + bx;              // 4-byte aligned
+            // An output row needs one source row per plane that no earlier row has touched (the lower tap row): pull the
+            // one the row FLOW_RAW_LEAD steps ahead will need from HBM into L2 now (one 32-byte sector per 8 lanes).
+            if ((lane & 7) == 0 && sy[0] + 1 + FLOW_RAW_LEAD < H) {
+                const uint8_t *pf = q + (size_t)(1 + FLOW_RAW_LEAD) * W;
+                for (int n = 0; n < N; n++, pf += P) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+            }
+            // The job is bound by how many loads it keeps in flight (L2 latency x 14 planes), so a lane loads only the
+            // FIRST word of its two window rows and takes the second from its right neighbour, whose window usually
+            // starts right there; four planes' loads are issued before the first blend.
+            const int nsy = __shfl_down_sync(fmask, sy[0], 1), nbx = __shfl_down_sync(fmask, bx, 1);
+            const bool share = lane < 31 && ((fmask >> (lane + 1)) & 1u) && nsy == sy[0] && nbx == bx + 4;
+            auto blend_store = [&](int n, uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
+                uint32_t r[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t t0 = __byte_perm(a0, a1, sel[k]), t1 = __byte_perm(b0, b1, sel[k]);
+                    uint32_t acc = __dp2a_lo(w01[k], t0, 1u << 14);     // p00*w0 + p01*w1 + 2^14
+                    acc = __dp2a_lo(w23[k], t1, acc);                   // + p10*w2 + p11*w3
+                    r[k] = acc >> 15;
+                }
+                *reinterpret_cast<uint32_t *>(dst + (size_t)n * W) =
+                    __byte_perm(__byte_perm(r[0], r[1], 0x0040), __byte_perm(r[2], r[3], 0x0040), 0x5410);
+            };
+            constexpr int DEPTH = 4;
+            for (int n0 = 0; n0 < N; n0 += DEPTH) {
+                uint32_t a0[DEPTH], b0[DEPTH], a1[DEPTH], b1[DEPTH];
+#pragma unroll
+                for (int d = 0; d < DEPTH; d++) {
+                    a0[d] = b0[d] = a1[d] = b1[d] = 0u;
+                    if (n0 + d < N) {
+                        const uint8_t *qd = q + (size_t)(n0 + d) * P;
+                        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(a0[d]) : "l"(qd));
+                        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(b0[d]) : "l"(qd + W));
+                        if (!share) {
+                            asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(a1[d]) : "l"(qd + 4));
+                            asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(b1[d]) : "l"(qd + W + 4));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < DEPTH; d++) {
+                    const uint32_t na = __shfl_down_sync(fmask, a0[d], 1), nb = __shfl_down_sync(fmask, b0[d], 1);
+                    if (n0 + d < N) blend_store(n0 + d, a0[d], share ? na : a1[d], b0[d], share ? nb : b1[d]);
+                }
+            }
+        }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, active && !fast);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int xs = __shfl_sync(0xffffffffu, x, src);
+        const unsigned dsts = __shfl_sync(0xffffffffu, slr::smem_u32(dst), src);
+        for (int item = lane; item < 4 * N; item += 32) {
+            const int n = item >> 2, k = item & 3;
+            const size_t ok = (size_t)i * W + xs + k;
+            const short2 m = __ldg(map1 + ok);
+            uint32_t w01, w23;
+            remap_weights(__ldg(map2 + ok), w01, w23);
+            const int sx = m.x, sy = m.y;
+            const bool in0 = (unsigned)sx < (unsigned)W, in1 = (unsigned)(sx + 1) < (unsigned)W;
+            const bool iy0 = (unsigned)sy < (unsigned)H, iy1 = (unsigned)(sy + 1) < (unsigned)H;
+            const uint8_t *pl = sv + (size_t)n * P + ((long long)sy * W + sx);
+            const uint32_t p00 = (in0 && iy0) ? __ldg(pl) : 0u, p01 = (in1 && iy0) ? __ldg(pl + 1) : 0u;
+            const uint32_t p10 = (in0 && iy1) ? __ldg(pl + W) : 0u, p11 = (in1 && iy1) ? __ldg(pl + W + 1) : 0u;
+            uint32_t acc = __dp2a_lo(w01, p00 | (p01 << 8), 1u << 14);
+            acc = __dp2a_lo(w23, p10 | (p11 << 8), acc);
+            const unsigned a = dsts + (unsigned)(n * W + k);
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(acc >> 15) : "memory");
+        }
+    }
+}
+
+template <int MODE, bool RAW>
 __global__ void __launch_bounds__(1024, 1)
-k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned js_magic)
+k_fused_flow(const FusedParams p, const int n_r, const int n_d, const int n_q, const unsigned js_magic)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool CLAMP = MODE == MODE_PHASE_INPUT;
     const int W = p.W, N = p.N, T = p.T;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
 
-    // this CTA's contiguous range of rows rg = i * batch + b (scan index b fastest)
+    // this CTA's contiguous range of rows rg = i * batch + b (scan index b fastest; RAW: rg = b * H + i)
     const long long rows = (long long)p.batch * p.H;
     const long long r_begin = rows * blockIdx.x / gridDim.x, r_end = rows * (blockIdx.x + 1) / gridDim.x;
     const int R = (int)(r_end - r_begin);
@@ -99,6 +237,7 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
     uint64_t *bar_stage = reinterpret_cast<uint64_t *>(smem);              // [FLOW_STAGES] a row's bulk copies have landed
     uint64_t *bar_dec = bar_stage + FLOW_STAGES;                           // [FLOW_CTX] phase u: row 4u+c is decoded (n_d arrivals)
     uint64_t *bar_clr = bar_dec + FLOW_CTX;                                // [FLOW_CTX] phase u: tables cleared after row 4u+c
+    uint64_t *bar_free = reinterpret_cast<uint64_t *>(smem + 192);         // [FLOW_STAGES] RAW: a row's decode jobs have read the stage
     int *job_ctr = reinterpret_cast<int *>(bar_clr + FLOW_CTX);
     int *done_q = job_ctr + 1;                                             // [FLOW_CTX] query jobs completed
     int *done_l = done_q + FLOW_CTX;                                       // [FLOW_CTX] decode jobs done reading the stage
@@ -136,7 +275,7 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
         for (int q = first; q < (T >> 2); q += stride) h4[q] = m4;
     };
 
-    const int JS = n_d + n_q;
+    const int JS = n_r + n_d + n_q;
     if (MODE == SLR_MODE_STRICT) {
         for (int k = tid; k < SLR_PTAB_SIZE; k += nthr) s_ptab[k] = p.ptab[k];
         for (int k = tid; k < SLR_BTAB_SIZE; k += nthr) s_btab[k] = p.btab[k];
@@ -144,7 +283,8 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
     for (int c = 0; c < FLOW_CTX; c++) clear_tables(c, tid, nthr);
     if (tid < 1 + 2 * FLOW_CTX) job_ctr[tid] = 0;
     if (tid == 0) {
-        for (int s = 0; s < FLOW_STAGES; s++) slr::mbar_init(&bar_stage[s], 1);
+        for (int s = 0; s < FLOW_STAGES; s++) slr::mbar_init(&bar_stage[s], RAW ? (uint32_t)n_r : 1u);
+        for (int s = 0; s < FLOW_STAGES; s++) slr::mbar_init(&bar_free[s], (uint32_t)n_d);
         for (int c = 0; c < FLOW_CTX; c++) slr::mbar_init(&bar_dec[c], (uint32_t)n_d), slr::mbar_init(&bar_clr[c], 1);
         slr::mbar_fence_init();
     }
@@ -184,7 +324,7 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nsrc + (size_t)v * p.H * W), "r"((uint32_t)W) : "memory");
         }
     };
-    if (tid < 32) {
+    if (!RAW && tid < 32) {
         issue_row(0);
         if (R > 1) issue_row(1);
     }
@@ -203,8 +343,35 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
         if (g >= total_jobs) break;
         FLOW_TRACE_DRAW();
         const int t = (int)__umulhi((unsigned)g, js_magic);   // g / JS (exact for g * JS < 2^32, checked by the launcher)
-        const int s = g - t * JS;
+        int s = g - t * JS;
 
+        if (RAW && s < n_r) {
+            // ================= rectify job s of row r = t: 128 pixels of one camera, all planes =================
+            const int r = t;
+            if (r >= R) continue;
+            // the stage buffer is free once every decode job of row r - 2 has read its bytes
+            if (r >= FLOW_STAGES) slr::mbar_wait(&bar_free[r % FLOW_STAGES], (uint32_t)((r / FLOW_STAGES - 1) & 1));
+            FLOW_TRACE_READY();
+            const long long rg = r_begin + r;
+            const int b = (int)(rg / p.H), i = (int)(rg - (long long)b * p.H);
+            const int per_cam = n_r >> 1, cam = s >= per_cam ? 1 : 0;
+            const int x = ((s - cam * per_cam) * 32 + lane) * 4;
+            if (s == 0 && lane == 0) {
+                rowinfo[r & 7].out_px = (unsigned)(((size_t)b * p.H + i) * W);
+                rowinfo[r & 7].map_px = (unsigned)((size_t)i * W);
+            }
+            {
+                const size_t P = (size_t)W * p.H;
+                unsigned char *dst = stage0 + (size_t)(r % FLOW_STAGES) * stage_bytes + (size_t)cam * ((size_t)N * W + cam_pad) + x;
+                rectify_job(p.stack + ((size_t)b * 2 + cam) * N * P, p.map1 + (size_t)cam * P, p.map2 + (size_t)cam * P, W,
+                            p.H, N, i, x, x < W, dst, lane);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_stage[r % FLOW_STAGES]);
+            FLOW_TRACE_END(3, r);
+            continue;
+        }
+        s -= n_r;
         if (s < n_d) {
             // ================= decode job s of row r = t - 1 =================
             const int r = t - 1;
@@ -229,10 +396,14 @@ k_fused_flow(const FusedParams p, const int n_d, const int n_q, const unsigned j
                 // warp that counts the last reader streams row r + 2 into the buffer: a third of a decode job earlier
                 // than its completion, which is the slack the bulk copies need to land before row r + 2 is drawn.
                 __syncwarp();
-                int last_reader = 0;
-                if (lane == 0) last_reader = add_acq_rel_s32(&done_l[c], 1) + 1 == (u + 1) * n_d;
-                last_reader = __shfl_sync(0xffffffffu, last_reader, 0);
-                if (last_reader && r + FLOW_STAGES < R) issue_row(r + FLOW_STAGES);
+                if (RAW) {
+                    if (lane == 0) mbar_arrive(&bar_free[r % FLOW_STAGES]);
+                } else {
+                    int last_reader = 0;
+                    if (lane == 0) last_reader = add_acq_rel_s32(&done_l[c], 1) + 1 == (u + 1) * n_d;
+                    last_reader = __shfl_sync(0xffffffffu, last_reader, 0);
+                    if (last_reader && r + FLOW_STAGES < R) issue_row(r + FLOW_STAGES);
+                }
                 // the right lane hands its upper two phases to the left lane: every lane decodes 4 pixels and files 2
                 const float n2 = __shfl_xor_sync(0xffffffffu, ph[2], 1), n3 = __shfl_xor_sync(0xffffffffu, ph[3], 1);
                 const unsigned okb = __shfl_xor_sync(0xffffffffu, (ok[2] ? 1u : 0u) | (ok[3] ? 2u : 0u), 1);
@@ -357,11 +528,14 @@ slr_status slr_launch_fused_flow(slr_engine *e, int mode, const FusedParams &p_i
     const size_t stage_bytes = (mode == MODE_PHASE_INPUT) ? (size_t)10 * W : (size_t)2 * p.N * W + FLOW_CAM_PAD;
     const size_t smem = FLOW_HEADER + FLOW_STAGES * stage_bytes + FLOW_CTX * flow_ctx_bytes(W, p.T) +
                         SLR_PTAB_SIZE * 4 + SLR_BTAB_SIZE * 4;
+    const bool raw = p.map1 != nullptr;   // the stack holds raw camera images: rectify jobs fill the stage buffer
     const int n_d = (W / 2 + 31) / 32, n_q = (W + 32 * FLOW_QPX - 1) / (32 * FLOW_QPX);
+    const int n_r = raw ? 2 * ((W + 127) / 128) : 0;
     if (smem > 227 * 1024 || 2 * p.T > 32768 || (stage_bytes % 16) != 0) return SLR_OK;
+    if (raw && (mode == MODE_PHASE_INPUT || p.calib.row0 != 0)) return SLR_OK;
     // rows per CTA must keep the job counter inside int32, pixel offsets inside uint32
     const long long rows = (long long)p.batch * p.H;
-    const long long JS = n_d + n_q;
+    const long long JS = n_r + n_d + n_q;
     if ((rows / e->num_sms + 8) * JS * JS >= (1LL << 32) || rows * W >= (1LL << 32)) return SLR_OK;
     const unsigned js_magic = (unsigned)(((1ULL << 32) + JS - 1) / JS);
     *handled = true;
@@ -369,21 +543,25 @@ slr_status slr_launch_fused_flow(slr_engine *e, int mode, const FusedParams &p_i
     // one CTA per SM, up to 32 warps; narrow rows (few jobs per step) run two smaller CTAs per SM when they fit
     const int ctas = (2 * (smem + 1024) <= 228 * 1024) ? 2 : 1;
     int warps = 32 / ctas;
-    while (warps > 2 && warps > n_d + n_q) warps >>= 1;
+    while (warps > 2 && warps > n_d + n_q) warps >>= 1;   // (n_r + n_d >= n_d + n_q: a rectify job covers 128 pixels, a query job 64)
     // (the mbarrier phases stay unambiguous only while a CTA has no more warps than one step has jobs: a stuck row then
     // blocks every warp before any of them can reach the jobs of the row that reuses its context)
     if (const char *ev = getenv("SLR_FLOW_WARPS")) {
         const int w = atoi(ev);
         if (w >= 1 && w <= 32 / ctas && w <= (n_d + n_q > 2 ? n_d + n_q : 2)) warps = w;
     }
-    void (*kern)(const FusedParams, int, int, unsigned) = (mode == SLR_MODE_STRICT)      ? k_fused_flow<SLR_MODE_STRICT>
-                                                : (mode == SLR_MODE_CORRECTED) ? k_fused_flow<SLR_MODE_CORRECTED>
-                                                                               : k_fused_flow<MODE_PHASE_INPUT>;
+    void (*kern)(const FusedParams, int, int, int, unsigned);
+    if (raw)
+        kern = (mode == SLR_MODE_STRICT) ? k_fused_flow<SLR_MODE_STRICT, true> : k_fused_flow<SLR_MODE_CORRECTED, true>;
+    else
+        kern = (mode == SLR_MODE_STRICT)      ? k_fused_flow<SLR_MODE_STRICT, false>
+               : (mode == SLR_MODE_CORRECTED) ? k_fused_flow<SLR_MODE_CORRECTED, false>
+                                              : k_fused_flow<MODE_PHASE_INPUT, false>;
     SLR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = (long long)e->num_sms * ctas;
     if (grid > rows) grid = rows;
     if (grid < 1) return SLR_OK;
-    kern<<<(unsigned)grid, warps * 32, smem, e->stream>>>(p, n_d, n_q, js_magic);
+    kern<<<(unsigned)grid, warps * 32, smem, e->stream>>>(p, n_r, n_d, n_q, js_magic);
     SLR_CHECK_LAUNCH(e);
 #ifdef SLR_FLOW_TRACE
     if (const char *path = getenv("SLR_FLOW_TRACE_OUT")) {

@@ -74,6 +74,10 @@ static void free_engine(slr_engine *e)
     cudaFree(e->d_map2);
     cudaFree(e->d_stage_rect[0]);
     cudaFree(e->d_stage_rect[1]);
+    cudaFree(e->d_ingest);
+    cudaFree(e->d_cloud_sum);
+    cudaFree(e->d_cloud_cnt);
+    if (e->ev_ingest) cudaEventDestroy(e->ev_ingest);
     if (e->h_counter) cudaFreeHost(e->h_counter);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_in) cudaStreamDestroy(e->copy_in);
@@ -472,6 +476,27 @@ extern "C" slr_status slr_run_mf(slr_engine *e, const uint8_t *d_stack, int batc
     return st == SLR_OK ? slr_copy_to_targets(e, batch) : st;
 }
 
+extern "C" slr_status slr_run_mf_raw(slr_engine *e, const uint8_t *d_raw_stack, int batch, int F, int S, int black_thr,
+                                     int mode, float *d_xyz, uint8_t *d_valid, int32_t *d_match_k,
+                                     unsigned long long *d_n_points)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(d_raw_stack && batch > 0 && (e->n_targets > 0 || (d_xyz && d_valid)), "slr_run_mf_raw: bad argument");
+    if (!e->calib_set || !e->maps_set) {
+        slr_set_error("slr_run_mf_raw: call slr_set_calib and slr_set_rectify_maps first");
+        return SLR_ERR_STATE;
+    }
+    if (mode == SLR_MODE_STRICT)
+        SLR_REQUIRE(F == 3 && S == 4, "strict mode reproduces the reference's hard-coded 3 frequencies x 4 steps; got F=%d S=%d", F, S);
+    else
+        SLR_REQUIRE(mode == SLR_MODE_CORRECTED && F >= 1 && F <= 8 && S >= 3 && S <= 16,
+                    "corrected mode supports 1<=F<=8, 3<=S<=16; got mode %d F=%d S=%d", mode, F, S);
+    if (e->n_targets > 0) slr_own_target_block(e, &d_xyz, &d_valid);
+    e->targets_written = false;
+    const slr_status st = slr_launch_fused_mf_raw(e, d_raw_stack, batch, F, S, black_thr, mode, d_xyz, d_valid, d_match_k, d_n_points);
+    return st == SLR_OK ? slr_copy_to_targets(e, batch) : st;
+}
+
 extern "C" slr_status slr_run_ge(slr_engine *e, const uint8_t *d_stack, int batch, int nbits_col, int black_thr,
                                  int white_thr, int scan_w, int have_color, float *d_xyz, uint8_t *d_valid,
                                  int32_t *d_match_k, uint8_t *d_color, unsigned long long *d_n_points)
@@ -780,7 +805,7 @@ static slr_status ensure_stage(slr_engine *e, size_t in_bytes_per_scan, bool wan
 template <typename LaunchFn>
 static slr_status host_pipeline_body(slr_engine *e, const uint8_t *h_stack, size_t in_bytes, int batch, bool color,
                                      float *h_xyz, uint8_t *h_valid, int32_t *h_match_k, uint8_t *h_color,
-                                     unsigned long long *h_n_points, LaunchFn launch)
+                                     unsigned long long *h_n_points, LaunchFn launch, bool rectify_in_launch)
 {
     const size_t P = (size_t)e->W * e->H;
     slr_status st = ensure_stage(e, in_bytes, color);
@@ -798,7 +823,7 @@ static slr_status host_pipeline_body(slr_engine *e, const uint8_t *h_stack, size
         SLR_CHECK_CUDA(cudaStreamWaitEvent(cs, e->ev_in[b], 0));
         SLR_CHECK_CUDA(cudaStreamWaitEvent(cs, e->ev_out[b], 0));
         uint8_t *d_in = e->d_stage_in[b];
-        if (e->host_input_raw) {  // K0: rectify the raw camera images on the GPU (stereoRect::doStereoRectify)
+        if (e->host_input_raw && !rectify_in_launch) {  // K0: rectify the raw camera images on the GPU (stereoRect::doStereoRectify)
             st = slr_launch_rectify(e, d_in, 1, (int)(in_bytes / (2 * P)), e->d_stage_rect[b]);
             if (st != SLR_OK) return st;
             d_in = e->d_stage_rect[b];
@@ -836,10 +861,10 @@ static slr_status host_pipeline_body(slr_engine *e, const uint8_t *h_stack, size
 template <typename LaunchFn>
 static slr_status host_pipeline(slr_engine *e, const uint8_t *h_stack, size_t in_bytes, int batch, bool color,
                                 float *h_xyz, uint8_t *h_valid, int32_t *h_match_k, uint8_t *h_color,
-                                unsigned long long *h_n_points, LaunchFn launch)
+                                unsigned long long *h_n_points, LaunchFn launch, bool rectify_in_launch = false)
 {
     const slr_status st = host_pipeline_body(e, h_stack, in_bytes, batch, color, h_xyz, h_valid, h_match_k, h_color,
-                                             h_n_points, launch);
+                                             h_n_points, launch, rectify_in_launch);
     if (st != SLR_OK) {
         char first[512];
         snprintf(first, sizeof(first), "%s", slr_last_error());
@@ -864,11 +889,124 @@ extern "C" slr_status slr_run_mf_host(slr_engine *e, const uint8_t *h_stack, int
         return SLR_ERR_STATE;
     }
     const size_t in_bytes = (size_t)2 * (2 + F * S) * e->W * e->H;
+    // raw camera images (MFReconstruct::loadCamImgs rectifies, never stretches: Duke/mfreconstruct.cpp:111-146): the
+    // rectification runs inside the fused kernel's stage fill, so a raw scan is ONE kernel like a rectified one
+    const bool raw = e->host_input_raw && !e->auto_contrast;
     return host_pipeline(e, h_stack, in_bytes, batch, false, h_xyz, h_valid, h_match_k, nullptr, h_n_points,
                          [&](uint8_t *d_in, float *d_xyz, uint8_t *d_valid, int32_t *d_k, uint8_t *) {
+                             if (raw)
+                                 return slr_launch_fused_mf_raw(e, d_in, 1, F, S, black_thr, mode, d_xyz, d_valid,
+                                                                h_match_k ? d_k : nullptr, e->d_counter);
                              return slr_launch_fused_mf(e, d_in, 1, F, S, black_thr, mode, d_xyz, d_valid,
                                                         h_match_k ? d_k : nullptr, e->d_counter);
-                         });
+                         }, raw);
+}
+
+// ------------------------------------------------------------------------------------------------
+// PNG ingest: images arrive one by one, as their host threads finish inflating them
+// ------------------------------------------------------------------------------------------------
+extern "C" slr_status slr_ingest_begin(slr_engine *e, int n_images)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(n_images > 0 && n_images % 2 == 0 && n_images <= 2 * 130, "slr_ingest_begin: bad image count %d", n_images);
+    SLR_REQUIRE(e->W % 4 == 0, "slr_ingest_begin: the GPU unfilter needs a width that is a multiple of 4");
+    const size_t P = (size_t)e->W * e->H, FB = (size_t)(e->W + 1) * e->H;
+    const slr_status st = ensure_stage(e, (size_t)n_images * P, false);
+    if (st != SLR_OK) return st;
+    if (e->ingest_bytes < (size_t)n_images * FB) {
+        if (e->d_ingest) SLR_CHECK_CUDA(cudaFree(e->d_ingest));
+        e->d_ingest = nullptr;
+        e->ingest_bytes = 0;
+        SLR_CHECK_CUDA(cudaMalloc(&e->d_ingest, (size_t)n_images * FB));
+        e->ingest_bytes = (size_t)n_images * FB;
+    }
+    if (!e->ev_ingest) SLR_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_ingest, cudaEventDisableTiming));
+    // the stage buffer may still be read by the kernels of an earlier call on the engine's stream
+    SLR_CHECK_CUDA(cudaEventRecord(e->ev_ingest, e->stream));
+    SLR_CHECK_CUDA(cudaStreamWaitEvent(e->copy_in, e->ev_ingest, 0));
+    e->ingest_images = n_images;
+    return SLR_OK;
+}
+
+extern "C" slr_status slr_ingest_image(slr_engine *e, int index, const uint8_t *h_data, int filtered, int has_up_rows)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(h_data && index >= 0 && index < e->ingest_images, "slr_ingest_image: bad argument (slr_ingest_begin first)");
+    const size_t P = (size_t)e->W * e->H, FB = (size_t)(e->W + 1) * e->H;
+    uint8_t *plane = e->d_stage_in[0] + (size_t)index * P;
+    if (!filtered) {
+        SLR_CHECK_CUDA(cudaMemcpyAsync(plane, h_data, P, cudaMemcpyHostToDevice, e->copy_in));
+        return SLR_OK;
+    }
+    uint8_t *f = e->d_ingest + (size_t)index * FB;
+    SLR_CHECK_CUDA(cudaMemcpyAsync(f, h_data, FB, cudaMemcpyHostToDevice, e->copy_in));
+    return slr_launch_png_unfilter(e, e->copy_in, f, plane, has_up_rows != 0);
+}
+
+extern "C" slr_status slr_run_mf_ingested(slr_engine *e, int F, int S, int black_thr, int mode, int scan_w, int scan_h,
+                                          float *h_sum, uint8_t *h_cnt, float *h_xyz, uint8_t *h_valid,
+                                          unsigned long long *h_n_points)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(F >= 1 && S >= 3 && e->ingest_images == 2 * (2 + F * S), "slr_run_mf_ingested: %d images ingested, the stack needs %d",
+                e->ingest_images, 2 * (2 + F * S));
+    SLR_REQUIRE((h_sum && h_cnt && scan_w > 0 && scan_h > 0) || (h_xyz && h_valid), "slr_run_mf_ingested: no output buffer");
+    if (!e->calib_set) {
+        slr_set_error("slr_run_mf_ingested: call slr_set_calib first");
+        return SLR_ERR_STATE;
+    }
+    const size_t P = (size_t)e->W * e->H;
+    cudaStream_t cs = e->stream;
+    slr_status st = SLR_OK;
+    do {
+        if (cudaEventRecord(e->ev_ingest, e->copy_in) != cudaSuccess || cudaStreamWaitEvent(cs, e->ev_ingest, 0) != cudaSuccess) {
+            slr_set_error("slr_run_mf_ingested: stream ordering failed");
+            st = SLR_ERR_CUDA;
+            break;
+        }
+        if (cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), cs) != cudaSuccess) { st = SLR_ERR_CUDA; break; }
+        if (e->host_input_raw)
+            st = slr_launch_fused_mf_raw(e, e->d_stage_in[0], 1, F, S, black_thr, mode, e->d_stage_xyz[0], e->d_stage_valid[0],
+                                         nullptr, e->d_counter);
+        else
+            st = slr_launch_fused_mf(e, e->d_stage_in[0], 1, F, S, black_thr, mode, e->d_stage_xyz[0], e->d_stage_valid[0],
+                                     nullptr, e->d_counter);
+        if (st != SLR_OK) break;
+        if (h_sum && h_cnt) {
+            const size_t cells = (size_t)scan_w * scan_h;
+            if (e->cloud_cells < cells) {
+                cudaFree(e->d_cloud_sum);
+                cudaFree(e->d_cloud_cnt);
+                e->d_cloud_sum = nullptr;
+                e->d_cloud_cnt = nullptr;
+                e->cloud_cells = 0;
+                if (cudaMalloc(&e->d_cloud_sum, cells * 3 * sizeof(float)) != cudaSuccess ||
+                    cudaMalloc(&e->d_cloud_cnt, cells) != cudaSuccess) {
+                    slr_set_error("slr_run_mf_ingested: out of device memory");
+                    st = SLR_ERR_NOMEM;
+                    break;
+                }
+                e->cloud_cells = cells;
+            }
+            st = slr_launch_cloud_image(e, e->d_stage_xyz[0], e->d_stage_valid[0], scan_w, scan_h, e->d_cloud_sum, e->d_cloud_cnt);
+            if (st != SLR_OK) break;
+            cudaMemcpyAsync(h_sum, e->d_cloud_sum, cells * 3 * sizeof(float), cudaMemcpyDeviceToHost, cs);
+            cudaMemcpyAsync(h_cnt, e->d_cloud_cnt, cells, cudaMemcpyDeviceToHost, cs);
+        }
+        if (h_xyz && h_valid) {
+            cudaMemcpyAsync(h_xyz, e->d_stage_xyz[0], P * 3 * sizeof(float), cudaMemcpyDeviceToHost, cs);
+            cudaMemcpyAsync(h_valid, e->d_stage_valid[0], P, cudaMemcpyDeviceToHost, cs);
+        }
+        cudaMemcpyAsync(e->h_counter, e->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, cs);
+    } while (false);
+    // the caller's buffers must be quiet when this returns, error or not
+    const cudaError_t ce = cudaStreamSynchronize(cs);
+    cudaStreamSynchronize(e->copy_in);
+    e->ingest_images = 0;
+    if (st != SLR_OK) return st;
+    SLR_CHECK_CUDA(ce);
+    if (h_n_points) *h_n_points = *e->h_counter;
+    return SLR_OK;
 }
 
 extern "C" slr_status slr_run_ge_host(slr_engine *e, const uint8_t *h_stack, int batch, int nbits_col,

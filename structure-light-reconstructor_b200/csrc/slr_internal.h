@@ -100,6 +100,16 @@ struct slr_engine {
     long long target_first_scan = 0;
     bool targets_written = false;   // set by a launcher whose kernel stored to all targets itself
 
+    // PNG ingest (k_png.cu): filtered scanlines of the images of one scan as uploaded, the image count, and the
+    // PointCloudImage-layout outputs of slr_run_mf_ingested
+    uint8_t *d_ingest = nullptr;
+    size_t ingest_bytes = 0;
+    int ingest_images = 0;
+    cudaEvent_t ev_ingest = nullptr;
+    float *d_cloud_sum = nullptr;
+    uint8_t *d_cloud_cnt = nullptr;
+    size_t cloud_cells = 0;
+
     unsigned long long launches = 0;
 };
 
@@ -154,6 +164,8 @@ slr_status slr_launch_bucket_triangulate(slr_engine *e, const int32_t *d_col, co
 slr_status slr_launch_fused_mf(slr_engine *e, const uint8_t *d_stack, int batch, int F, int S,
                                int black_thr, int mode, float *d_xyz, uint8_t *d_valid,
                                int32_t *d_match_k, unsigned long long *d_n_points);
+slr_status slr_launch_fused_mf_raw(slr_engine *e, const uint8_t *d_raw, int batch, int F, int S, int black_thr, int mode,
+                                   float *d_xyz, uint8_t *d_valid, int32_t *d_match_k, unsigned long long *d_n_points);
 slr_status slr_launch_fused_ge(slr_engine *e, const uint8_t *d_stack, int batch, int nbits_col,
                                int black_thr, int white_thr, int scan_w, int have_color,
                                float *d_xyz, uint8_t *d_valid, int32_t *d_match_k, uint8_t *d_color,
@@ -161,6 +173,10 @@ slr_status slr_launch_fused_ge(slr_engine *e, const uint8_t *d_stack, int batch,
 slr_status slr_launch_undistort_maps(slr_engine *e);
 slr_status slr_launch_rectify(slr_engine *e, const uint8_t *d_raw, int batch, int N, uint8_t *d_out);
 slr_status slr_build_strict_tables(slr_engine *e);
+slr_status slr_launch_png_unfilter(slr_engine *e, cudaStream_t stream, const uint8_t *d_filtered, uint8_t *d_plane,
+                                   bool has_up_rows);
+slr_status slr_launch_cloud_image(slr_engine *e, const float *d_xyz, const uint8_t *d_valid, int scan_w, int scan_h,
+                                  float *d_sum, uint8_t *d_cnt);
 slr_status slr_launch_auto_contrast(slr_engine *e, uint8_t *d_images, int n_images);
 // padded route for e->W % 16 != 0 (slr_engine.cu); kind: 0 = image stacks (MF), 1 = image stacks (GE),
 // 2 = phase + mask rows, 3 = code + mask rows

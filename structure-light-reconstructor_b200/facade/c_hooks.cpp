@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "imageio.h"
+#include "inflate.h"
 #include "meshcreator.h"
 #include "rectify.h"
 #include "stereorect.h"
@@ -52,6 +53,12 @@ int duke_read_gray_image(const char *path, int *w, int *h, uint8_t *pix, int cap
     if ((int)img.pix.size() > cap) return -2;
     memcpy(pix, img.pix.data(), img.pix.size());
     return 0;
+}
+
+// zlib stream -> bytes with the ingest path's own decoder (inflate.cpp); 0 = ok, -1 = rejected
+int duke_zlib_inflate(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
+{
+    return duke::zlib_inflate(in, in_len, out, out_len) ? 0 : -1;
 }
 
 int duke_write_png_gray(const char *path, const uint8_t *pix, int w, int h) { return duke::write_png_gray(path, pix, w, h) ? 0 : -1; }

@@ -1,5 +1,7 @@
 #include "imageio.h"
 
+#include "inflate.h"
+
 #include <stdio.h>
 #include <string.h>
 #include <zlib.h>
@@ -71,9 +73,8 @@ static bool read_png(const std::vector<uint8_t> &buf, Image &out, std::string *e
     }
     const size_t stride = (size_t)W * ch;
     std::vector<uint8_t> raw((stride + 1) * H);
-    uLongf rawlen = (uLongf)raw.size();
-    if (uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size()) != Z_OK || rawlen != raw.size())
-        return fail(err, "PNG inflate failed");
+    std::string zerr;
+    if (!zlib_inflate(idat.data(), idat.size(), raw.data(), raw.size(), &zerr)) return fail(err, "PNG " + zerr);
     std::vector<uint8_t> img(stride * H);
     for (uint32_t y = 0; y < H; y++) {
         const uint8_t ft = raw[y * (stride + 1)];

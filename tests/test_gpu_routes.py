@@ -238,3 +238,132 @@ def test_row_band_engines_reproduce_the_full_image(cuda_engine_factory):
         gx, gv, gk, _, _ = band.run_ge(ge[:, :, :, lo:hi].contiguous(), nb, black_thr=40, white_thr=3)
         assert torch.equal(gk, gk_f[:, lo:hi]) and torch.equal(gv, gv_f[:, lo:hi])
         assert (bits(gx.cpu().numpy()) == bits(gx_f[:, lo:hi].cpu().numpy())).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY.md 8f N1 as written: rectification inside the fused kernel's stage fill (slr_run_mf_raw) —
+# stereoRect::doStereoRectify (Duke/stereorect.cpp:26-34) + MFReconstruct::runReconstruction, raw bytes -> XYZ
+# ------------------------------------------------------------------------------------------------
+def _rect_maps(W, H, seed, border=False):
+    cv2 = pytest.importorskip("cv2")
+    xs, ys = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32))
+    maps1, maps2 = [], []
+    for cam in range(2):
+        mx = xs * (1.004 - 0.008 * cam) - 2 + 1.5 * np.sin(ys / 17 + seed)
+        my = ys * 0.995 + 1 - 2 * cam + 1.5 * np.cos(xs / 41 + seed)       # rows drift: groups straddle source rows
+        if border:                                                         # taps outside the image: BORDER_CONSTANT 0
+            mx, my = mx - 6, my - 3
+        mx[:2], my[:2] = xs[:2], ys[:2]                                    # integer coordinates: the (0,0) weight entry
+        m1, m2 = cv2.convertMaps(mx, my, cv2.CV_16SC2)
+        maps1.append(m1)
+        maps2.append(m2)
+    return np.stack(maps1), np.stack(maps2)
+
+
+@pytest.mark.parametrize("W,H,B,mode,border", [(1280, 40, 3, slr_b200.MODE_STRICT, False),
+                                               (640, 33, 2, slr_b200.MODE_STRICT, True),
+                                               (1280, 24, 2, slr_b200.MODE_CORRECTED, False),
+                                               (2048, 20, 1, slr_b200.MODE_STRICT, False)])
+def test_run_mf_raw_rectifies_inside_the_fused_kernel_vs_oracle(cuda_engine_factory, oracle, W, H, B, mode, border):
+    eng = cuda_engine_factory(W, H, B)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    m1, m2 = _rect_maps(W, H, 0.7, border)
+    eng.set_rectify_maps(m1, m2)
+    raw = np.stack([synth.synth_mf(W, H, seed=40 + s, integer_disparity=False, noise_dn=1.5) for s in range(B)])
+    l0 = eng.launches()
+    xyz, valid, k, n = eng.run_mf_raw(_t(raw), black_thr=40, mode=mode)
+    import torch
+    torch.cuda.synchronize()
+    if W <= 1280:    # (2048-wide rows exceed the dataflow kernel's shared memory: K0 + the wide-row kernel per scan)
+        assert eng.launches() - l0 == 1, "raw stacks -> XYZ must be ONE kernel"
+    tot = 0
+    for b in range(B):
+        rect = np.stack([[oracle.remap_linear(raw[b, cam, i], m1[cam], m2[cam]) for i in range(raw.shape[2])]
+                         for cam in range(2)])
+        xyz_o, valid_o, k_o, n_o = oracle.run_mf(rect, cams, Q, mode=mode, nthreads=oracle.max_threads())
+        if mode == slr_b200.MODE_STRICT:
+            _assert_cloud_equal(xyz[b], valid[b], k[b], n_o, xyz_o, valid_o, k_o, n_o, f"raw scan {b}")
+        else:   # corrected mode (oracle-only): phases agree to 1e-4, matches may differ where a phase sits on the window edge
+            same = k[b].cpu().numpy() == k_o
+            assert same.mean() > 0.995, same.mean()
+            ok = same & (valid_o != 0)
+            assert np.allclose(xyz[b].cpu().numpy()[ok], xyz_o[ok], rtol=RTOL, atol=1e-5)
+        tot += n_o
+    assert tot > 1000
+    if mode == slr_b200.MODE_STRICT:
+        assert int(n.item()) == tot
+    # the two-kernel route (K0 into HBM, then the fused kernel) gives the same bits
+    xyz2, valid2, k2, n2 = eng.run_mf(eng.rectify_stack(_t(raw)), black_thr=40, mode=mode)
+    assert (bits(xyz2.cpu().numpy()) == bits(xyz.cpu().numpy())).all() and (k2 == k).all() and int(n2.item()) == int(n.item())
+
+
+# ------------------------------------------------------------------------------------------------
+# PNG ingest — scanlines as the zlib stream holds them (filter byte + filtered row) are unfiltered on
+# the GPU, image by image; the cloud comes back in the reference's PointCloudImage storage layout
+# ------------------------------------------------------------------------------------------------
+def _png_filter_rows(img, types):
+    """forward PNG filters None / Sub / Up of an 8-bit grey image -> [H, 1 + W] scanlines"""
+    H, W = img.shape
+    out = np.empty((H, W + 1), np.uint8)
+    a = img.astype(np.int16)
+    for y in range(H):
+        t = int(types[y])
+        if t == 0:
+            f = a[y]
+        elif t == 1:
+            f = a[y] - np.concatenate([[0], a[y, :-1]])
+        else:
+            f = a[y] - (a[y - 1] if y else 0)
+        out[y, 0] = t
+        out[y, 1:] = (f & 255).astype(np.uint8)
+    return out
+
+
+@pytest.mark.parametrize("W,H,scan_w,scan_h,raw", [(1280, 48, 1280, 1024, False), (640, 40, 30, 500, True)])
+def test_png_ingest_unfilters_on_the_gpu_and_returns_the_pointcloudimage_layout(cuda_engine_factory, oracle, W, H,
+                                                                                 scan_w, scan_h, raw):
+    eng = cuda_engine_factory(W, H, 1)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    if raw:
+        m1, m2 = _rect_maps(W, H, 0.2)
+        eng.set_rectify_maps(m1, m2)
+        eng.set_host_input_raw(True)
+    stack = synth.synth_mf(W, H, seed=91, integer_disparity=False, noise_dn=2.0)      # [2, 14, H, W]
+    rng = np.random.default_rng(5)
+    images, filtered = [], []
+    for k in range(28):
+        img = stack[k // 14, k % 14]
+        kind = k % 4
+        if kind == 0:
+            images.append(img), filtered.append(False)                                  # decoded by the caller
+        else:
+            types = np.ones(H, np.int64) if kind == 1 else rng.integers(0, 3 if kind == 2 else 2, H)
+            images.append(_png_filter_rows(img, types)), filtered.append(True)
+    h_xyz = np.empty((H, W, 3), np.float32)
+    h_valid = np.empty((H, W), np.uint8)
+    h_sum = np.full((scan_h, scan_w, 3), -7.0, np.float32)
+    h_cnt = np.full((scan_h, scan_w), 9, np.uint8)
+    n = eng.run_mf_ingested(images, filtered, h_sum, h_cnt, h_xyz, h_valid, scan_w, scan_h)
+    # the same scan through the device-pointer entry points
+    if raw:
+        xyz, valid, k, n2 = eng.run_mf_raw(_t(stack[None]))
+        eng.set_host_input_raw(False)
+        rect = np.stack([[oracle.remap_linear(stack[cam, i], m1[cam], m2[cam]) for i in range(14)] for cam in range(2)])
+    else:
+        xyz, valid, k, n2 = eng.run_mf(_t(stack[None]))
+        rect = stack
+    assert n == int(n2.item()) and n > 1000
+    assert (bits(h_xyz) == bits(xyz[0].cpu().numpy())).all() and (h_valid == valid[0].cpu().numpy()).all()
+    xyz_o, valid_o, k_o, n_o = oracle.run_mf(rect, cams, Q, nthreads=oracle.max_threads())
+    assert n == n_o and (bits(h_xyz) == bits(xyz_o)).all()
+    # PointCloudImage(scan_w, scan_h) after addPoint(i, j, p) for every valid (row i, column j): cell (i_w = i, j_h = j),
+    # stored at [j_h][i_w]; i >= scan_w or j >= scan_h dropped (Duke/pointcloudimage.cpp:86-97)
+    exp_sum = np.zeros((scan_h, scan_w, 3), np.float32)
+    exp_cnt = np.zeros((scan_h, scan_w), np.uint8)
+    hh, ww = min(H, scan_w), min(W, scan_h)
+    v = valid_o[:hh, :ww] != 0
+    exp_cnt[:ww, :hh] = v.T
+    exp_sum[:ww, :hh] = np.where(v[..., None], xyz_o[:hh, :ww], 0).transpose(1, 0, 2)
+    assert (h_cnt == exp_cnt).all() and (bits(h_sum) == bits(exp_sum)).all()
