@@ -324,6 +324,66 @@ def run_reference(args):
     }), flush=True)
 
 
+def drop_in_call(stack_one_scan, W, H, calls=8):
+    """The reference's own entry point on its own input format: a project directory (28 PNG files as cv::imwrite writes
+    them + the calibration text files) through the drop-in MFReconstruct::runReconstruction (facade_demo drives it as
+    MainWindow::startreconstruct does), in steady state: image files -> PointCloudImage, nothing skipped.
+    Returns None when the facade is not built."""
+    import re
+    import shutil
+    import tempfile
+    import numpy as np
+    from slr_b200 import synth
+    demo = os.path.join(ROOT, "structure-light-reconstructor_b200", "facade", "facade_demo")
+    if not os.path.exists(demo):
+        return None
+    tmp = tempfile.mkdtemp(prefix="slr_bench_")
+    try:
+        def write_mat(path, m):
+            with open(path, "w") as f:
+                for r in np.atleast_2d(np.asarray(m, np.float64)):
+                    f.write("\t".join(f"{v:.9g}" for v in r) + "\t\n")
+        for side, fx, cx, cy, dist, R, t in (
+                ("left", 2400.0, W / 2 + 2.25, H / 2 - 1.5, [-0.11, 0.07, 0.0006, -0.0003, 0.0], np.eye(3), [0, 0, 0]),
+                ("right", 2396.0, W / 2 - 1.75, H / 2 + 1.25, [-0.09, 0.04, -0.0004, 0.0005, 0.0],
+                 [[0.9998, 0.0, 0.02], [0.0, 1.0, 0.0], [-0.02, 0.0, 0.9998]], [-200.0, 0.5, 1.0])):
+            d = os.path.join(tmp, "calib", side)
+            os.makedirs(d)
+            K = [[fx, 0, cx], [0, fx + 1, cy], [0, 0, 1]]
+            for name, m in (("cam_matrix.txt", K), ("cam_distortion.txt", np.array(dist)[:, None]), ("cam_rotation_matrix.txt", R),
+                            ("cam_trans_vectror.txt", np.array(t)[:, None]), ("cam_stereo.txt", K),
+                            ("distortion_stereo.txt", np.array(dist)[:, None])):
+                write_mat(os.path.join(d, name), m)
+        write_mat(os.path.join(tmp, "calib", "R_stereo.txt"), [[0.99985, 0.002, 0.0172], [-0.0021, 0.999995, 0.004], [-0.0172, -0.004, 0.99984]])
+        write_mat(os.path.join(tmp, "calib", "T_stereo.txt"), np.array([-200.0, 0.4, 1.2])[:, None])
+        for name in ("fundamental_stereo.txt", "H1_mat.txt", "H2_mat.txt"):
+            write_mat(os.path.join(tmp, "calib", name), np.eye(3))
+        png_bytes = 0
+        for cam, side, pre in ((0, "left", "L"), (1, "right", "R")):
+            d = os.path.join(tmp, "scan", side, "0")
+            os.makedirs(d)
+            for i in range(stack_one_scan.shape[1]):
+                synth.write_png_opencv_style(os.path.join(d, f"{pre}{i}.png"), stack_one_scan[cam, i])
+                png_bytes += os.path.getsize(os.path.join(d, f"{pre}{i}.png"))
+        env = dict(os.environ, DUKE_REPEAT=str(calls + 2))
+        r = subprocess.run([demo, "mf", tmp, "0", str(W), str(H), str(W), str(H), str(BLACK_THR), "0", "0",
+                            os.path.join(tmp, "out.bin")], capture_output=True, text=True, env=env, timeout=300)
+        ms = [float(x) for x in re.findall(r"runReconstruction #\d+ .*?: ([0-9.]+) ms", r.stderr)]
+        pts = re.search(r"mf: (\d+) points", r.stdout)
+        if r.returncode != 0 or len(ms) < 3 or not pts:
+            return {"error": (r.stderr or r.stdout)[-300:]}
+        steady = statistics.median(ms[2:])
+        return {"ms_per_call": steady, "first_call_ms": ms[0], "points_per_call": int(pts.group(1)),
+                "value": int(pts.group(1)) / (steady * 1e-3) / 1e6, "unit": UNIT, "png_bytes_per_scan": png_bytes,
+                "host_threads": host_threads(),
+                "what": "MFReconstruct::runReconstruction of the drop-in classes on a project directory: 28 PNG files (Sub filter, "
+                        "Z_RLE, as cv::imwrite writes them) -> inflate on the host threads -> GPU (PNG unfilter, rectification "
+                        "inside the fused kernel, decode, match, triangulation, PointCloudImage layout) -> PointCloudImage; median "
+                        f"of calls 3..{len(ms)} of one process"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # CUDA arm
 # ---------------------------------------------------------------------------------------------------------------------
@@ -587,6 +647,8 @@ def main():
         e2e = {"pts": pts, "dt": time.perf_counter() - t0, "steps": e_steps, "batch": Be,
                "h2d": Be * 2 * n_img * H * W, "d2h": Be * H * W * 13, "h2d_rate": h2d_rate}
         del h_stack, h_xyz, h_valid
+        if world == 1 and args.config == 3 and rank == 0:
+            e2e["drop_in"] = drop_in_call(make_host_inputs(1, rank, noise_dn=2.0, integer_disparity=False)[0], W, H)
 
     # ---- reduce over ranks: time = max, points = sum ----
     g_keys = [k for k in ("peer_ms", "nccl_ms", "band_ms") if k in gather]
@@ -646,6 +708,8 @@ def main():
                                           "frac": e2e["h2d"] / (ms_e * 1e-3) / 1e9 / h2d_rate if h2d_rate else None,
                                           "peak_source": "pinned copy of the same buffers measured in this process, both "
                                                          "directions at once, all ranks at once (min over ranks)"}}
+            if e2e.get("drop_in"):
+                result["e2e"]["drop_in_call"] = e2e["drop_in"]
         if gather:
             w = {"bytes_received_per_rank_per_step": gather["recv_bytes"]}
             for key, name, note in (("peer_ms", "peer_stores", "no collective call: every rank's k_fused_flow stores each output row "

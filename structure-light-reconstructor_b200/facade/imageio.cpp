@@ -50,6 +50,7 @@ static bool read_png(const std::vector<uint8_t> &buf, Image &out, std::string *e
         const uint8_t *type = &buf[pos + 4], *data = &buf[pos + 8];
         if (pos + 12 + len > buf.size()) return fail(err, "truncated PNG chunk");
         if (!memcmp(type, "IHDR", 4)) {
+            if (len < 13) return fail(err, "PNG IHDR chunk too short");
             W = be32(data);
             H = be32(data + 4);
             depth = data[8];
@@ -62,6 +63,8 @@ static bool read_png(const std::vector<uint8_t> &buf, Image &out, std::string *e
         }
         pos += 12 + len;
     }
+    // the file is not trusted: sizes are checked before anything is allocated from them
+    if (W == 0 || H == 0 || W > 65535 || H > 65535) return fail(err, "PNG without a usable IHDR (size 0 or beyond 65535)");
     if (depth != 8 || interlace != 0) return fail(err, "only 8-bit non-interlaced PNG is supported");
     int ch;
     switch (ctype) {

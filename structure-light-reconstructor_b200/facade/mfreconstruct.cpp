@@ -4,6 +4,7 @@
 
 #include <stdio.h>
 
+#include "ingest.h"
 #include "reconstruct_common.h"
 
 MFReconstruct::MFReconstruct(void *) : points3DProjView(nullptr), imgSuffix(".png"), numberOfImgs(14)
@@ -93,14 +94,39 @@ bool MFReconstruct::runReconstruction()
         if (scanSN > 0) {  // mfreconstruct.cpp:276-282
             if (duke::load_rigid(savePath_ + "/scan/transfer_mat" + std::to_string(scanSN) + ".txt", rigid)) rg = rigid;
         }
-        if (slr_set_calib(eng, cams, sr->Q.v.data(), rg) != SLR_OK) break;
-        if (slr_set_rectify_maps(eng, sr->map1().data(), sr->map2().data()) != SLR_OK) break;
+        // calibration and the 16 MB of rectification maps go to the GPU once per session, not once per scan
+        if (!duke::upload_calibration(eng, cams, sr->Q.v.data(), rg, sr->calibrationId(), sr->map1().data(), sr->map2().data())) break;
         if (slr_set_host_input_raw(eng, 1) != SLR_OK) break;
         if (slr_set_auto_contrast(eng, 0) != SLR_OK) break;   // MFReconstruct has no such setting; the engine is shared
+        lap("CUDA context + engine + calib");
+        if (W % 4 == 0 && !getenv("DUKE_HOST_DECODE")) {
+            // files -> GPU: inflate on all host threads, upload + PNG unfiltering + rectification + decode + match +
+            // triangulation on the GPU, the cloud back in PointCloudImage's own storage layout (ingest.h)
+            std::string err;
+            if (!duke::ingest_scan(eng, scanFolder, imgPrefix, imgSuffix, numberOfImgs, W, H, &err)) {
+                fprintf(stderr, "%s\n", err.c_str());
+                slr_run_mf_ingested(eng, 3, 4, blackThreshold, mode, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr);   // drains the copies
+                break;
+            }
+            lap("image files -> inflate -> GPU");
+            float *sums = nullptr;
+            uint8_t *counts = nullptr;
+            if (!duke::cloud_storage_acquire((size_t)scan_w * scan_h, &sums, &counts)) break;
+            n_points_ = 0;
+            if (slr_run_mf_ingested(eng, 3, 4, blackThreshold, mode, scan_w, scan_h, sums, counts, nullptr, nullptr, &n_points_) != SLR_OK) {
+                duke::cloud_storage_release(sums, counts);
+                break;
+            }
+            lap("slr_run_mf_ingested (fused kernel, D2H)");
+            delete points3DProjView;
+            points3DProjView = new PointCloudImage(scan_w, scan_h, sums, counts, duke::cloud_storage_release);
+            lap("PointCloudImage (adopts the buffers)");
+            ok = true;
+            break;
+        }
         if (!(h_stack = duke::pinned_scratch(0, 2 * (size_t)numberOfImgs * P))) break;
         if (!(h_xyz = duke::pinned_scratch(1, P * 3 * sizeof(float)))) break;
         if (!(h_valid = duke::pinned_scratch(2, P))) break;
-        lap("CUDA context + engine + calib + pinned");
         bool loaded = true;
         for (int i = 0; i < 2 && loaded; i++)
             loaded = duke::load_stack(scanFolder[i], imgPrefix[i], imgSuffix, numberOfImgs, W, H,
@@ -111,7 +137,7 @@ bool MFReconstruct::runReconstruction()
         if (slr_run_mf_host(eng, (const uint8_t *)h_stack, 1, 3, 4, blackThreshold, mode, (float *)h_xyz, (uint8_t *)h_valid,
                             nullptr, &n_points_) != SLR_OK)
             break;
-        lap("slr_run_mf_host (H2D, K0, fused, D2H)");
+        lap("slr_run_mf_host (H2D, fused, D2H)");
         delete points3DProjView;
         points3DProjView = new PointCloudImage(scan_w, scan_h, false);
         points3DProjView->addDense((const float *)h_xyz, (const uint8_t *)h_valid, nullptr, W, H);

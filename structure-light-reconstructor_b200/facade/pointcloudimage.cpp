@@ -6,11 +6,20 @@
 #include <thread>
 
 PointCloudImage::PointCloudImage(int imageW, int imageH, bool colorFlag)
-    : w(imageW), h(imageH), has_color_(colorFlag), points_((size_t)imageW * imageH * 3, 0.0f), num_((size_t)imageW * imageH, 0)
+    : w(imageW), h(imageH), has_color_(colorFlag), own_points_((size_t)imageW * imageH * 3, 0.0f), own_num_((size_t)imageW * imageH, 0)
 {
+    points_ = own_points_.data();
+    num_ = own_num_.data();
     if (colorFlag) color_.assign((size_t)imageW * imageH * 3, 0);
 }
-PointCloudImage::~PointCloudImage() {}
+PointCloudImage::PointCloudImage(int imageW, int imageH, float *sums, uint8_t *counts, void (*release)(float *, uint8_t *))
+    : w(imageW), h(imageH), has_color_(false), points_(sums), num_(counts), release_(release)
+{
+}
+PointCloudImage::~PointCloudImage()
+{
+    if (release_) release_(points_, num_);
+}
 
 bool PointCloudImage::setPoint(int i_w, int j_h, duke::Point3f point, duke::Vec3i colorgray)
 {

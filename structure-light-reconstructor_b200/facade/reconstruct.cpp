@@ -117,8 +117,7 @@ bool Reconstruct::runReconstruction_GE()
         float rigid[12];
         const float *rg = nullptr;
         if (scanSN > 0 && duke::load_rigid(savePath_ + "/scan/transfer_mat" + std::to_string(scanSN) + ".txt", rigid)) rg = rigid;
-        if (slr_set_calib(eng, cams, sr->Q.v.data(), rg) != SLR_OK) break;
-        if (slr_set_rectify_maps(eng, sr->map1().data(), sr->map2().data()) != SLR_OK) break;
+        if (!duke::upload_calibration(eng, cams, sr->Q.v.data(), rg, sr->calibrationId(), sr->map1().data(), sr->map2().data())) break;
         if (slr_set_host_input_raw(eng, 1) != SLR_OK) break;
         // Utilities::autoContrast on every rectified image (Duke/reconstruct.cpp:182-183), on the GPU after K0
         if (slr_set_auto_contrast(eng, autoContrast_ ? 1 : 0) != SLR_OK) break;
@@ -170,7 +169,7 @@ bool Reconstruct::runReconstruction()
         float rigid[12];
         const float *rg = nullptr;
         if (scanSN > 0 && duke::load_rigid(savePath_ + "/scan/transfer_mat" + std::to_string(scanSN) + ".txt", rigid)) rg = rigid;
-        if (slr_set_calib(eng, cams, Qid, rg) != SLR_OK) break;
+        if (!duke::upload_calibration(eng, cams, Qid, rg, 0, nullptr, nullptr)) break;
         if (slr_set_host_input_raw(eng, 0) != SLR_OK) break;   // the shared engine may have rectified for a GE / MF scan
         if (slr_set_auto_contrast(eng, autoContrast_ ? 1 : 0) != SLR_OK) break;
         bool loaded = true;

@@ -44,7 +44,13 @@ bool load_stack(const std::string &folder, const std::string &prefix, const std:
             Image img;
             std::string err;
             char msg[1024];
-            if (!read_gray_image(base + suffix, img, &err) && !read_gray_image(base + ".pgm", img, &err)) {
+            bool got = false;
+            try {
+                got = read_gray_image(base + suffix, img, &err) || read_gray_image(base + ".pgm", img, &err);
+            } catch (const std::exception &ex) {   // e.g. bad_alloc on a hostile header: report, do not terminate the thread
+                err = ex.what();
+            }
+            if (!got) {
                 snprintf(msg, sizeof(msg), "Load Images: Scan Images not found! (%s: %s)", (base + suffix).c_str(), err.c_str());
                 errors[i] = msg;
                 failed[i] = 1;
@@ -77,7 +83,15 @@ bool load_stack(const std::string &folder, const std::string &prefix, const std:
 
 namespace {
 std::mutex g_mu;
-struct EngineSlot { int device, W, H; slr_engine *e; };
+struct EngineSlot {
+    int device, W, H;
+    slr_engine *e;
+    bool calib_valid = false, has_rigid = false;
+    slr_camera cams[2];
+    double Q[16];
+    float rigid[12];
+    unsigned long long maps_id = 0;   // stereoRect::calibrationId() of the maps on the GPU (0: none)
+};
 std::vector<EngineSlot> g_engines;      // never destroyed: the driver tears the context down at process exit
 void *g_pinned[4] = {nullptr, nullptr, nullptr, nullptr};
 size_t g_pinned_bytes[4] = {0, 0, 0, 0};
@@ -90,8 +104,41 @@ slr_engine *shared_engine(int device, int W, int H)
         if (s.device == device && s.W == W && s.H == H) return s.e;
     slr_engine *e = nullptr;
     if (slr_create(&e, device, W, H, 1) != SLR_OK) return nullptr;
-    g_engines.push_back({device, W, H, e});
+    EngineSlot slot;
+    slot.device = device;
+    slot.W = W;
+    slot.H = H;
+    slot.e = e;
+    g_engines.push_back(slot);
     return e;
+}
+
+bool upload_calibration(slr_engine *eng, const slr_camera cams[2], const double Q[16], const float *rigid3x4,
+                        unsigned long long cal_id, const int16_t *h_map1, const uint16_t *h_map2)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    EngineSlot *s = nullptr;
+    for (auto &g : g_engines)
+        if (g.e == eng) s = &g;
+    const bool same = s && s->calib_valid && memcmp(s->cams, cams, sizeof(s->cams)) == 0 && memcmp(s->Q, Q, sizeof(s->Q)) == 0 &&
+                      s->has_rigid == (rigid3x4 != nullptr) && (!rigid3x4 || memcmp(s->rigid, rigid3x4, sizeof(s->rigid)) == 0);
+    if (!same) {
+        if (s) s->calib_valid = false;
+        if (slr_set_calib(eng, cams, Q, rigid3x4) != SLR_OK) return false;
+        if (s) {
+            memcpy(s->cams, cams, sizeof(s->cams));
+            memcpy(s->Q, Q, sizeof(s->Q));
+            s->has_rigid = rigid3x4 != nullptr;
+            if (rigid3x4) memcpy(s->rigid, rigid3x4, sizeof(s->rigid));
+            s->calib_valid = true;
+        }
+    }
+    if (h_map1 && h_map2 && !(s && cal_id != 0 && s->maps_id == cal_id)) {
+        if (s) s->maps_id = 0;
+        if (slr_set_rectify_maps(eng, h_map1, h_map2) != SLR_OK) return false;
+        if (s) s->maps_id = cal_id;
+    }
+    return true;
 }
 
 void *pinned_scratch(int slot, size_t bytes)

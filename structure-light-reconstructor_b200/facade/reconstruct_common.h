@@ -27,6 +27,13 @@ slr_engine *shared_engine(int device, int W, int H);
 // Grow-only pinned host buffers shared by the facades (slot 0 image stack, 1 xyz / sums, 2 valid / counts, 3 colour)
 void *pinned_scratch(int slot, size_t bytes);
 
+// slr_set_calib + slr_set_rectify_maps, skipped when this engine already holds exactly these values (cal_id =
+// stereoRect::calibrationId() of the maps; h_map1 == nullptr: no maps).  The reference builds a new reconstructor per
+// scan with the same project calibration; re-uploading 16 MB of maps and rebuilding the undistortPoints tables
+// each time would cost more than the scan.
+bool upload_calibration(slr_engine *eng, const slr_camera cams[2], const double Q[16], const float *rigid3x4,
+                        unsigned long long cal_id, const int16_t *h_map1, const uint16_t *h_map2);
+
 // 3x4 matrix of scan/transfer_mat<sn>.txt (mfreconstruct.cpp:276-282); false if unreadable
 bool load_rigid(const std::string &path, float out[12]);
 

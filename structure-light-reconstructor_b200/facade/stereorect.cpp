@@ -27,8 +27,9 @@ namespace {
 struct CalCache {
     std::vector<double> key;
     duke::RectifyResult r;
-    std::vector<int16_t> map1;
-    std::vector<uint16_t> map2;
+    std::shared_ptr<const std::vector<int16_t>> map1;
+    std::shared_ptr<const std::vector<uint16_t>> map2;
+    unsigned long long id = 0;
 };
 std::mutex g_cal_mu;
 CalCache g_cal;
@@ -47,11 +48,12 @@ void stereoRect::calParameters()
         std::thread right([&] { duke::init_undistort_rectify_map(M2, D2, g_cal.r.R2, g_cal.r.P2, img_size, b1, b2); });
         duke::init_undistort_rectify_map(M1, D1, g_cal.r.R1, g_cal.r.P1, img_size, a1, a2);
         right.join();
-        g_cal.map1 = a1;
-        g_cal.map1.insert(g_cal.map1.end(), b1.begin(), b1.end());
-        g_cal.map2 = a2;
-        g_cal.map2.insert(g_cal.map2.end(), b2.begin(), b2.end());
+        a1.insert(a1.end(), b1.begin(), b1.end());
+        a2.insert(a2.end(), b2.begin(), b2.end());
+        g_cal.map1 = std::make_shared<const std::vector<int16_t>>(std::move(a1));
+        g_cal.map2 = std::make_shared<const std::vector<uint16_t>>(std::move(a2));
         g_cal.key = key;
+        g_cal.id++;
     }
     R1 = g_cal.r.R1;
     R2 = g_cal.r.R2;
@@ -60,13 +62,16 @@ void stereoRect::calParameters()
     Q = g_cal.r.Q;
     map1_ = g_cal.map1;
     map2_ = g_cal.map2;
+    cal_id_ = g_cal.id;
 }
 
 void stereoRect::doStereoRectify(duke::Image &img, bool isleft)
 {
     // cv::remap(INTER_LINEAR), CV_16SC2 maps, BORDER_CONSTANT 0 — same fixed point as k0_rectify.cu
     const int W = img_size.width, H = img_size.height;
-    if (img.empty() || img.width != W || img.height != H || map2_.empty()) return;
+    if (img.empty() || img.width != W || img.height != H || map2_->empty()) return;
+    const std::vector<int16_t> &map1_ = *this->map1_;
+    const std::vector<uint16_t> &map2_ = *this->map2_;
     const size_t P = (size_t)W * H, off = isleft ? 0 : P;
     std::vector<uint8_t> out(P);
     for (int y = 0; y < H; y++)

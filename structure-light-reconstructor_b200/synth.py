@@ -82,3 +82,24 @@ def synth_gray(W, H, scan_w=None, scan_h=None, seed=0, integer_disparity=True, n
             out[:, 2 + 2 * nc + 2 * c] = _finish(np.where(lit & (bit == 1), 200.0, 20.0), noise_dn, rng)
             out[:, 3 + 2 * nc + 2 * c] = _finish(np.where(lit & (bit == 0), 200.0, 20.0), noise_dn, rng)
     return out
+
+
+def write_png_opencv_style(path, img):
+    """An 8-bit grey PNG as cv::imwrite writes the reference's scan images: Sub filter on every row, zlib level 1 with
+    the Z_RLE strategy, the stream cut into 8 KB IDAT chunks (libpng's default buffer)."""
+    import struct
+    import zlib
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    rows = np.empty((h, w + 1), np.uint8)
+    rows[:, 0] = 1
+    rows[:, 1] = img[:, 0]
+    rows[:, 2:] = img[:, 1:] - img[:, :-1]          # uint8 arithmetic wraps mod 256, as the filter does
+    c = zlib.compressobj(1, zlib.DEFLATED, 15, 8, zlib.Z_RLE)
+    z = c.compress(rows.tobytes()) + c.flush()
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 0, 0, 0, 0)) +
+                b"".join(chunk(b"IDAT", z[o:o + 8192]) for o in range(0, len(z), 8192)) + chunk(b"IEND", b""))

@@ -129,6 +129,62 @@ def test_png_pgm_roundtrip_and_filters(duke, tmp_path):
     assert duke.duke_read_gray_image(str(tmp_path / "missing.png").encode(), C.byref(w), C.byref(h), None, 0) == -1
 
 
+def _inflate(duke, comp, n):
+    out = np.full(n + 8, 0xAB, np.uint8)
+    src = np.frombuffer(comp, np.uint8)
+    rc = duke.duke_zlib_inflate(ptr(src), C.c_size_t(len(comp)), ptr(out), C.c_size_t(n))
+    assert (out[n:] == 0xAB).all(), "wrote past the end of the output"
+    return rc, out[:n]
+
+
+def test_own_inflate_equals_zlib_on_every_level_and_strategy(duke):
+    """facade/inflate.cpp (the PNG ingest path's entropy decoder) against zlib streams of every compression level,
+    strategy and memory level — stored, fixed and dynamic blocks, long codes (second-level tables), long distances —
+    and against damaged input, which must be rejected, not trusted."""
+    rng = np.random.default_rng(3)
+    n_cases = 0
+    for kind in range(7):
+        for sz in (0, 1, 7, 300, 5000, 70000, 300000):
+            if kind == 0:
+                raw = rng.integers(0, 256, sz, dtype=np.uint8)                                  # incompressible
+            elif kind == 1:
+                raw = np.zeros(sz, np.uint8)
+            elif kind == 2:                                                                     # noisy fringe, Sub-filtered
+                x = np.arange(sz)
+                v = (128 + 60 * np.sin(x * 0.05) + rng.integers(-3, 4, sz)).astype(np.int16)
+                raw = (np.diff(v, prepend=0) & 255).astype(np.uint8)
+            elif kind == 3:
+                raw = np.frombuffer((b"abcabcabdabc" * (sz // 12 + 1))[:sz], np.uint8)          # short distances
+            elif kind == 4:
+                raw = (np.arange(sz) >> 8).astype(np.uint8)                                     # long runs
+            elif kind == 5:
+                raw = np.where(rng.random(sz) < 0.03, rng.integers(0, 256, sz), 7).astype(np.uint8)
+            else:                                                                               # alphabet grows: long codes
+                raw = (rng.integers(0, 1 << 30, sz) % (1 + (np.arange(sz) >> 10))).astype(np.uint8)
+            for level in (0, 1, 6, 9):
+                for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED):
+                    for mem in (1, 9):
+                        c = zlib.compressobj(level, zlib.DEFLATED, 15, mem, strategy)
+                        comp = c.compress(raw.tobytes()) + c.flush()
+                        rc, out = _inflate(duke, comp, sz)
+                        assert rc == 0 and (out == raw).all(), (kind, sz, level, strategy, mem)
+                        n_cases += 1
+            if sz >= 300:
+                comp = zlib.compress(raw.tobytes(), 6)
+                assert _inflate(duke, comp[:len(comp) // 2], sz)[0] != 0          # truncated
+                assert _inflate(duke, comp, sz - 1)[0] != 0                       # stream longer than the output
+                assert _inflate(duke, comp, sz + 1)[0] != 0                       # stream shorter than the output
+                bad = bytearray(comp)
+                bad[-1] ^= 1                                                      # Adler-32
+                assert _inflate(duke, bytes(bad), sz)[0] != 0
+                for pos in rng.integers(2, len(comp) - 4, 40):                    # bit rot: rejected or (rarely) same length,
+                    bad = bytearray(comp)                                         # never a crash or an overrun
+                    bad[pos] ^= 1 << int(rng.integers(0, 8))
+                    _inflate(duke, bytes(bad), sz)
+    assert n_cases == 7 * 7 * 4 * 5 * 2
+    assert _inflate(duke, b"\x78\x9c", 0)[0] != 0 and _inflate(duke, b"", 0)[0] != 0
+
+
 def write_mat(path, m):
     with open(path, "w") as f:
         for r in np.atleast_2d(m):

@@ -136,6 +136,82 @@ def test_mfreconstruct_facade_end_to_end(tmp_path, oracle, sn, rigid):
             assert probes[k_, 0] == 0
 
 
+def _write_png_filtered(path, img, mode, rng):
+    """8-bit grey PNG the way real encoders write it: per-row filters (mode 'sub' = OpenCV's encoder: Sub on every row,
+    Z_RLE; 'up' = None / Sub / Up rows; 'all' = all five filter types) and the zlib stream cut into 8 KB IDAT chunks."""
+    h, w = img.shape
+    a = img.astype(np.int32)
+    rows = []
+    for y in range(h):
+        t = {"sub": 1, "up": int(rng.integers(0, 3)), "all": int(rng.integers(0, 5))}[mode]
+        left = np.concatenate([[0], a[y, :-1]])
+        up = a[y - 1] if y else np.zeros(w, np.int32)
+        ul = np.concatenate([[0], up[:-1]])
+        if t == 0:
+            f = a[y]
+        elif t == 1:
+            f = a[y] - left
+        elif t == 2:
+            f = a[y] - up
+        elif t == 3:
+            f = a[y] - ((left + up) >> 1)
+        else:
+            pa, pb, pc = np.abs(up - ul), np.abs(left - ul), np.abs(left + up - 2 * ul)
+            f = a[y] - np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, up, ul))
+        rows.append(bytes([t]) + (f & 255).astype(np.uint8).tobytes())
+    c = zlib.compressobj(1, zlib.DEFLATED, 15, 8, zlib.Z_RLE if mode == "sub" else zlib.Z_DEFAULT_STRATEGY)
+    z = c.compress(b"".join(rows)) + c.flush()
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 0, 0, 0, 0)) +
+                chunk(b"tEXt", b"Software\x00test") + b"".join(chunk(b"IDAT", z[o:o + 8192]) for o in range(0, len(z), 8192)) +
+                chunk(b"IEND", b""))
+
+
+def test_mfreconstruct_ingests_real_world_png_encodings(tmp_path, oracle):
+    """The ingest path (facade/ingest.cpp + k_png.cu) on the encodings scan images come in: OpenCV-style Sub-filtered
+    files go to the GPU as filtered scanlines, files with Up rows too (second kernel), files with Average / Paeth rows
+    are unfiltered on their host thread, a .pgm stands in for a missing .png.  Same cloud as the oracle on the pixels,
+    and as the host-decode route (DUKE_HOST_DECODE=1: zlib-free reader + slr_run_mf_host + addDense).  scan size !=
+    camera size exercises addPoint's (i_w, j_h) drop rule in the GPU epilogue."""
+    W, H = 320, 64
+    scan_w, scan_h = 48, 400
+    stacks = synth.synth_mf(W, H, seed=67, integer_disparity=False, noise_dn=2.0)
+    cams = make_project(str(tmp_path), W, H, 0, stacks)
+    rng = np.random.default_rng(1)
+    for cam, side, pre in ((0, "left", "L"), (1, "right", "R")):
+        for i in range(14):
+            path = os.path.join(str(tmp_path), "scan", side, "0", f"{pre}{i}.png")
+            mode = ("sub", "up", "all")[(i + cam) % 3]
+            _write_png_filtered(path, stacks[cam, i], mode, rng)
+    os.remove(os.path.join(str(tmp_path), "scan", "right", "0", "R5.png"))
+    with open(os.path.join(str(tmp_path), "scan", "right", "0", "R5.pgm"), "wb") as f:
+        f.write(b"P5\n%d %d\n255\n" % (W, H) + stacks[1, 5].tobytes())
+    sums, cnt, Q, m1, m2, _ = run_demo("mf", str(tmp_path), 0, scan_w, scan_h, W, H, 40, 0, False)
+    rect = np.stack([[oracle.remap_linear(stacks[c, i], m1[c], m2[c]) for i in range(14)] for c in range(2)])
+    xyz, valid, k, n = oracle.run_mf(rect, cams, Q)
+    pts_o, cnt_o = oracle.pointcloud_from_dense(xyz, valid, scan_w, scan_h)
+    assert cnt.shape == (scan_h, scan_w) and (cnt == cnt_o).all() and cnt.sum() > 500
+    assert (bits(sums[cnt > 0]) == bits(pts_o[cnt_o > 0])).all() and (sums[cnt == 0] == 0).all()
+    os.environ["DUKE_HOST_DECODE"] = "1"
+    try:
+        sums_h, cnt_h, *_ = run_demo("mf", str(tmp_path), 0, scan_w, scan_h, W, H, 40, 0, False)
+    finally:
+        del os.environ["DUKE_HOST_DECODE"]
+    assert (cnt_h == cnt).all() and (bits(sums_h) == bits(sums)).all()
+    # a damaged file is reported, not decoded
+    p = os.path.join(str(tmp_path), "scan", "left", "0", "L3.png")
+    blob = bytearray(open(p, "rb").read())
+    blob[len(blob) // 2] ^= 0x40
+    open(p, "wb").write(bytes(blob))
+    out = os.path.join(str(tmp_path), "out2.bin")
+    r = subprocess.run([DEMO, "mf", str(tmp_path), "0", str(scan_w), str(scan_h), str(W), str(H), "40", "0", "0", out],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "L3.png" in r.stderr
+
+
 def test_reconstruct_ge_facade_end_to_end(tmp_path, oracle):
     W, H = 320, 48
     stacks = synth.synth_gray(W, H, seed=62, noise_dn=2.0)
