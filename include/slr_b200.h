@@ -256,6 +256,29 @@ SLR_API slr_status slr_set_gather_targets(slr_engine *e, int n_targets, float *c
                                           uint8_t *const *d_valid_all, long long first_scan);
 SLR_API slr_status slr_set_row_offset(slr_engine *e, int first_row);
 
+/* ---- rigid alignment + multi-scan merge ----------------------------------------
+ * DotMatch::calMatrix (Duke/dotmatch.cpp:1180-1324): matched marker positions of two consecutive scans -> transfer matrix.
+ *   slr_horn_method    mrpt::scanmatching::HornMethod as the reference calls it (:1238; MRPT 1.2.2 is a third-party
+ *                      dependency that is not part of the reference tree — restated from Horn 1987, see k_merge.cu):
+ *                      pairs = n x {base xyz, moving xyz} (the layout of :1230-1237), out7 = {tx ty tz qr qx qy qz} of
+ *                      the transform that moves `moving` onto `base`; force_unit_scale = 0 is MRPT's default (the
+ *                      translation then carries the estimated scale, which *scale_out also returns).  Host function.
+ *   slr_register_scan  the whole of calMatrix's arithmetic: Horn -> quaternion -> 3x4 matrix (:1241-1250) chained onto
+ *                      the previous scan's accumulated matrix (:1312-1317; prev3x4 = NULL for scanSN == 1) =
+ *                      the contents of scan/transfer_mat<sn>.txt, row-major doubles.  Host function.
+ *   slr_merge_scans    d_xyz_all = float [n_scans][H][W][3] + d_valid_all (e.g. the assembled cloud of
+ *                      slr_set_gather_targets / slr_allgather), h_rigid3x4 = float [n_scans][12] transfer matrices
+ *                      (NULL: none; h_has_rigid[s] == 0: scan s is already in the common frame, as scanSN == 0 is) ->
+ *                      d_points = float [count][3], every valid point transformed as MFReconstruct::triangulation
+ *                      does (Duke/mfreconstruct.cpp:315-323), scans in order, pixels in row-major order; d_source
+ *                      (may be NULL) = int64 [count], index scan*H*W + pixel of each point; *d_count (device) = count.
+ *                      d_points / d_source must hold n_scans*H*W entries.  Stream-ordered. */
+SLR_API slr_status slr_horn_method(const double *pairs, int n, int force_unit_scale, double out7[7], double *scale_out);
+SLR_API slr_status slr_register_scan(const double *pairs, int n, const double *prev3x4, double out3x4[12]);
+SLR_API slr_status slr_merge_scans(slr_engine *e, const float *d_xyz_all, const uint8_t *d_valid_all, int n_scans,
+                                   const float *h_rigid3x4, const uint8_t *h_has_rigid, float *d_points,
+                                   long long *d_source, unsigned long long *d_count);
+
 /* ---- mesh indexing ---------------------------------------------------------- */
 /* The index passes of MeshCreator::exportPlyMesh / exportObjMesh, Duke/meshcreator.cpp:16-65, 67-166, on a
  * PointCloudImage stored as the reference stores it (Duke/pointcloudimage.cpp:3-13): d_sum = float [h][w][3]

@@ -64,6 +64,7 @@ EXPORTS = [
     "slr_kernel_launches", "slr_mesh_index", "slr_mesh_index_host", "slr_allgather", "slr_nccl_unique_id",
     "slr_nccl_comm_create", "slr_nccl_comm_destroy", "slr_set_rectify_maps", "slr_rectify_stack", "slr_set_host_input_raw", "slr_run_gray_host",
     "slr_run_mf_raw", "slr_ingest_begin", "slr_ingest_image", "slr_run_mf_ingested",
+    "slr_horn_method", "slr_register_scan", "slr_merge_scans",
 ]
 
 
@@ -95,6 +96,9 @@ def capi():
     lib.slr_bucket_triangulate.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, u64p]
     lib.slr_run_mf.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, u64p]
     lib.slr_run_mf_raw.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, u64p]
+    lib.slr_horn_method.argtypes = [vp, i32, i32, vp, vp]
+    lib.slr_register_scan.argtypes = [vp, i32, vp, vp]
+    lib.slr_merge_scans.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.slr_ingest_begin.argtypes = [vp, i32]
     lib.slr_ingest_image.argtypes = [vp, i32, vp, i32, i32]
     lib.slr_run_mf_ingested.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(C.c_ulonglong)]
@@ -155,6 +159,26 @@ def generate_mf_patterns(projW: int, projH: int) -> np.ndarray:
     out = np.empty((14, projH, projW), np.uint8)
     _check(capi().slr_generate_mf_patterns(out.ctypes.data, projW, projH), "slr_generate_mf_patterns")
     return out
+
+
+def horn_method(base, moving, force_unit_scale=False):
+    """slr_horn_method: (7-vector {tx ty tz qr qx qy qz}, scale) of the transform that moves `moving` [n,3] onto `base`."""
+    pairs = np.ascontiguousarray(np.concatenate([np.asarray(base, np.float64), np.asarray(moving, np.float64)], 1))
+    out, scale = np.zeros(7), C.c_double(0)
+    _check(capi().slr_horn_method(C.c_void_p(pairs.ctypes.data), len(pairs), int(force_unit_scale), C.c_void_p(out.ctypes.data),
+                                  C.byref(scale)), "slr_horn_method")
+    return out, scale.value
+
+
+def register_scan(base, moving, prev=None):
+    """slr_register_scan: DotMatch::calMatrix's transfer matrix [3,4] (float64) for a scan whose markers `moving` were
+    matched to the previous scan's `base`; prev = the previous scan's accumulated matrix (None for the first)."""
+    pairs = np.ascontiguousarray(np.concatenate([np.asarray(base, np.float64), np.asarray(moving, np.float64)], 1))
+    out = np.zeros(12)
+    pv = np.ascontiguousarray(np.asarray(prev, np.float64).reshape(12)) if prev is not None else None
+    _check(capi().slr_register_scan(C.c_void_p(pairs.ctypes.data), len(pairs), C.c_void_p(pv.ctypes.data) if pv is not None else None,
+                                    C.c_void_p(out.ctypes.data)), "slr_register_scan")
+    return out.reshape(3, 4)
 
 
 def synthetic_rig(W: int, H: int, f: float = 2400.0, tx: float = -200.0, distort: bool = True):
@@ -445,6 +469,21 @@ class Engine:
     def set_row_offset(self, first_row: int):
         self._bind_stream()
         _check(self.lib.slr_set_row_offset(self.h, first_row), "slr_set_row_offset")
+
+    def merge_scans(self, xyz_all, valid_all, rigid=None, has_rigid=None):
+        """slr_merge_scans -> (points [count,3] device tensor, source [count] int64 device tensor)"""
+        n = xyz_all.shape[0]
+        cells = n * self.H * self.W
+        pts = self._empty((cells, 3), self._torch.float32)
+        src = self._empty((cells,), self._torch.int64)
+        cnt = self._torch.zeros(1, dtype=self._torch.int64, device=xyz_all.device)
+        r = np.ascontiguousarray(np.asarray(rigid, np.float32).reshape(n, 12)) if rigid is not None else None
+        hr = np.ascontiguousarray(np.asarray(has_rigid, np.uint8)) if has_rigid is not None else None
+        self._bind_stream()
+        _check(self.lib.slr_merge_scans(self.h, self._p(xyz_all), self._p(valid_all), n, self._hp(r), self._hp(hr), self._p(pts),
+                                        self._p(src), self._p(cnt)), "slr_merge_scans")
+        c = int(cnt.item())
+        return pts[:c], src[:c]
 
     def mesh_index(self, sums, counts, first_vertex=0):
         """slr_mesh_index on device tensors sums [h,w,3] f32 / counts [h,w] u8 -> (vertices [nv,3], vertex_src [nv],

@@ -74,6 +74,7 @@ static void free_engine(slr_engine *e)
     cudaFree(e->d_map2);
     cudaFree(e->d_stage_rect[0]);
     cudaFree(e->d_stage_rect[1]);
+    cudaFree(e->d_merge);
     cudaFree(e->d_ingest);
     cudaFree(e->d_cloud_sum);
     cudaFree(e->d_cloud_cnt);
@@ -900,6 +901,15 @@ extern "C" slr_status slr_run_mf_host(slr_engine *e, const uint8_t *h_stack, int
                              return slr_launch_fused_mf(e, d_in, 1, F, S, black_thr, mode, d_xyz, d_valid,
                                                         h_match_k ? d_k : nullptr, e->d_counter);
                          }, raw);
+}
+
+extern "C" slr_status slr_merge_scans(slr_engine *e, const float *d_xyz_all, const uint8_t *d_valid_all, int n_scans,
+                                      const float *h_rigid3x4, const uint8_t *h_has_rigid, float *d_points,
+                                      long long *d_source, unsigned long long *d_count)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(d_xyz_all && d_valid_all && d_points && d_count && n_scans > 0, "slr_merge_scans: bad argument");
+    return slr_launch_merge(e, d_xyz_all, d_valid_all, n_scans, h_rigid3x4, h_has_rigid, d_points, d_source, d_count);
 }
 
 // ------------------------------------------------------------------------------------------------

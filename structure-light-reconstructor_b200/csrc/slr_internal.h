@@ -110,6 +110,9 @@ struct slr_engine {
     uint8_t *d_cloud_cnt = nullptr;
     size_t cloud_cells = 0;
 
+    void *d_merge = nullptr;         // slr_merge_scans: tile offsets + per-scan transforms
+    size_t merge_bytes = 0;
+
     unsigned long long launches = 0;
 };
 
@@ -173,6 +176,8 @@ slr_status slr_launch_fused_ge(slr_engine *e, const uint8_t *d_stack, int batch,
 slr_status slr_launch_undistort_maps(slr_engine *e);
 slr_status slr_launch_rectify(slr_engine *e, const uint8_t *d_raw, int batch, int N, uint8_t *d_out);
 slr_status slr_build_strict_tables(slr_engine *e);
+slr_status slr_launch_merge(slr_engine *e, const float *d_xyz, const uint8_t *d_valid, int n_scans, const float *h_rigid,
+                            const uint8_t *h_has_rigid, float *d_points, long long *d_source, unsigned long long *d_count);
 slr_status slr_launch_png_unfilter(slr_engine *e, cudaStream_t stream, const uint8_t *d_filtered, uint8_t *d_plane,
                                    bool has_up_rows);
 slr_status slr_launch_cloud_image(slr_engine *e, const float *d_xyz, const uint8_t *d_valid, int scan_w, int scan_h,

@@ -367,3 +367,35 @@ def test_png_ingest_unfilters_on_the_gpu_and_returns_the_pointcloudimage_layout(
     exp_cnt[:ww, :hh] = v.T
     exp_sum[:ww, :hh] = np.where(v[..., None], xyz_o[:hh, :ww], 0).transpose(1, 0, 2)
     assert (h_cnt == exp_cnt).all() and (bits(h_sum) == bits(exp_sum)).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-scan merge — the clouds of several scans, each with its transfer matrix, as one point list
+# ------------------------------------------------------------------------------------------------
+def test_merge_scans_equals_the_per_scan_rigid_epilogue_and_the_oracle(cuda_engine_factory, oracle):
+    W, H, B = 640, 40, 3
+    eng = cuda_engine_factory(W, H, B)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    stack = np.stack([synth.synth_mf(W, H, seed=70 + s, integer_disparity=False, noise_dn=1.0) for s in range(B)])
+    Ms = np.array([np.eye(3, 4),
+                   [[0.98, -0.17, 0.05, 12.5], [0.17, 0.98, 0.02, -3.25], [-0.05, -0.01, 0.99, 40.0]],
+                   [[0.7, 0.1, -0.7, -100.0], [0.0, 0.99, 0.14, 3.0], [0.71, -0.1, 0.69, 250.5]]], np.float32)
+    has = np.array([0, 1, 1], np.uint8)                 # scan 0 is the common frame (scanSN == 0: no transfer matrix)
+    xyz, valid, k, n = eng.run_mf(_t(stack))
+    pts, src = eng.merge_scans(xyz, valid, Ms, has)
+    pts, src = pts.cpu().numpy(), src.cpu().numpy()
+    exp_pts, exp_src = [], []
+    for s in range(B):
+        xyz_o, valid_o, _, n_o = oracle.run_mf(stack[s], cams, Q, rigid=Ms[s] if has[s] else None,
+                                               nthreads=oracle.max_threads())
+        idx = np.flatnonzero(valid_o.reshape(-1))
+        exp_pts.append(xyz_o.reshape(-1, 3)[idx])
+        exp_src.append(idx + s * W * H)
+    exp_pts, exp_src = np.concatenate(exp_pts), np.concatenate(exp_src)
+    assert len(pts) == len(exp_pts) == int(n.item()) and len(pts) > 3000
+    assert (src == exp_src).all() and (bits(pts) == bits(exp_pts)).all()
+    # no matrices: plain ordered compaction
+    p0, s0 = eng.merge_scans(xyz, valid)
+    assert (s0.cpu().numpy() == exp_src).all()
+    assert (bits(p0.cpu().numpy()) == bits(xyz.cpu().numpy().reshape(-1, 3)[exp_src])).all()

@@ -91,3 +91,63 @@ def test_oracle_pipeline_on_numpy_synth(oracle):
     xyz, valid, mk, n = oracle.run_mf(st, cams, Q)
     assert n == valid.sum() and n > 0.5 * W * H
     assert np.isfinite(xyz[valid == 1]).all() and np.isnan(xyz[valid == 0]).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# DotMatch::calMatrix's arithmetic (Duke/dotmatch.cpp:1180-1324) — host functions, no GPU needed
+# ------------------------------------------------------------------------------------------------
+def _kabsch(base, moving):
+    """independent solution: rotation + translation moving -> base by SVD (Kabsch / Umeyama with unit scale)"""
+    cb, cm = base.mean(0), moving.mean(0)
+    Hm = (moving - cm).T @ (base - cb)
+    U, _, Vt = np.linalg.svd(Hm)
+    d = np.sign(np.linalg.det(Vt.T @ U.T))
+    R = Vt.T @ np.diag([1, 1, d]) @ U.T
+    return R, cb - R @ cm
+
+
+def _rot(axis, deg):
+    axis = np.asarray(axis, float) / np.linalg.norm(axis)
+    a = np.deg2rad(deg)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + np.sin(a) * K + (1 - np.cos(a)) * K @ K
+
+
+@pytest.mark.parametrize("n,noise,deg", [(3, 0.0, 20), (12, 0.0, 175), (40, 0.05, 63), (6, 0.0, 0.0)])
+def test_horn_method_and_transfer_matrix_chain(n, noise, deg):
+    rng = np.random.default_rng(n)
+    R0, t0 = _rot([0.3, -1, 0.5], deg), np.array([12.5, -40.0, 310.0])
+    moving = rng.normal(0, 80, (n, 3)) + [0, 0, 600]
+    base = moving @ R0.T + t0 + rng.normal(0, noise, (n, 3))
+    q7, scale = slr_b200.horn_method(base, moving, force_unit_scale=True)
+    R, t = _kabsch(base, moving)
+    w, x, y, z = q7[3:]
+    assert w >= 0 and abs(w * w + x * x + y * y + z * z - 1) < 1e-12
+    Rq = np.array([[w*w + x*x - y*y - z*z, 2*(x*y - w*z), 2*(x*z + w*y)],
+                   [2*(x*y + w*z), w*w - x*x + y*y - z*z, 2*(y*z - w*x)],
+                   [2*(z*x - w*y), 2*(z*y + w*x), w*w - x*x - y*y + z*z]])
+    assert np.allclose(Rq, R, atol=1e-9) and np.allclose(q7[:3], t, atol=1e-6)
+    assert abs(scale - 1) < (1e-9 if noise == 0 else 0.01)
+    if noise == 0:
+        assert np.allclose(Rq, R0, atol=1e-9) and np.allclose(q7[:3], t0, atol=1e-7)
+    # MRPT's default: the translation carries the estimated scale  t = c_base - s R c_moving
+    q7s, s = slr_b200.horn_method(base, moving)
+    assert np.allclose(q7s[3:], q7[3:]) and np.allclose(q7s[:3], base.mean(0) - s * Rq @ moving.mean(0), atol=1e-9)
+    # calMatrix: scan 1 writes the matrix itself, scan n > 1 chains it onto the accumulated one (:1299-1317)
+    M1 = slr_b200.register_scan(base, moving)
+    assert np.allclose(M1[:, :3], Rq, atol=1e-12) and np.allclose(M1[:, 3], q7s[:3], atol=1e-12)
+    R2, t2 = _rot([1, 0.2, 0], 33), np.array([-5.0, 7.0, 90.0])
+    moving2 = rng.normal(0, 60, (n, 3))
+    base2 = moving2 @ R2.T + t2
+    M2 = slr_b200.register_scan(base2, moving2, prev=M1)
+    cur = slr_b200.register_scan(base2, moving2)
+    assert np.allclose(M2[:, :3], M1[:, :3] @ cur[:, :3], atol=1e-12)
+    assert np.allclose(M2[:, 3], M1[:, :3] @ cur[:, 3] + M1[:, 3], atol=1e-9)
+    # a point of scan 2 lands where chaining the two motions puts it
+    p = np.array([3.0, -2.0, 50.0])
+    assert np.allclose(M2[:, :3] @ p + M2[:, 3], M1[:, :3] @ (cur[:, :3] @ p + cur[:, 3]) + M1[:, 3], atol=1e-9)
+
+
+def test_horn_method_rejects_too_few_points():
+    with pytest.raises(slr_b200.SlrError):
+        slr_b200.horn_method(np.zeros((2, 3)), np.zeros((2, 3)))
