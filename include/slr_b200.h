@@ -313,7 +313,7 @@ SLR_API slr_status slr_host_free(void *p);
  * d_stack = [batch][2][14][H][W].  integer_disparity != 0 makes left/right samples coincide exactly. */
 SLR_API slr_status slr_synth_mf(slr_engine *e, uint8_t *d_stack, int batch, int proj_w,
                                 unsigned seed, int integer_disparity, float noise_dn);
-/* The same scene under F frequencies x S shifts (BASELINE config 5: F = 4, S = 8; frequencies 70, 64, 59, 55, ...):
+/* The same scene under F frequencies x S shifts (BASELINE config 5: F = 4, S = 8; frequencies 70, 64, 59, 56, ...):
  * d_stack = [batch][2][2+F*S][H][W], plane [2 + S*f + s].  F = 3, S = 4 gives slr_synth_mf's bytes. */
 SLR_API slr_status slr_synth_mf_fs(slr_engine *e, uint8_t *d_stack, int batch, int F, int S, int proj_w,
                                    unsigned seed, int integer_disparity, float noise_dn);

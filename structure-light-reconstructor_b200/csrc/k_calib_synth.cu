@@ -140,7 +140,9 @@ __global__ void k_synth_mf(uint8_t *__restrict__ stack, int W, int H, int batch,
     const uint32_t key0 = hash_u32(seed ^ (uint32_t)(view * 0x01000193u)) + (uint32_t)(i * W + x) * keys_per_px;
     base[0] = add_noise(lit ? 200.0f : 30.0f, noise_dn, key0);
     base[P] = add_noise(20.0f, noise_dn, key0 + 1);
-    const int freq[8] = {70, 64, 59, 55, 52, 50, 47, 45};  // first three: Duke/multifrequency.cpp:3
+    // first three: Duke/multifrequency.cpp:3; the fourth keeps the last level of a 4-frequency cascade from beating at
+    // frequency 0 ((70-64)-(64-59) = 1, (64-59)-(59-56) = 2; 55 would give 1 and 1: a constant phase along every row)
+    const int freq[8] = {70, 64, 59, 56, 52, 50, 47, 45};
     for (int f = 0; f < F; f++)
         for (int sft = 0; sft < S; sft++) {
             // same form as the reference's generator (Duke/multifrequency.cpp:27) at a fractional column u; the shift

@@ -59,9 +59,10 @@ class PeerAssembly:
         dist.all_gather_object(everyone, handles, group=group)
         for slot in range(slots):
             mapped = []
-            for r in range(self.world):
-                if r == self.rank:
-                    continue
+            # rank r walks its targets in the order r+1, r+2, ...: at any moment every GPU is written by ONE peer (all
+            # ranks starting with rank 0's buffer would queue seven writers on one NVLink ingress at a time)
+            for k in range(1, self.world):
+                r = (self.rank + k) % self.world
                 xh, vh = everyone[r][slot]
                 mapped.append((eng.peer_open(xh), eng.peer_open(vh)))
             self.peers.append(mapped)

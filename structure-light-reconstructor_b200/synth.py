@@ -4,7 +4,10 @@ from __future__ import annotations
 
 import numpy as np
 
-FREQ = (70, 64, 59, 55, 52, 50, 47, 45)   # first three: Duke/multifrequency.cpp:3; the rest extend the series
+# first three: Duke/multifrequency.cpp:3.  The fourth is 56, not the 55 a constant-difference series would give: a
+# heterodyne cascade subtracts neighbouring beats, (70-64)-(64-59) = 1 and (64-59)-(59-f4) must not be 1 as well, or the
+# last level beats at frequency 0 and every pixel of a row decodes to the same phase (with 56: 1 and 2 -> one period).
+FREQ = (70, 64, 59, 56, 52, 50, 47, 45)
 PI_GEN = 3.1416            # Duke/multifrequency.h:5
 
 
