@@ -120,6 +120,30 @@ def main():
     ms = timed(lambda: eng.rectify_stack(mf))
     c = cpu_time(lambda: [orc.remap_linear(h_mf[0, cam, n], m1s[cam], m2s[cam]) for cam in range(2) for n in range(14)]) if orc else None
     report("k0_rectify (14 planes)", "stereoRect::doStereoRectify (cv::remap)", ms, B * 2 * P * (14 * 2 + 6), c, B * 2 * 14 * P, "pixels")
+    # raw stacks -> XYZ in one kernel (N1 as written): rectification inside the fused kernel's stage fill
+    ms = timed(lambda: eng.run_mf_raw(mf, out=out))
+    report("k_fused_flow<RAW> (rectify + strict MF pipeline, one kernel)", "doStereoRectify x 28 + MFReconstruct::runReconstruction - IO", ms,
+           B * (2 * P * 14 + P * 13) + 2 * P * 6, None, B * P, "pixels")
+    rect_tmp = torch.empty_like(mf)
+    ms = timed(lambda: eng.run_mf(eng.rectify_stack(mf, out=rect_tmp), out=out))
+    report("k0_rectify then k_fused_flow (two kernels)", "same", ms, B * (2 * P * 14 + P * 13) + 2 * P * 6, None, B * P, "pixels")
+    del rect_tmp
+    # ---------------- N4: PNG unfilter (Sub rows) + PointCloudImage layout; N2: merge ----------------
+    filt = torch.randint(0, 256, (28, H, W + 1), dtype=torch.uint8, device="cuda")
+    filt[:, :, 0] = 1
+    planes = torch.empty((28, H, W), dtype=torch.uint8, device="cuda")
+    lib = slr_b200.capi()
+    import ctypes as C
+    def unfilter_all():
+        for k in range(28):
+            lib.slr_png_unfilter(eng.h, C.c_void_p(filt[k].data_ptr()), C.c_void_p(planes[k].data_ptr()), 0)
+    eng._bind_stream()
+    ms = timed(unfilter_all)
+    report("k_png_rows (28 images of Sub-filtered scanlines = one scan)", "PNG unfiltering inside cv::imread", ms, 28 * (P + H + P), None, 28 * P, "pixels")
+    pts, src = eng.merge_scans(out[0], out[1])
+    ms = timed(lambda: eng.merge_scans(out[0], out[1]))
+    report("slr_merge_scans (ordered compaction + 3x4 transform)", "transfer_mat application + concatenation of the scans' clouds", ms,
+           B * P * 13 + pts.shape[0] * 20, None, B * P, "pixels")
     # ---------------- K5: mesh indexing of one full-frame cloud (N3) ----------------
     import oracle_lib as _ol
     _o = orc if orc else _ol.load()

@@ -206,6 +206,9 @@ SLR_API slr_status slr_run_ge_host(slr_engine *e, const uint8_t *h_stack, int ba
  *                      Duke/pointcloudimage.cpp:86-97): h_sum = float [scan_h][scan_w][3], h_cnt = uint8 [scan_h][scan_w],
  *                      cell (i_w = image row, j_h = image column), points with i_w >= scan_w or j_h >= scan_h dropped.
  *                      Either output pair may be NULL.  Synchronous. */
+/* The GPU unfilter on its own, device pointers, stream-ordered: d_scanlines = H x [type][W bytes] (types 0 / 1 / 2),
+ * d_pixels = H x W. */
+SLR_API slr_status slr_png_unfilter(slr_engine *e, const uint8_t *d_scanlines, uint8_t *d_pixels, int has_up_rows);
 SLR_API slr_status slr_ingest_begin(slr_engine *e, int n_images);
 SLR_API slr_status slr_ingest_image(slr_engine *e, int index, const uint8_t *h_data, int filtered, int has_up_rows);
 SLR_API slr_status slr_run_mf_ingested(slr_engine *e, int F, int S, int black_thr, int mode, int scan_w, int scan_h,

@@ -64,7 +64,7 @@ EXPORTS = [
     "slr_kernel_launches", "slr_mesh_index", "slr_mesh_index_host", "slr_allgather", "slr_nccl_unique_id",
     "slr_nccl_comm_create", "slr_nccl_comm_destroy", "slr_set_rectify_maps", "slr_rectify_stack", "slr_set_host_input_raw", "slr_run_gray_host",
     "slr_run_mf_raw", "slr_ingest_begin", "slr_ingest_image", "slr_run_mf_ingested",
-    "slr_horn_method", "slr_register_scan", "slr_merge_scans",
+    "slr_horn_method", "slr_register_scan", "slr_merge_scans", "slr_png_unfilter",
 ]
 
 
@@ -99,6 +99,7 @@ def capi():
     lib.slr_horn_method.argtypes = [vp, i32, i32, vp, vp]
     lib.slr_register_scan.argtypes = [vp, i32, vp, vp]
     lib.slr_merge_scans.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.slr_png_unfilter.argtypes = [vp, vp, vp, i32]
     lib.slr_ingest_begin.argtypes = [vp, i32]
     lib.slr_ingest_image.argtypes = [vp, i32, vp, i32, i32]
     lib.slr_run_mf_ingested.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(C.c_ulonglong)]

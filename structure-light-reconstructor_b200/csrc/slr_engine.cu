@@ -953,6 +953,14 @@ extern "C" slr_status slr_ingest_image(slr_engine *e, int index, const uint8_t *
     return slr_launch_png_unfilter(e, e->copy_in, f, plane, has_up_rows != 0);
 }
 
+extern "C" slr_status slr_png_unfilter(slr_engine *e, const uint8_t *d_scanlines, uint8_t *d_pixels, int has_up_rows)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(d_scanlines && d_pixels && e->W % 4 == 0 && ((uintptr_t)d_pixels & 3) == 0,
+                "slr_png_unfilter: bad argument (width and output must be multiples of 4)");
+    return slr_launch_png_unfilter(e, e->stream, d_scanlines, d_pixels, has_up_rows != 0);
+}
+
 extern "C" slr_status slr_run_mf_ingested(slr_engine *e, int F, int S, int black_thr, int mode, int scan_w, int scan_h,
                                           float *h_sum, uint8_t *h_cnt, float *h_xyz, uint8_t *h_valid,
                                           unsigned long long *h_n_points)
