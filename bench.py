@@ -685,7 +685,8 @@ def main():
             config["single_scan_latency_ms"] = single_scan_ms
             config["raw_input"] = dict(raw_leg, note="the same stacks taken as RAW camera images: stereoRect::doStereoRectify "
                                        "(cv::remap, CV_16SC2 maps of a 0.4 degree / 0.4 % warp) inside the fused kernel's "
-                                       "stage fill vs as a separate pass; algorithmic bytes = the step's + 6 map bytes per "
+                                       "stage fill (one launch, the rectified stack never exists in HBM) vs as a separate "
+                                       "pass (K0 writes it, the fused kernel reads it back); algorithmic bytes = the step's + 6 map bytes per "
                                        "pixel and camera")
         result = {
             "metric": METRIC, "value": points_all / (ms_per_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,

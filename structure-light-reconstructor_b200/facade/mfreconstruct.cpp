@@ -127,10 +127,7 @@ bool MFReconstruct::runReconstruction()
         if (!(h_stack = duke::pinned_scratch(0, 2 * (size_t)numberOfImgs * P))) break;
         if (!(h_xyz = duke::pinned_scratch(1, P * 3 * sizeof(float)))) break;
         if (!(h_valid = duke::pinned_scratch(2, P))) break;
-        bool loaded = true;
-        for (int i = 0; i < 2 && loaded; i++)
-            loaded = duke::load_stack(scanFolder[i], imgPrefix[i], imgSuffix, numberOfImgs, W, H,
-                                      (uint8_t *)h_stack + (size_t)i * numberOfImgs * P);
+        const bool loaded = duke::load_stacks(scanFolder, imgPrefix, imgSuffix, 2, numberOfImgs, W, H, (uint8_t *)h_stack);
         if (!loaded) break;
         lap("image files -> pinned stack");
         n_points_ = 0;

@@ -125,9 +125,7 @@ bool Reconstruct::runReconstruction_GE()
         if (!(h_xyz = duke::pinned_scratch(1, P * 3 * sizeof(float)))) break;
         if (!(h_valid = duke::pinned_scratch(2, P))) break;
         if (haveColor && !(h_color = duke::pinned_scratch(3, P))) break;
-        bool loaded = true;
-        for (int i = 0; i < 2 && loaded; i++)
-            loaded = duke::load_stack(scanFolder[i], imgPrefix[i], imgSuffix, nimg, W, H, (uint8_t *)h_stack + (size_t)i * nimg * P);
+        const bool loaded = duke::load_stacks(scanFolder, imgPrefix, imgSuffix, 2, nimg, W, H, (uint8_t *)h_stack);
         if (!loaded) break;
         unsigned long long n = 0;
         if (slr_run_ge_host(eng, (const uint8_t *)h_stack, 1, nbits, blackThreshold, whiteThreshold, scan_w, haveColor ? 1 : 0,
@@ -172,9 +170,7 @@ bool Reconstruct::runReconstruction()
         if (!duke::upload_calibration(eng, cams, Qid, rg, 0, nullptr, nullptr)) break;
         if (slr_set_host_input_raw(eng, 0) != SLR_OK) break;   // the shared engine may have rectified for a GE / MF scan
         if (slr_set_auto_contrast(eng, autoContrast_ ? 1 : 0) != SLR_OK) break;
-        bool loaded = true;
-        for (int i = 0; i < 2 && loaded; i++)
-            loaded = duke::load_stack(scanFolder[i], imgPrefix[i], imgSuffix, nimg, W, H, stack.data() + (size_t)i * nimg * P);
+        const bool loaded = duke::load_stacks(scanFolder, imgPrefix, imgSuffix, 2, nimg, W, H, stack.data());
         if (!loaded) break;
         unsigned long long n = 0;
         if (slr_run_gray_host(eng, stack.data(), 1, nc, nr, blackThreshold, whiteThreshold, scan_w, scan_h, sum.data(),

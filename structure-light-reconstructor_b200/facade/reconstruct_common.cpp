@@ -30,6 +30,14 @@ slr_camera to_slr_camera(const VirtualCamera &vc)
 bool load_stack(const std::string &folder, const std::string &prefix, const std::string &suffix, int n, int W, int H,
                 uint8_t *dst)
 {
+    const std::string folders[2] = {folder, folder}, prefixes[2] = {prefix, prefix};
+    return load_stacks(folders, prefixes, suffix, 1, n, W, H, dst);
+}
+
+bool load_stacks(const std::string folders[2], const std::string prefixes[2], const std::string &suffix, int cams, int n_per_cam,
+                 int W, int H, uint8_t *dst)
+{
+    const int n = cams * n_per_cam;
     // The images of a stack are independent files: decode them on all host threads (PNG inflate of a 1280x1024
     // frame costs ~10 ms, the GPU pipeline for the whole scan ~0.05 ms).  Errors are reported for the lowest failing
     // index, as the reference's sequential loop would (mfreconstruct.cpp:119-139).
@@ -40,7 +48,7 @@ bool load_stack(const std::string &folder, const std::string &prefix, const std:
         for (;;) {
             const int i = next.fetch_add(1);
             if (i >= n) return;
-            const std::string base = folder + prefix + std::to_string(i);
+            const std::string base = folders[i / n_per_cam] + prefixes[i / n_per_cam] + std::to_string(i % n_per_cam);
             Image img;
             std::string err;
             char msg[1024];

@@ -18,6 +18,10 @@ slr_camera to_slr_camera(const VirtualCamera &vc);
 // missing / mismatching image, after printing what the reference shows in a message box.
 bool load_stack(const std::string &folder, const std::string &prefix, const std::string &suffix, int n, int W, int H,
                 uint8_t *dst);
+// Both cameras' stacks in one pass over all host threads (2 x n images share one work queue: three rounds of decoding
+// instead of four for 2 x 24 Gray-code images on 16 threads): dst[cam][i][H][W].
+bool load_stacks(const std::string folders[2], const std::string prefixes[2], const std::string &suffix, int cams, int n_per_cam,
+                 int W, int H, uint8_t *dst);
 
 // Process-wide engine for (device, W, H): created on first use and kept, so that only the first reconstruction of a
 // session pays for CUDA context creation (~0.5 s) and the device / pinned allocations.  The reference news a
