@@ -211,9 +211,20 @@ SLR_API slr_status slr_run_ge_host(slr_engine *e, const uint8_t *h_stack, int ba
 SLR_API slr_status slr_png_unfilter(slr_engine *e, const uint8_t *d_scanlines, uint8_t *d_pixels, int has_up_rows);
 SLR_API slr_status slr_ingest_begin(slr_engine *e, int n_images);
 SLR_API slr_status slr_ingest_image(slr_engine *e, int index, const uint8_t *h_data, int filtered, int has_up_rows);
+/* Gives up a scan begun with slr_ingest_begin (an image turned out to be missing): waits until no copy reads the
+ * caller's buffers any more. */
+SLR_API slr_status slr_ingest_abort(slr_engine *e);
 SLR_API slr_status slr_run_mf_ingested(slr_engine *e, int F, int S, int black_thr, int mode, int scan_w, int scan_h,
                                        float *h_sum, uint8_t *h_cnt, float *h_xyz, uint8_t *h_valid,
                                        unsigned long long *h_n_points);
+/* The Gray-EPI pipeline on an ingested scan of 2 * (2 + 2*nbits_col) images: Reconstruct::loadCamImgs' rectification
+ * (slr_set_host_input_raw) and autoContrast (slr_set_auto_contrast) + runReconstruction_GE (Duke/reconstruct.cpp:150-196,
+ * 271-307, 555-611).  code_w = the scan width the codes are checked against (slr_run_ge's scan_w); scan_w / scan_h = the
+ * PointCloudImage size of the h_sum / h_cnt outputs; h_cell_gray = uint8 [scan_h][scan_w], the colour every cell received
+ * (have_color; the reference stores it as a grey triple); h_xyz / h_valid / h_color as slr_run_ge_host.  Synchronous. */
+SLR_API slr_status slr_run_ge_ingested(slr_engine *e, int nbits_col, int black_thr, int white_thr, int code_w, int have_color,
+                                       int scan_w, int scan_h, float *h_sum, uint8_t *h_cnt, uint8_t *h_cell_gray,
+                                       float *h_xyz, uint8_t *h_valid, uint8_t *h_color, unsigned long long *h_n_points);
 /* Reconstruct::runReconstruction minus image IO (Gray-only: column + row codes on UN-rectified images, ray-ray
  * triangulation), Duke/reconstruct.cpp:230-265.  h_stack = [batch][2][2+2*nbits_col+2*nbits_row][H][W];
  * h_sum = float [batch][scan_w*scan_h][3], h_cnt = uint8 [batch][scan_w*scan_h], indexed ac(x,y) = x*scan_h + y. */

@@ -63,7 +63,7 @@ EXPORTS = [
     "slr_peer_free", "slr_set_gather_targets", "slr_set_row_offset", "slr_synth_gray",
     "slr_kernel_launches", "slr_mesh_index", "slr_mesh_index_host", "slr_allgather", "slr_nccl_unique_id",
     "slr_nccl_comm_create", "slr_nccl_comm_destroy", "slr_set_rectify_maps", "slr_rectify_stack", "slr_set_host_input_raw", "slr_run_gray_host",
-    "slr_run_mf_raw", "slr_ingest_begin", "slr_ingest_image", "slr_run_mf_ingested",
+    "slr_run_mf_raw", "slr_ingest_begin", "slr_ingest_image", "slr_run_mf_ingested", "slr_run_ge_ingested", "slr_ingest_abort",
     "slr_horn_method", "slr_register_scan", "slr_merge_scans", "slr_png_unfilter",
 ]
 
@@ -103,6 +103,8 @@ def capi():
     lib.slr_ingest_begin.argtypes = [vp, i32]
     lib.slr_ingest_image.argtypes = [vp, i32, vp, i32, i32]
     lib.slr_run_mf_ingested.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(C.c_ulonglong)]
+    lib.slr_ingest_abort.argtypes = [vp]
+    lib.slr_run_ge_ingested.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_ulonglong)]
     lib.slr_run_ge.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, u64p]
     lib.slr_run_mf_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, C.POINTER(C.c_ulonglong)]
     lib.slr_run_ge_host.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp,

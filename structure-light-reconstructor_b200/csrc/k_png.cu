@@ -17,7 +17,9 @@
 //   k_cloud_image  dense cloud [H][W] -> the storage of the reference's PointCloudImage (Duke/pointcloudimage.cpp:3-13):
 //                sums float [scan_h][scan_w][3] + counts u8 [scan_h][scan_w], with MFReconstruct's addPoint(i, j, p)
 //                addressing — cell (i_w = image row, j_h = image column), dropped when i_w >= scan_w or j_h >= scan_h
-//                (Duke/mfreconstruct.cpp:326, Duke/pointcloudimage.cpp:86-97) — i.e. a clipped transpose.
+//                (Duke/mfreconstruct.cpp:326, Duke/pointcloudimage.cpp:86-97) — i.e. a clipped transpose; with a colour
+//                plane (Reconstruct::triangulation_ge's haveColor, Duke/reconstruct.cpp:596-603) the grey value of every
+//                cell goes along.
 #include "slr_device.cuh"
 
 namespace {
@@ -79,24 +81,26 @@ k_png_up(const uint8_t *__restrict__ filt, uint8_t *__restrict__ dst, int W, int
 }
 
 __global__ void __launch_bounds__(256)
-k_cloud_image(const float *__restrict__ xyz, const uint8_t *__restrict__ valid, int W, int H, int scan_w, int scan_h,
-              float *__restrict__ sum, uint8_t *__restrict__ cnt)
+k_cloud_image(const float *__restrict__ xyz, const uint8_t *__restrict__ valid, const uint8_t *__restrict__ gray, int W,
+              int H, int scan_w, int scan_h, float *__restrict__ sum, uint8_t *__restrict__ cnt, uint8_t *__restrict__ cell_gray)
 {
     // one 32 x 32 tile of the PointCloudImage per CTA, read transposed through shared memory
     __shared__ float t[3][32][33];
-    __shared__ uint8_t tv[32][33];
+    __shared__ uint8_t tv[32][33], tg[32][33];
     const int iw0 = blockIdx.x * 32, jh0 = blockIdx.y * 32;   // cell (i_w, j_h) = image (row i_w, column j_h)
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 warps
     for (int r = ty; r < 32; r += 8) {                        // image row iw0 + r, columns jh0 .. jh0 + 31: coalesced
         const int i = iw0 + r, j = jh0 + tx;
         const bool in = i < H && j < W && i < scan_w && j < scan_h;
-        uint8_t v = 0;
+        uint8_t v = 0, g = 0;
         float px = 0.f, py = 0.f, pz = 0.f;
         if (in) {
             const size_t p = (size_t)i * W + j;
             v = valid[p];
             if (v) px = xyz[p * 3], py = xyz[p * 3 + 1], pz = xyz[p * 3 + 2];
+            if (v && gray) g = gray[p];
         }
+        tg[r][tx] = g;
         t[0][r][tx] = px;
         t[1][r][tx] = py;
         t[2][r][tx] = pz;
@@ -111,6 +115,7 @@ k_cloud_image(const float *__restrict__ xyz, const uint8_t *__restrict__ valid, 
             sum[o * 3 + 1] = t[1][tx][r];
             sum[o * 3 + 2] = t[2][tx][r];
             cnt[o] = tv[tx][r];
+            if (cell_gray) cell_gray[o] = tg[tx][r];
         }
     }
 }
@@ -130,11 +135,11 @@ slr_status slr_launch_png_unfilter(slr_engine *e, cudaStream_t stream, const uin
     return SLR_OK;
 }
 
-slr_status slr_launch_cloud_image(slr_engine *e, const float *d_xyz, const uint8_t *d_valid, int scan_w, int scan_h,
-                                  float *d_sum, uint8_t *d_cnt)
+slr_status slr_launch_cloud_image(slr_engine *e, const float *d_xyz, const uint8_t *d_valid, const uint8_t *d_gray, int scan_w,
+                                  int scan_h, float *d_sum, uint8_t *d_cnt, uint8_t *d_cell_gray)
 {
     dim3 grid((scan_w + 31) / 32, (scan_h + 31) / 32);
-    k_cloud_image<<<grid, 256, 0, e->stream>>>(d_xyz, d_valid, e->W, e->H, scan_w, scan_h, d_sum, d_cnt);
+    k_cloud_image<<<grid, 256, 0, e->stream>>>(d_xyz, d_valid, d_gray, e->W, e->H, scan_w, scan_h, d_sum, d_cnt, d_cell_gray);
     SLR_CHECK_LAUNCH(e);
     return SLR_OK;
 }

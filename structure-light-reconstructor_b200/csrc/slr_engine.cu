@@ -78,6 +78,7 @@ static void free_engine(slr_engine *e)
     cudaFree(e->d_ingest);
     cudaFree(e->d_cloud_sum);
     cudaFree(e->d_cloud_cnt);
+    cudaFree(e->d_cloud_gray);
     if (e->ev_ingest) cudaEventDestroy(e->ev_ingest);
     if (e->h_counter) cudaFreeHost(e->h_counter);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -953,12 +954,82 @@ extern "C" slr_status slr_ingest_image(slr_engine *e, int index, const uint8_t *
     return slr_launch_png_unfilter(e, e->copy_in, f, plane, has_up_rows != 0);
 }
 
+extern "C" slr_status slr_ingest_abort(slr_engine *e)
+{
+    SLR_ENTER(e);
+    e->ingest_images = 0;
+    SLR_CHECK_CUDA(cudaStreamSynchronize(e->copy_in));   // the caller's pinned images are no longer read
+    return SLR_OK;
+}
+
 extern "C" slr_status slr_png_unfilter(slr_engine *e, const uint8_t *d_scanlines, uint8_t *d_pixels, int has_up_rows)
 {
     SLR_ENTER(e);
     SLR_REQUIRE(d_scanlines && d_pixels && e->W % 4 == 0 && ((uintptr_t)d_pixels & 3) == 0,
                 "slr_png_unfilter: bad argument (width and output must be multiples of 4)");
     return slr_launch_png_unfilter(e, e->stream, d_scanlines, d_pixels, has_up_rows != 0);
+}
+
+// the tail shared by slr_run_mf_ingested / slr_run_ge_ingested: the cloud of d_stage_xyz[0] / d_stage_valid[0] (and the
+// colour plane) back to the host in the requested forms; synchronises, error or not (the caller's buffers must be quiet)
+static slr_status ingested_outputs(slr_engine *e, slr_status st, bool color, int scan_w, int scan_h, float *h_sum, uint8_t *h_cnt,
+                                   uint8_t *h_cell_gray, float *h_xyz, uint8_t *h_valid, uint8_t *h_color,
+                                   unsigned long long *h_n_points)
+{
+    const size_t P = (size_t)e->W * e->H;
+    cudaStream_t cs = e->stream;
+    while (st == SLR_OK) {
+        if (h_sum && h_cnt) {
+            const size_t cells = (size_t)scan_w * scan_h;
+            if (e->cloud_cells < cells) {
+                cudaFree(e->d_cloud_sum);
+                cudaFree(e->d_cloud_cnt);
+                cudaFree(e->d_cloud_gray);
+                e->d_cloud_sum = nullptr;
+                e->d_cloud_cnt = e->d_cloud_gray = nullptr;
+                e->cloud_cells = 0;
+                if (cudaMalloc(&e->d_cloud_sum, cells * 3 * sizeof(float)) != cudaSuccess || cudaMalloc(&e->d_cloud_cnt, cells) != cudaSuccess ||
+                    cudaMalloc(&e->d_cloud_gray, cells) != cudaSuccess) {
+                    slr_set_error("slr_run_*_ingested: out of device memory");
+                    st = SLR_ERR_NOMEM;
+                    break;
+                }
+                e->cloud_cells = cells;
+            }
+            const bool cg = color && h_cell_gray;
+            st = slr_launch_cloud_image(e, e->d_stage_xyz[0], e->d_stage_valid[0], cg ? e->d_stage_color[0] : nullptr, scan_w, scan_h,
+                                        e->d_cloud_sum, e->d_cloud_cnt, cg ? e->d_cloud_gray : nullptr);
+            if (st != SLR_OK) break;
+            cudaMemcpyAsync(h_sum, e->d_cloud_sum, cells * 3 * sizeof(float), cudaMemcpyDeviceToHost, cs);
+            cudaMemcpyAsync(h_cnt, e->d_cloud_cnt, cells, cudaMemcpyDeviceToHost, cs);
+            if (cg) cudaMemcpyAsync(h_cell_gray, e->d_cloud_gray, cells, cudaMemcpyDeviceToHost, cs);
+        }
+        if (h_xyz && h_valid) {
+            cudaMemcpyAsync(h_xyz, e->d_stage_xyz[0], P * 3 * sizeof(float), cudaMemcpyDeviceToHost, cs);
+            cudaMemcpyAsync(h_valid, e->d_stage_valid[0], P, cudaMemcpyDeviceToHost, cs);
+            if (color && h_color) cudaMemcpyAsync(h_color, e->d_stage_color[0], P, cudaMemcpyDeviceToHost, cs);
+        }
+        cudaMemcpyAsync(e->h_counter, e->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, cs);
+        break;
+    }
+    const cudaError_t ce = cudaStreamSynchronize(cs);
+    cudaStreamSynchronize(e->copy_in);
+    e->ingest_images = 0;
+    if (st != SLR_OK) return st;
+    SLR_CHECK_CUDA(ce);
+    if (h_n_points) *h_n_points = *e->h_counter;
+    return SLR_OK;
+}
+
+// ingested images are complete on the device once copy_in's work so far is: make the engine's stream wait for it
+static slr_status ingested_ready(slr_engine *e)
+{
+    if (cudaEventRecord(e->ev_ingest, e->copy_in) != cudaSuccess || cudaStreamWaitEvent(e->stream, e->ev_ingest, 0) != cudaSuccess ||
+        cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream) != cudaSuccess) {
+        slr_set_error("slr_run_*_ingested: stream ordering failed");
+        return SLR_ERR_CUDA;
+    }
+    return SLR_OK;
 }
 
 extern "C" slr_status slr_run_mf_ingested(slr_engine *e, int F, int S, int black_thr, int mode, int scan_w, int scan_h,
@@ -973,58 +1044,43 @@ extern "C" slr_status slr_run_mf_ingested(slr_engine *e, int F, int S, int black
         slr_set_error("slr_run_mf_ingested: call slr_set_calib first");
         return SLR_ERR_STATE;
     }
-    const size_t P = (size_t)e->W * e->H;
-    cudaStream_t cs = e->stream;
-    slr_status st = SLR_OK;
-    do {
-        if (cudaEventRecord(e->ev_ingest, e->copy_in) != cudaSuccess || cudaStreamWaitEvent(cs, e->ev_ingest, 0) != cudaSuccess) {
-            slr_set_error("slr_run_mf_ingested: stream ordering failed");
-            st = SLR_ERR_CUDA;
-            break;
-        }
-        if (cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), cs) != cudaSuccess) { st = SLR_ERR_CUDA; break; }
+    slr_status st = ingested_ready(e);
+    if (st == SLR_OK) {
         if (e->host_input_raw)
             st = slr_launch_fused_mf_raw(e, e->d_stage_in[0], 1, F, S, black_thr, mode, e->d_stage_xyz[0], e->d_stage_valid[0],
                                          nullptr, e->d_counter);
         else
             st = slr_launch_fused_mf(e, e->d_stage_in[0], 1, F, S, black_thr, mode, e->d_stage_xyz[0], e->d_stage_valid[0],
                                      nullptr, e->d_counter);
-        if (st != SLR_OK) break;
-        if (h_sum && h_cnt) {
-            const size_t cells = (size_t)scan_w * scan_h;
-            if (e->cloud_cells < cells) {
-                cudaFree(e->d_cloud_sum);
-                cudaFree(e->d_cloud_cnt);
-                e->d_cloud_sum = nullptr;
-                e->d_cloud_cnt = nullptr;
-                e->cloud_cells = 0;
-                if (cudaMalloc(&e->d_cloud_sum, cells * 3 * sizeof(float)) != cudaSuccess ||
-                    cudaMalloc(&e->d_cloud_cnt, cells) != cudaSuccess) {
-                    slr_set_error("slr_run_mf_ingested: out of device memory");
-                    st = SLR_ERR_NOMEM;
-                    break;
-                }
-                e->cloud_cells = cells;
-            }
-            st = slr_launch_cloud_image(e, e->d_stage_xyz[0], e->d_stage_valid[0], scan_w, scan_h, e->d_cloud_sum, e->d_cloud_cnt);
-            if (st != SLR_OK) break;
-            cudaMemcpyAsync(h_sum, e->d_cloud_sum, cells * 3 * sizeof(float), cudaMemcpyDeviceToHost, cs);
-            cudaMemcpyAsync(h_cnt, e->d_cloud_cnt, cells, cudaMemcpyDeviceToHost, cs);
-        }
-        if (h_xyz && h_valid) {
-            cudaMemcpyAsync(h_xyz, e->d_stage_xyz[0], P * 3 * sizeof(float), cudaMemcpyDeviceToHost, cs);
-            cudaMemcpyAsync(h_valid, e->d_stage_valid[0], P, cudaMemcpyDeviceToHost, cs);
-        }
-        cudaMemcpyAsync(e->h_counter, e->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, cs);
-    } while (false);
-    // the caller's buffers must be quiet when this returns, error or not
-    const cudaError_t ce = cudaStreamSynchronize(cs);
-    cudaStreamSynchronize(e->copy_in);
-    e->ingest_images = 0;
-    if (st != SLR_OK) return st;
-    SLR_CHECK_CUDA(ce);
-    if (h_n_points) *h_n_points = *e->h_counter;
-    return SLR_OK;
+    }
+    return ingested_outputs(e, st, false, scan_w, scan_h, h_sum, h_cnt, nullptr, h_xyz, h_valid, nullptr, h_n_points);
+}
+
+extern "C" slr_status slr_run_ge_ingested(slr_engine *e, int nbits_col, int black_thr, int white_thr, int code_w, int have_color,
+                                          int scan_w, int scan_h, float *h_sum, uint8_t *h_cnt, uint8_t *h_cell_gray,
+                                          float *h_xyz, uint8_t *h_valid, uint8_t *h_color, unsigned long long *h_n_points)
+{
+    SLR_ENTER(e);
+    SLR_REQUIRE(nbits_col >= 1 && nbits_col <= 16 && e->ingest_images == 2 * (2 + 2 * nbits_col),
+                "slr_run_ge_ingested: %d images ingested, the stack needs %d", e->ingest_images, 2 * (2 + 2 * nbits_col));
+    SLR_REQUIRE((h_sum && h_cnt && scan_w > 0 && scan_h > 0) || (h_xyz && h_valid), "slr_run_ge_ingested: no output buffer");
+    if (!e->calib_set) {
+        slr_set_error("slr_run_ge_ingested: call slr_set_calib first");
+        return SLR_ERR_STATE;
+    }
+    const size_t P = (size_t)e->W * e->H, in_bytes = (size_t)e->ingest_images * P;
+    slr_status st = ensure_stage(e, in_bytes, have_color != 0);   // colour buffers, the rectified copy
+    if (st == SLR_OK) st = ingested_ready(e);
+    uint8_t *d_in = e->d_stage_in[0];
+    if (st == SLR_OK && e->host_input_raw) {   // as Reconstruct::loadCamImgs: rectify, then (optionally) stretch
+        st = slr_launch_rectify(e, d_in, 1, e->ingest_images / 2, e->d_stage_rect[0]);
+        d_in = e->d_stage_rect[0];
+    }
+    if (st == SLR_OK && e->auto_contrast) st = slr_launch_auto_contrast(e, d_in, e->ingest_images);
+    if (st == SLR_OK)
+        st = slr_launch_fused_ge(e, d_in, 1, nbits_col, black_thr, white_thr, code_w, have_color, e->d_stage_xyz[0],
+                                 e->d_stage_valid[0], nullptr, have_color ? e->d_stage_color[0] : nullptr, e->d_counter);
+    return ingested_outputs(e, st, have_color != 0, scan_w, scan_h, h_sum, h_cnt, h_cell_gray, h_xyz, h_valid, h_color, h_n_points);
 }
 
 extern "C" slr_status slr_run_ge_host(slr_engine *e, const uint8_t *h_stack, int batch, int nbits_col,

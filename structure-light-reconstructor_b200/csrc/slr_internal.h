@@ -107,7 +107,7 @@ struct slr_engine {
     int ingest_images = 0;
     cudaEvent_t ev_ingest = nullptr;
     float *d_cloud_sum = nullptr;
-    uint8_t *d_cloud_cnt = nullptr;
+    uint8_t *d_cloud_cnt = nullptr, *d_cloud_gray = nullptr;
     size_t cloud_cells = 0;
 
     void *d_merge = nullptr;         // slr_merge_scans: tile offsets + per-scan transforms
@@ -180,8 +180,8 @@ slr_status slr_launch_merge(slr_engine *e, const float *d_xyz, const uint8_t *d_
                             const uint8_t *h_has_rigid, float *d_points, long long *d_source, unsigned long long *d_count);
 slr_status slr_launch_png_unfilter(slr_engine *e, cudaStream_t stream, const uint8_t *d_filtered, uint8_t *d_plane,
                                    bool has_up_rows);
-slr_status slr_launch_cloud_image(slr_engine *e, const float *d_xyz, const uint8_t *d_valid, int scan_w, int scan_h,
-                                  float *d_sum, uint8_t *d_cnt);
+slr_status slr_launch_cloud_image(slr_engine *e, const float *d_xyz, const uint8_t *d_valid, const uint8_t *d_gray, int scan_w,
+                                  int scan_h, float *d_sum, uint8_t *d_cnt, uint8_t *d_cell_gray);
 slr_status slr_launch_auto_contrast(slr_engine *e, uint8_t *d_images, int n_images);
 // padded route for e->W % 16 != 0 (slr_engine.cu); kind: 0 = image stacks (MF), 1 = image stacks (GE),
 // 2 = phase + mask rows, 3 = code + mask rows

@@ -105,7 +105,7 @@ bool MFReconstruct::runReconstruction()
             std::string err;
             if (!duke::ingest_scan(eng, scanFolder, imgPrefix, imgSuffix, numberOfImgs, W, H, &err)) {
                 fprintf(stderr, "%s\n", err.c_str());
-                slr_run_mf_ingested(eng, 3, 4, blackThreshold, mode, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr);   // drains the copies
+                slr_ingest_abort(eng);
                 break;
             }
             lap("image files -> inflate -> GPU");

@@ -12,9 +12,23 @@ PointCloudImage::PointCloudImage(int imageW, int imageH, bool colorFlag)
     num_ = own_num_.data();
     if (colorFlag) color_.assign((size_t)imageW * imageH * 3, 0);
 }
-PointCloudImage::PointCloudImage(int imageW, int imageH, float *sums, uint8_t *counts, void (*release)(float *, uint8_t *))
-    : w(imageW), h(imageH), has_color_(false), points_(sums), num_(counts), release_(release)
+PointCloudImage::PointCloudImage(int imageW, int imageH, float *sums, uint8_t *counts, void (*release)(float *, uint8_t *),
+                                 const uint8_t *cell_gray)
+    : w(imageW), h(imageH), has_color_(cell_gray != nullptr), points_(sums), num_(counts), release_(release)
 {
+    if (!cell_gray) return;
+    const size_t cells = (size_t)w * h;
+    color_.resize(cells * 3);
+    auto band = [&](size_t c0, size_t c1) {
+        for (size_t c = c0; c < c1; c++) color_[3 * c] = color_[3 * c + 1] = color_[3 * c + 2] = cell_gray[c];
+    };
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt == 0 ? 1 : nt > 8 ? 8 : nt;
+    if (cells < 65536) nt = 1;
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nt; t++) pool.emplace_back(band, cells * t / nt, cells * (t + 1) / nt);
+    band(0, cells / nt);
+    for (auto &t : pool) t.join();
 }
 PointCloudImage::~PointCloudImage()
 {

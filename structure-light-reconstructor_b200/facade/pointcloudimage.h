@@ -14,7 +14,10 @@ public:
     // The cloud as the GPU pipeline delivers it (slr_run_mf_ingested): sums = float [imageH][imageW][3], counts = uint8
     // [imageH][imageW] already in this class's storage layout, in (pinned) memory the object keeps until it is
     // destroyed, when release(sums, counts) hands it back.  No host pass over the 17 MB of a 1280x1024 cloud.
-    PointCloudImage(int imageW, int imageH, float *sums, uint8_t *counts, void (*release)(float *, uint8_t *));
+    // cell_gray (may be NULL: no colour) = uint8 [imageH][imageW], the grey value every cell with a point received as
+    // its (g, g, g) colour (Reconstruct::triangulation_ge with haveColor, Duke/reconstruct.cpp:596-603); copied.
+    PointCloudImage(int imageW, int imageH, float *sums, uint8_t *counts, void (*release)(float *, uint8_t *),
+                    const uint8_t *cell_gray = nullptr);
     ~PointCloudImage();
     PointCloudImage(const PointCloudImage &) = delete;
     PointCloudImage &operator=(const PointCloudImage &) = delete;

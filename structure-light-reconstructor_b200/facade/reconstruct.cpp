@@ -4,6 +4,7 @@
 
 #include <vector>
 
+#include "ingest.h"
 #include "reconstruct_common.h"
 
 Reconstruct::Reconstruct(bool useEpi) : points3DProjView(nullptr), EPI(useEpi), imgSuffix(".png")
@@ -121,13 +122,38 @@ bool Reconstruct::runReconstruction_GE()
         if (slr_set_host_input_raw(eng, 1) != SLR_OK) break;
         // Utilities::autoContrast on every rectified image (Duke/reconstruct.cpp:182-183), on the GPU after K0
         if (slr_set_auto_contrast(eng, autoContrast_ ? 1 : 0) != SLR_OK) break;
+        unsigned long long n = 0;
+        if (W % 4 == 0 && !getenv("DUKE_HOST_DECODE")) {
+            // files -> GPU (facade/ingest.h): inflate on all host threads, everything after it on the GPU, the cloud back
+            // in PointCloudImage's own storage layout
+            std::string err;
+            if (!duke::ingest_scan(eng, scanFolder, imgPrefix, imgSuffix, nimg, W, H, &err)) {
+                fprintf(stderr, "%s\n", err.c_str());
+                slr_ingest_abort(eng);
+                break;
+            }
+            const size_t cells = (size_t)scan_w * scan_h;
+            float *sums = nullptr;
+            uint8_t *counts = nullptr;
+            if (haveColor && !(h_color = duke::pinned_scratch(3, cells))) break;
+            if (!duke::cloud_storage_acquire(cells, &sums, &counts)) break;
+            if (slr_run_ge_ingested(eng, nbits, blackThreshold, whiteThreshold, scan_w, haveColor ? 1 : 0, scan_w, scan_h, sums, counts,
+                                    (uint8_t *)h_color, nullptr, nullptr, nullptr, &n) != SLR_OK) {
+                duke::cloud_storage_release(sums, counts);
+                break;
+            }
+            delete points3DProjView;
+            points3DProjView = new PointCloudImage(scan_w, scan_h, sums, counts, duke::cloud_storage_release,
+                                                   haveColor ? (const uint8_t *)h_color : nullptr);
+            ok = true;
+            break;
+        }
         if (!(h_stack = duke::pinned_scratch(0, 2 * (size_t)nimg * P))) break;
         if (!(h_xyz = duke::pinned_scratch(1, P * 3 * sizeof(float)))) break;
         if (!(h_valid = duke::pinned_scratch(2, P))) break;
         if (haveColor && !(h_color = duke::pinned_scratch(3, P))) break;
         const bool loaded = duke::load_stacks(scanFolder, imgPrefix, imgSuffix, 2, nimg, W, H, (uint8_t *)h_stack);
         if (!loaded) break;
-        unsigned long long n = 0;
         if (slr_run_ge_host(eng, (const uint8_t *)h_stack, 1, nbits, blackThreshold, whiteThreshold, scan_w, haveColor ? 1 : 0,
                             (float *)h_xyz, (uint8_t *)h_valid, nullptr, (uint8_t *)h_color, &n) != SLR_OK)
             break;

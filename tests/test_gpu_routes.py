@@ -399,3 +399,44 @@ def test_merge_scans_equals_the_per_scan_rigid_epilogue_and_the_oracle(cuda_engi
     p0, s0 = eng.merge_scans(xyz, valid)
     assert (s0.cpu().numpy() == exp_src).all()
     assert (bits(p0.cpu().numpy()) == bits(xyz.cpu().numpy().reshape(-1, 3)[exp_src])).all()
+
+
+def test_raw_and_merge_edge_cases(cuda_engine_factory, oracle):
+    """slr_run_mf_raw on a width the TMA rows cannot take (100: K0's per-pixel kernel, then the padded route), maps that
+    send whole rows outside the image, a merge without a single valid point, and argument errors."""
+    import torch
+    W, H = 100, 20
+    eng = cuda_engine_factory(W, H, 2)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    with pytest.raises(slr_b200.SlrError):                 # no maps yet
+        eng.run_mf_raw(_t(np.zeros((1, 2, 14, H, W), np.uint8)))
+    m1, m2 = _rect_maps(W, H, 0.4)
+    m1[1, 5:8, :, 1] = -30                                 # right camera, rows 5..7: every tap above the image
+    eng.set_rectify_maps(m1, m2)
+    raw = np.stack([synth.synth_mf(W, H, seed=80 + s, noise_dn=1.0) for s in range(2)])
+    xyz, valid, k, n = eng.run_mf_raw(_t(raw))
+    tot = 0
+    for b in range(2):
+        rect = np.stack([[oracle.remap_linear(raw[b, cam, i], m1[cam], m2[cam]) for i in range(14)] for cam in range(2)])
+        assert (rect[1, :, 5:8] == 0).all()
+        xyz_o, valid_o, k_o, n_o = oracle.run_mf(rect, cams, Q)
+        _assert_cloud_equal(xyz[b], valid[b], k[b], n_o, xyz_o, valid_o, k_o, n_o, f"ragged raw scan {b}")
+        assert (valid_o[5:8] == 0).all()
+        tot += n_o
+    assert int(n.item()) == tot and tot > 100
+    # merge: nothing valid -> an empty list; everything valid -> identity order
+    none = torch.zeros((2, H, W), dtype=torch.uint8, device="cuda")
+    pts, src = eng.merge_scans(xyz, none)
+    assert pts.shape[0] == 0 and src.shape[0] == 0
+    allv = torch.ones((2, H, W), dtype=torch.uint8, device="cuda")
+    dense = torch.arange(2 * H * W * 3, dtype=torch.float32, device="cuda").reshape(2, H, W, 3)
+    pts, src = eng.merge_scans(dense, allv)
+    assert (src.cpu().numpy() == np.arange(2 * H * W)).all() and torch.equal(pts, dense.reshape(-1, 3))
+    # ingest: odd image counts and a stack of the wrong size are refused
+    with pytest.raises(slr_b200.SlrError):
+        eng.run_mf_ingested([np.zeros((H, W), np.uint8)] * 3, [False] * 3, h_xyz=np.empty((H, W, 3), np.float32),
+                            h_valid=np.empty((H, W), np.uint8))
+    with pytest.raises(slr_b200.SlrError):
+        eng.run_mf_ingested([np.zeros((H, W), np.uint8)] * 4, [False] * 4, h_xyz=np.empty((H, W, 3), np.float32),
+                            h_valid=np.empty((H, W), np.uint8))
