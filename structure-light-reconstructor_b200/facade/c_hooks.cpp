@@ -4,6 +4,7 @@
 
 #include "imageio.h"
 #include "inflate.h"
+#include "ingest.h"
 #include "meshcreator.h"
 #include "rectify.h"
 #include "stereorect.h"
@@ -53,6 +54,12 @@ int duke_read_gray_image(const char *path, int *w, int *h, uint8_t *pix, int cap
     if ((int)img.pix.size() > cap) return -2;
     memcpy(pix, img.pix.data(), img.pix.size());
     return 0;
+}
+
+// the host half of the PNG ingest path for one image: returns the route (ingest.h) and fills out[H * (1 + W)]
+int duke_decode_scan_image(const char *base, const char *suffix, int w, int h, uint8_t *out)
+{
+    return duke::decode_scan_image(base, suffix, w, h, out, nullptr);
 }
 
 // zlib stream -> bytes with the ingest path's own decoder (inflate.cpp); 0 = ok, -1 = rejected

@@ -132,6 +132,14 @@ Route decode_into(const std::string &base, const std::string &suffix, int W, int
 
 }  // namespace
 
+int decode_scan_image(const std::string &base, const std::string &suffix, int W, int H, uint8_t *slot, std::string *err)
+{
+    std::string e;
+    const Route r = decode_into(base, suffix, W, H, slot, &e);
+    if (err) *err = e;
+    return r == ROUTE_FILTERED ? 1 : r == ROUTE_FILTERED_UP ? 2 : r == ROUTE_PIXELS ? 3 : 0;
+}
+
 bool ingest_scan(slr_engine *eng, const std::string folder[2], const std::string prefix[2], const std::string &suffix,
                  int n, int W, int H, std::string *err)
 {

@@ -20,6 +20,11 @@ namespace duke {
 bool ingest_scan(slr_engine *eng, const std::string folder[2], const std::string prefix[2], const std::string &suffix,
                  int n, int W, int H, std::string *err);
 
+// The host half of one image, as ingest_scan's workers run it: <base><suffix> (or <base>.pgm) into `slot` (room for
+// H * (1 + W) bytes).  Returns 0 on failure (*err says why), 1 = PNG scanlines with filter types 0 / 1 only, 2 = PNG
+// scanlines that also have Up rows (both: H x [type][W bytes], to be unfiltered on the GPU), 3 = H x W finished pixels.
+int decode_scan_image(const std::string &base, const std::string &suffix, int W, int H, uint8_t *slot, std::string *err);
+
 // Pinned sums / counts of a PointCloudImage(w, h) from a small process-wide pool, and their way back
 // (PointCloudImage's release hook).  nullptr when pinned memory cannot be had.
 bool cloud_storage_acquire(size_t cells, float **sums, uint8_t **counts);

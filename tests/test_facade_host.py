@@ -287,3 +287,60 @@ def test_pointcloudimage_export_xyz_writes_the_reference_bytes(duke, tmp_path, c
     if ref_lib.available():
         ref_lib.load().export_xyz(pts, cnt, w, h, tmp_path / "r.xyz", export_off, True, col)
         assert open(tmp_path / "r.xyz", "rb").read() == want
+
+
+def test_ingest_host_half_routes_every_encoding(duke, tmp_path):
+    """facade/ingest.cpp's per-image work (no GPU): OpenCV-style Sub-filtered PNGs stay scanlines for the GPU unfilter,
+    files with Up rows are flagged, Average / Paeth rows are unfiltered on the host, PGM / colour PNG arrive as pixels,
+    wrong sizes / damaged / missing files are refused."""
+    from slr_b200 import synth
+    rng = np.random.default_rng(4)
+    W, H = 64, 21
+    img = rng.integers(0, 256, (H, W)).astype(np.uint8)
+    out = np.zeros(H * (W + 1), np.uint8)
+
+    def decode(base, w=W, h=H):
+        out[:] = 0xEE
+        return duke.duke_decode_scan_image(str(tmp_path / base).encode(), b".png", w, h, ptr(out))
+
+    synth.write_png_opencv_style(str(tmp_path / "sub.png"), img)
+    assert decode("sub") == 1
+    rows = out.reshape(H, W + 1)
+    assert (rows[:, 0] == 1).all() and (np.cumsum(rows[:, 1:], axis=1, dtype=np.uint8) == img).all()
+
+    def write_filtered(name, types):
+        a = img.astype(np.int32)
+        raw = b""
+        for y in range(H):
+            t = types[y]
+            left = np.concatenate([[0], a[y, :-1]])
+            up = a[y - 1] if y else np.zeros(W, np.int32)
+            ul = np.concatenate([[0], up[:-1]])
+            pa, pb, pc = np.abs(up - ul), np.abs(left - ul), np.abs(left + up - 2 * ul)
+            pred = [0 * left, left, up, (left + up) >> 1, np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, up, ul))][t]
+            raw += bytes([t]) + ((a[y] - pred) & 255).astype(np.uint8).tobytes()
+        z = zlib.compress(raw, 6)
+
+        def chunk(t, d):
+            return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+        (tmp_path / name).write_bytes(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, 8, 0, 0, 0, 0)) +
+                                      chunk(b"IDAT", z[:7]) + chunk(b"IDAT", z[7:]) + chunk(b"IEND", b""))
+
+    write_filtered("up.png", [y % 3 for y in range(H)])
+    assert decode("up") == 2 and (out.reshape(H, W + 1)[:, 0] == [y % 3 for y in range(H)]).all()
+    write_filtered("paeth.png", [y % 5 for y in range(H)])
+    assert decode("paeth") == 3 and (out[:H * W].reshape(H, W) == img).all()
+    assert duke.duke_write_pgm(str(tmp_path / "only_pgm.pgm").encode(), ptr(img), W, H) == 0
+    assert decode("only_pgm") == 3 and (out[:H * W].reshape(H, W) == img).all()
+    rgb = rng.integers(0, 256, (H, W, 3)).astype(np.uint8)
+    (tmp_path / "rgb.png").write_bytes(_png_with_all_filters(rgb))
+    assert decode("rgb") == 3
+    exp = (rgb[..., 0].astype(int) * 4899 + rgb[..., 1].astype(int) * 9617 + rgb[..., 2].astype(int) * 1868 + 8192) >> 14
+    assert (out[:H * W].reshape(H, W) == exp).all()
+    assert decode("sub", W + 4, H) == 0 and decode("missing") == 0
+    blob = bytearray((tmp_path / "sub.png").read_bytes())
+    blob[60] ^= 0x10
+    (tmp_path / "bad.png").write_bytes(bytes(blob))
+    assert decode("bad") == 0
+    (tmp_path / "cut.png").write_bytes(bytes(blob[:len(blob) // 2]))
+    assert decode("cut") == 0
