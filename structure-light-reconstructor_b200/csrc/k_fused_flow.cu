@@ -10,11 +10,11 @@
 //   row r     decode jobs: image bytes -> phases, right phases filed in the tables, left phases parked
 //             (context r % 4, stage buffer r % 2)
 //   row r-1   decoded, waiting (its last decode jobs may still be running)
-//   row r-2   query jobs: first-k match of 32 left pixels + Q reprojection + stores   (context (r-2) % 4)
+//   row r-2   query jobs: first-k match of 64 left pixels + Q reprojection + stores   (context (r-2) % 4)
 //   row r-3   its tables being cleared by the warp that finished its last query job  (context (r-3) % 4)
 //
 // Work is cut into warp-sized jobs; every warp draws the next job from ONE shared counter whose order lists, per
-// step, the decode jobs of row r and then the query jobs of row r-1, so table-lookup-bound, latency-bound and
+// step, the decode jobs of row r and then the query jobs of row r-2, so table-lookup-bound, latency-bound and
 // fp64-bound instruction streams share the SM at all times.  A job waits only on per-context mbarriers that jobs
 // preceding it in the global order arrive on, which makes the schedule deadlock-free: decode(r) needs the clear after
 // query(r-4) and the stage re-armed after decode(r-2); query(r) needs decode(r).  A waiting warp sleeps in
@@ -24,10 +24,10 @@
 // RAW = true (slr_run_mf_raw): the stack holds the RAW camera images and the stage buffer is not
 // filled by bulk copies but by a third kind of job, listed one step ahead of the row's decode jobs: rectify jobs
 // evaluate stereoRect::doStereoRectify = cv::remap(INTER_LINEAR, CV_16SC2 maps) (Duke/stereorect.cpp:26-34) for 128
-// pixels of one camera's row and all N planes — map entries read once, four aligned 32-bit loads per plane for the
-// 2 x 8-byte tap window of four pixels, OpenCV's fixed-point blend as two DP2A — straight into the stage buffer, so the
-// rectified images never exist in HBM: raw bytes in, XYZ out, one kernel.  Rows are walked image-row-fastest there, so
-// that the two source rows an output row blends are still in L2 for the next output row.
+// pixels of one camera's row and all N planes (slr::rectify_job, slr_rectify.cuh — the code the stand-alone K0 runs too)
+// straight into the stage buffer, so the rectified images never exist in HBM: raw bytes in, XYZ out, one kernel.  Rows
+// are walked image-row-fastest there, so that the two source rows an output row blends are still in L2 for the next
+// output row.
 #include <limits.h>
 #include <stdlib.h>
 
