@@ -440,3 +440,23 @@ def test_raw_and_merge_edge_cases(cuda_engine_factory, oracle):
     with pytest.raises(slr_b200.SlrError):
         eng.run_mf_ingested([np.zeros((H, W), np.uint8)] * 4, [False] * 4, h_xyz=np.empty((H, W, 3), np.float32),
                             h_valid=np.empty((H, W), np.uint8))
+
+
+@pytest.mark.parametrize("black_thr", [-1, 0, 179, 180, 254, 300])
+def test_run_mf_extreme_shadow_thresholds_vs_oracle(cuda_engine_factory, oracle, black_thr):
+    """computeShadows' threshold at its extremes (Duke/mfreconstruct.cpp:199-204): below zero every pixel is decoded
+    (degenerate G1 == G3 && G4 == G2 pixels included: the oracle's 'pixel dropped'), at white - black (180 in the synthetic
+    scene) and above nothing is lit and the cloud is empty."""
+    W, H = 640, 24
+    eng = cuda_engine_factory(W, H, 1)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    stack = synth.synth_mf(W, H, seed=33, integer_disparity=False, noise_dn=0.0)
+    stack[:, 2:, :, 100:140] = 77                      # a flat patch: every frequency degenerate
+    xyz, valid, k, n = eng.run_mf(_t(stack[None]), black_thr=black_thr)
+    xyz_o, valid_o, k_o, n_o = oracle.run_mf(stack, cams, Q, black_thr=black_thr)
+    _assert_cloud_equal(xyz[0], valid[0], k[0], int(n.item()), xyz_o, valid_o, k_o, n_o, f"black_thr {black_thr}")
+    if black_thr >= 180:
+        assert n_o == 0
+    if black_thr < 0:
+        assert n_o > 0 and (valid_o[:, 100:140] == 0).all()
