@@ -460,3 +460,33 @@ def test_run_mf_extreme_shadow_thresholds_vs_oracle(cuda_engine_factory, oracle,
         assert n_o == 0
     if black_thr < 0:
         assert n_o > 0 and (valid_o[:, 100:140] == 0).all()
+
+
+@pytest.mark.parametrize("W,H,mode", [(1536, 40, slr_b200.MODE_STRICT), (1920, 33, slr_b200.MODE_STRICT),
+                                      (2048, 24, slr_b200.MODE_CORRECTED), (1424, 17, slr_b200.MODE_STRICT)])
+def test_widths_between_the_dataflow_and_the_wide_row_kernel_vs_oracle(cuda_engine_factory, oracle, W, H, mode):
+    """Rows too wide for the dataflow kernel's four row contexts (more than 1408 pixels) run k_fused_mf's one 1024-thread
+    CTA per SM: widths around the hand-over, partially filled tasks, both decode modes.  (A two-context dataflow schedule
+    for these widths was built and measured 10 % slower than k_fused_mf at 2048 wide; not kept.)"""
+    B = 3
+    eng = cuda_engine_factory(W, H, B)
+    cams, Q = slr_b200.synthetic_rig(W, H)
+    eng.set_calib(cams, Q)
+    stack = np.stack([synth.synth_mf(W, H, seed=50 + s, integer_disparity=False, noise_dn=1.5) for s in range(B)])
+    l0 = eng.launches()
+    xyz, valid, k, n = eng.run_mf(_t(stack), black_thr=40, mode=mode)
+    assert eng.launches() - l0 == 1
+    tot = 0
+    for b in range(B):
+        xyz_o, valid_o, k_o, n_o = oracle.run_mf(stack[b], cams, Q, mode=mode, nthreads=oracle.max_threads())
+        if mode == slr_b200.MODE_STRICT:
+            _assert_cloud_equal(xyz[b], valid[b], k[b], n_o, xyz_o, valid_o, k_o, n_o, f"{W}-wide scan {b}")
+        else:
+            same = k[b].cpu().numpy() == k_o
+            assert same.mean() > 0.995, same.mean()
+            ok = same & (valid_o != 0)
+            assert np.allclose(xyz[b].cpu().numpy()[ok], xyz_o[ok], rtol=RTOL, atol=1e-5)
+        tot += n_o
+    assert tot > 1000
+    if mode == slr_b200.MODE_STRICT:
+        assert int(n.item()) == tot
