@@ -90,13 +90,19 @@ struct RowInfo {
     unsigned out_px, map_px;
 };
 
-template <int MODE, bool RAW>
+// WCT > 0: the row width (and with it the table size and, in strict mode, the plane count) as compile-time constants —
+// plane loads become [base + immediate], bounds tests fold away.  Instantiated for the reference camera's 1280 pixels.
+template <int MODE, bool RAW, int WCT>
 __global__ void __launch_bounds__(1024, 1)
-k_fused_flow(const FusedParams p, const int n_r, const int n_d, const int n_q, const unsigned js_magic)
+k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int n_q_rt, const unsigned js_magic)
 {
+    // jobs per row: rectify (RAW), decode, query
+    const int n_r = WCT ? (RAW ? 2 * ((WCT + 127) / 128) : 0) : n_r_rt;
+    const int n_d = WCT ? (WCT / 2 + 31) / 32 : n_d_rt;
+    const int n_q = WCT ? (WCT + 32 * FLOW_QPX - 1) / (32 * FLOW_QPX) : n_q_rt;
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool CLAMP = MODE == MODE_PHASE_INPUT;
-    const int W = p.W, N = p.N, T = p.T;
+    const int W = WCT ? WCT : p.W, N = (WCT && MODE == SLR_MODE_STRICT) ? 14 : p.N, T = (WCT == 1280) ? 2048 : p.T;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
 
     // this CTA's contiguous range of rows rg = i * batch + b (scan index b fastest; RAW: rg = b * H + i)
@@ -127,7 +133,7 @@ k_fused_flow(const FusedParams p, const int n_r, const int n_d, const int n_q, c
         FlowTables t;
         unsigned char *base = ctx0 + (unsigned)c * ctx_bytes;
         t.T = T;
-        t.logT = p.logT;
+        t.logT = (WCT == 1280) ? 11 : p.logT;
         t.HB = T;
         t.ent = reinterpret_cast<uint2 *>(base);
         t.head = reinterpret_cast<int *>(t.ent + T);
@@ -419,11 +425,15 @@ slr_status slr_launch_fused_flow(slr_engine *e, int mode, const FusedParams &p_i
     }
     void (*kern)(const FusedParams, int, int, int, unsigned);
     if (raw)
-        kern = (mode == SLR_MODE_STRICT) ? k_fused_flow<SLR_MODE_STRICT, true> : k_fused_flow<SLR_MODE_CORRECTED, true>;
+        kern = (mode == SLR_MODE_STRICT) ? k_fused_flow<SLR_MODE_STRICT, true, 0> : k_fused_flow<SLR_MODE_CORRECTED, true, 0>;
     else
-        kern = (mode == SLR_MODE_STRICT)      ? k_fused_flow<SLR_MODE_STRICT, false>
-               : (mode == SLR_MODE_CORRECTED) ? k_fused_flow<SLR_MODE_CORRECTED, false>
-                                              : k_fused_flow<MODE_PHASE_INPUT, false>;
+        kern = (mode == SLR_MODE_STRICT)      ? k_fused_flow<SLR_MODE_STRICT, false, 0>
+               : (mode == SLR_MODE_CORRECTED) ? k_fused_flow<SLR_MODE_CORRECTED, false, 0>
+                                              : k_fused_flow<MODE_PHASE_INPUT, false, 0>;
+    if (W == 1280 && p.T == 2048 && !getenv("SLR_FLOW_GENERIC_W")) {   // the reference camera's width, specialised
+        if (mode == SLR_MODE_STRICT && p.N == 14) kern = raw ? k_fused_flow<SLR_MODE_STRICT, true, 1280> : k_fused_flow<SLR_MODE_STRICT, false, 1280>;
+        if (mode == SLR_MODE_CORRECTED) kern = raw ? k_fused_flow<SLR_MODE_CORRECTED, true, 1280> : k_fused_flow<SLR_MODE_CORRECTED, false, 1280>;
+    }
     SLR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = (long long)e->num_sms * ctas;
     if (grid > rows) grid = rows;
