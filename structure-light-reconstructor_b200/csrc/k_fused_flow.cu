@@ -106,8 +106,9 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
 
     // this CTA's contiguous range of rows rg = i * batch + b (scan index b fastest; RAW: rg = b * H + i)
+    // (batch * H < 2^31, checked by the launcher: row indices are 32-bit, and so are the divisions that split them)
     const long long rows = (long long)p.batch * p.H;
-    const long long r_begin = rows * blockIdx.x / gridDim.x, r_end = rows * (blockIdx.x + 1) / gridDim.x;
+    const unsigned r_begin = (unsigned)(rows * blockIdx.x / gridDim.x), r_end = (unsigned)(rows * (blockIdx.x + 1) / gridDim.x);
     const int R = (int)(r_end - r_begin);
     if (R <= 0) return;
 
@@ -171,8 +172,8 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
 
     // TMA bulk copies of row r (CTA-local index) into stage r % FLOW_STAGES, issued by one whole warp
     auto issue_row = [&](int r) {
-        const long long rg = r_begin + r;
-        const int i = (int)(rg / p.batch), b = (int)(rg - (long long)i * p.batch);
+        const unsigned rg = r_begin + (unsigned)r;
+        const int i = (int)(rg / (unsigned)p.batch), b = (int)(rg - (unsigned)i * (unsigned)p.batch);
         uint64_t *bar = &bar_stage[r % FLOW_STAGES];
         unsigned char *stage = stage0 + (size_t)(r % FLOW_STAGES) * stage_bytes;
         if (lane == 0) {
@@ -225,8 +226,8 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
             // the stage buffer is free once every decode job of row r - 2 has read its bytes
             if (r >= FLOW_STAGES) slr::mbar_wait(&bar_free[r % FLOW_STAGES], (uint32_t)((r / FLOW_STAGES - 1) & 1));
             FLOW_TRACE_READY();
-            const long long rg = r_begin + r;
-            const int b = (int)(rg / p.H), i = (int)(rg - (long long)b * p.H);
+            const unsigned rg = r_begin + (unsigned)r;
+            const int b = (int)(rg / (unsigned)p.H), i = (int)(rg - (unsigned)b * (unsigned)p.H);
             const int per_cam = n_r >> 1, cam = s >= per_cam ? 1 : 0;
             const int x = ((s - cam * per_cam) * 32 + lane) * 4;
             if (s == 0 && lane == 0) {
