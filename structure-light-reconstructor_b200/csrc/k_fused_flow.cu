@@ -70,11 +70,15 @@ __device__ long long g_flow_trace[TRACE_JOBS * 4];   // {type | row << 8 | warp 
 #define FLOW_TRACE_END(type, row) do { } while (0)
 #endif
 
+// counter += 1 with acquire-release ordering, returns the old value.  (atom.inc, not atom.add: ptxas wraps an add of a
+// warp-uniform operand into its warp-aggregation sequence — vote, popc, lane masks — which costs more than the atomic
+// when a single lane executes it.)
 __device__ __forceinline__ int add_acq_rel_s32(int *p, int v)
 {
-    int old;
-    asm volatile("atom.acq_rel.cta.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(slr::smem_u32(p)), "r"(v) : "memory");
-    return old;
+    (void)v;   // always 1
+    unsigned old;
+    asm volatile("atom.acq_rel.cta.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(old) : "r"(slr::smem_u32(p)) : "memory");
+    return (int)old;
 }
 // one arrival (release) on an mbarrier that counts jobs
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -210,7 +214,8 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
     // its decode jobs and practically never wait.
     for (;;) {
         int g = 0;
-        if (lane == 0) g = atomicAdd(job_ctr, 1);
+        // (atom.inc in plain PTX: atomicAdd / atom.add under `lane == 0` becomes a 14-instruction warp-aggregation sequence)
+        if (lane == 0) asm volatile("atom.relaxed.cta.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(g) : "r"(slr::smem_u32(job_ctr)) : "memory");
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= total_jobs) break;
         FLOW_TRACE_DRAW();
