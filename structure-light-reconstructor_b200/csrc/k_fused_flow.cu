@@ -70,14 +70,16 @@ __device__ long long g_flow_trace[TRACE_JOBS * 4];   // {type | row << 8 | warp 
 #define FLOW_TRACE_END(type, row) do { } while (0)
 #endif
 
-// counter += 1 with acquire-release ordering, returns the old value.  (atom.inc, not atom.add: ptxas wraps an add of a
+// counter += 1, returns the old value: elects the job that finishes a row's stage reads / queries last.  The ORDERING
+// between the jobs' shared-memory accesses and what the elected job does next (bulk copies into the stage, the table
+// clear) comes from an mbarrier every job arrives on (release) and the elected job waits on (acquire) — an acq_rel atomic
+// costs a MEMBAR.ALL.CTA that also waits for the job's global stores.  (atom.inc, not atom.add: ptxas wraps an add of a
 // warp-uniform operand into its warp-aggregation sequence — vote, popc, lane masks — which costs more than the atomic
 // when a single lane executes it.)
-__device__ __forceinline__ int add_acq_rel_s32(int *p, int v)
+__device__ __forceinline__ int count_job(int *p)
 {
-    (void)v;   // always 1
     unsigned old;
-    asm volatile("atom.acq_rel.cta.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(old) : "r"(slr::smem_u32(p)) : "memory");
+    asm volatile("atom.relaxed.cta.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(old) : "r"(slr::smem_u32(p)) : "memory");
     return (int)old;
 }
 // one arrival (release) on an mbarrier that counts jobs
@@ -120,7 +122,8 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
     uint64_t *bar_stage = reinterpret_cast<uint64_t *>(smem);              // [FLOW_STAGES] a row's bulk copies have landed
     uint64_t *bar_dec = bar_stage + FLOW_STAGES;                           // [FLOW_CTX] phase u: row 4u+c is decoded (n_d arrivals)
     uint64_t *bar_clr = bar_dec + FLOW_CTX;                                // [FLOW_CTX] phase u: tables cleared after row 4u+c
-    uint64_t *bar_free = reinterpret_cast<uint64_t *>(smem + 192);         // [FLOW_STAGES] RAW: a row's decode jobs have read the stage
+    uint64_t *bar_free = reinterpret_cast<uint64_t *>(smem + 192);         // [FLOW_STAGES] a row's decode jobs have read the stage
+    uint64_t *bar_qry = bar_free + FLOW_STAGES;                            // [FLOW_CTX] a row's query jobs are done with its tables
     int *job_ctr = reinterpret_cast<int *>(bar_clr + FLOW_CTX);
     int *done_q = job_ctr + 1;                                             // [FLOW_CTX] query jobs completed
     int *done_l = done_q + FLOW_CTX;                                       // [FLOW_CTX] decode jobs done reading the stage
@@ -168,6 +171,7 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
     if (tid == 0) {
         for (int s = 0; s < FLOW_STAGES; s++) slr::mbar_init(&bar_stage[s], RAW ? (uint32_t)n_r : 1u);
         for (int s = 0; s < FLOW_STAGES; s++) slr::mbar_init(&bar_free[s], (uint32_t)n_d);
+        for (int c = 0; c < FLOW_CTX; c++) slr::mbar_init(&bar_qry[c], (uint32_t)n_q);
         for (int c = 0; c < FLOW_CTX; c++) slr::mbar_init(&bar_dec[c], (uint32_t)n_d), slr::mbar_init(&bar_clr[c], 1);
         slr::mbar_fence_init();
     }
@@ -271,17 +275,19 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
                 float ph[4];
                 bool ok[4];
                 load_phases<MODE, 4>(stage, W, N, x0, right, p, s_ptab, s_btab, ph, ok, cam_pad);
-                // this job has read its bytes of the stage buffer (the release orders the loads before the count).  The
-                // warp that counts the last reader streams row r + 2 into the buffer: a third of a decode job earlier
-                // than its completion, which is the slack the bulk copies need to land before row r + 2 is drawn.
+                // this job has read its bytes of the stage buffer (arrival = release of the loads).  The warp that counts
+                // the last reader streams row r + 2 into the buffer: a third of a decode job earlier than its completion,
+                // which is the slack the bulk copies need to land before row r + 2 is drawn.
                 __syncwarp();
-                if (RAW) {
-                    if (lane == 0) mbar_arrive(&bar_free[r % FLOW_STAGES]);
-                } else {
+                if (lane == 0) mbar_arrive(&bar_free[r % FLOW_STAGES]);
+                if (!RAW) {
                     int last_reader = 0;
-                    if (lane == 0) last_reader = add_acq_rel_s32(&done_l[c], 1) + 1 == (u + 1) * n_d;
+                    if (lane == 0) last_reader = count_job(&done_l[c]) + 1 == (u + 1) * n_d;
                     last_reader = __shfl_sync(0xffffffffu, last_reader, 0);
-                    if (last_reader && r + FLOW_STAGES < R) issue_row(r + FLOW_STAGES);
+                    if (last_reader && r + FLOW_STAGES < R) {
+                        slr::mbar_wait(&bar_free[r % FLOW_STAGES], (uint32_t)((r / FLOW_STAGES) & 1));   // acquire: every reader's loads
+                        issue_row(r + FLOW_STAGES);
+                    }
                 }
                 // the right lane hands its upper two phases to the left lane: every lane decodes 4 pixels and files 2
                 const float n2 = __shfl_xor_sync(0xffffffffu, ph[2], 1), n3 = __shfl_xor_sync(0xffffffffu, ph[3], 1);
@@ -377,9 +383,13 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
             }
             __syncwarp();
             int last = 0;
-            if (lane == 0) last = add_acq_rel_s32(&done_q[c], 1) + 1 == (u + 1) * n_q;
+            if (lane == 0) {
+                mbar_arrive(&bar_qry[c]);
+                last = count_job(&done_q[c]) + 1 == (u + 1) * n_q;
+            }
             last = __shfl_sync(0xffffffffu, last, 0);
             if (last) {  // nobody reads this row's tables any more: clear them for row r + FLOW_CTX
+                slr::mbar_wait(&bar_qry[c], (uint32_t)(u & 1));   // acquire: every query job's table reads
                 clear_tables(c, lane, 32);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_clr[c]);
