@@ -212,7 +212,8 @@ k_fused_mf(const FusedParams p)
         int32_t *k_row = p.match_k ? p.match_k + orow : nullptr;
         for (;;) {
             int g = 0;
-            if (lane == 0) g = atomicAdd(grp_ctr, 1);
+            // (atom.inc in plain PTX: ptxas turns a single-lane atomicAdd into a 14-instruction warp-aggregation sequence)
+            if (lane == 0) asm volatile("atom.relaxed.cta.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(g) : "r"(slr::smem_u32(grp_ctr)) : "memory");
             g = __shfl_sync(0xffffffffu, g, 0);
             if (g >= ngroups) break;
             int j[QPX], best[QPX];
