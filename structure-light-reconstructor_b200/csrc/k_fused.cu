@@ -45,13 +45,15 @@ namespace {
 using namespace slr_fused;
 
 // MAXT/MINB: launch bounds.  QPX: left pixels per lane in one query group (group = 32*QPX pixels).
-template <int MODE, int MAXT, int MINB, int QPX>
+// WCT > 0: the row width (table size, strict-mode plane count) as compile-time constants, as in k_fused_flow;
+// instantiated for BASELINE config 4's 2048 pixels.
+template <int MODE, int MAXT, int MINB, int QPX, int WCT = 0>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_fused_mf(const FusedParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool CLAMP = MODE == MODE_PHASE_INPUT;
-    const int W = p.W, N = p.N, T = p.T;
+    const int W = WCT ? WCT : p.W, N = (WCT && MODE == SLR_MODE_STRICT) ? 14 : p.N, T = (WCT == 2048) ? 4096 : p.T;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
 
     // this CTA's contiguous range of rows r = i * batch + b (scan index b fastest, so consecutive rows share the
@@ -68,7 +70,7 @@ k_fused_mf(const FusedParams p)
     const size_t stage_bytes = (MODE == MODE_PHASE_INPUT) ? (size_t)10 * W : (size_t)2 * N * W;
     RowTables tab;
     tab.T = T;
-    tab.logT = p.logT;
+    tab.logT = (WCT == 2048) ? 12 : p.logT;
     tab.HB = 2 * T;
     tab.ent = reinterpret_cast<uint2 *>(stage + stage_bytes);
     tab.head = reinterpret_cast<int *>(tab.ent + T);
@@ -427,6 +429,9 @@ static slr_status launch_fused(slr_engine *e, int mode, const uint8_t *d_stack, 
     }
 #undef SLR_PICK
 #undef SLR_PICK_Q
+    if (mode == SLR_MODE_STRICT && W == 2048 && T == 4096 && N == 14 && threads == FUSED_MAX_THREADS && qpx == 1 && !two &&
+        !getenv("SLR_FUSED_GENERIC_W"))
+        kern = k_fused_mf<SLR_MODE_STRICT, 1024, 1, 1, 2048>;
     SLR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     SLR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
