@@ -55,13 +55,12 @@ k1_mf_decode_strict(const uint8_t *__restrict__ stack, size_t P, long long chunk
             uint32_t m4 = 0;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                bool ok = (int)slr::byte_of(word(0), i) - (int)slr::byte_of(word(1), i) > black_thr;  // computeShadows (:199-204)
+                bool ok = slr::byte_diff<1>(word(0), word(1), i) > black_thr;  // computeShadows (:199-204)
                 int Pw[3];
 #pragma unroll
                 for (int f = 0; f < 3; f++)   // a = G4 - G2, b = G1 - G3 (:239-242)
-                    Pw[f] = slr::wrapped_strict_fx((int)slr::byte_of(word(5 + 4 * f), i) - (int)slr::byte_of(word(3 + 4 * f), i),
-                                                   (int)slr::byte_of(word(2 + 4 * f), i) - (int)slr::byte_of(word(4 + 4 * f), i),
-                                                   s_ptab, s_btab);
+                    Pw[f] = slr::wrapped_strict_fx_px(word(2 + 4 * f), word(3 + 4 * f), word(4 + 4 * f), word(5 + 4 * f), i,
+                                                      s_ptab, s_btab);
                 const float p = slr::heterodyne_strict_fx(Pw[0], Pw[1], Pw[2], ok);
                 ph[i] = ok ? p : slr::qnan();
                 m4 |= (ok ? 1u : 0u) << (8 * i);
@@ -136,12 +135,12 @@ k1_mf_decode_corrected_3x4(const uint8_t *__restrict__ stack, size_t P, long lon
             uint32_t m4 = 0;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                bool ok = (int)slr::byte_of(img[0][w], i) - (int)slr::byte_of(img[1][w], i) > black_thr;
+                bool ok = slr::byte_diff<1>(img[0][w], img[1][w], i) > black_thr;
                 float l[3];
 #pragma unroll
                 for (int f = 0; f < 3; f++) {
-                    const int a = (int)slr::byte_of(img[5 + 4 * f][w], i) - (int)slr::byte_of(img[3 + 4 * f][w], i);   // G4 - G2
-                    const int b = (int)slr::byte_of(img[2 + 4 * f][w], i) - (int)slr::byte_of(img[4 + 4 * f][w], i);   // G1 - G3
+                    const int a = slr::byte_diff<1>(img[5 + 4 * f][w], img[3 + 4 * f][w], i);   // G4 - G2
+                    const int b = slr::byte_diff<1>(img[2 + 4 * f][w], img[4 + 4 * f][w], i);   // G1 - G3
                     ok = ok && ((a | b) != 0);
                     l[f] = slr::atan2_pos((float)a, (float)b);
                 }
@@ -195,14 +194,14 @@ k1_mf_decode_corrected_fs(const uint8_t *__restrict__ stack, size_t P, long long
             uint32_t m4 = 0;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                bool ok = (int)slr::byte_of(img[0][w], i) - (int)slr::byte_of(img[1][w], i) > black_thr;
+                bool ok = slr::byte_diff<1>(img[0][w], img[1][w], i) > black_thr;
                 float lvl[F];
 #pragma unroll
                 for (int f = 0; f < F; f++) {
                     float nn = 0.0f, dd = 0.0f;
                     if (S == 4) {   // exact integer form: num = G4-G2, den = G1-G3
-                        const int in = (int)slr::byte_of(img[2 + 4 * f + 3][w], i) - (int)slr::byte_of(img[2 + 4 * f + 1][w], i);
-                        const int id = (int)slr::byte_of(img[2 + 4 * f + 0][w], i) - (int)slr::byte_of(img[2 + 4 * f + 2][w], i);
+                        const int in = slr::byte_diff<1>(img[2 + 4 * f + 3][w], img[2 + 4 * f + 1][w], i);
+                        const int id = slr::byte_diff<1>(img[2 + 4 * f + 0][w], img[2 + 4 * f + 2][w], i);
                         if (in == 0 && id == 0) ok = false;
                         nn = (float)in, dd = (float)id;
                     } else {

@@ -287,26 +287,43 @@ slr_status slr_build_strict_tables(slr_engine *e)
         if ((double)r != s) exact = false;
         return r;
     };
+    for (int k = 0; k < SLR_PTAB_SIZE; k++) ptab[k] = SLR_PTAB_DEGENERATE;   // (entries no (a, b) pair reaches)
     for (int q = 0; q <= 255; q++) {
         const float atp = atanf((float)q), atn = atanf((float)(-q));
-        ptab[0 * SLR_PTAB_STRIDE + q] = fx(atn);                       // b > 0, a <= 0 (:261 / :246)
-        ptab[1 * SLR_PTAB_STRIDE + q] = fx(atp + 2 * PI);              // b > 0, a > 0  (:259)
-        ptab[2 * SLR_PTAB_STRIDE + q] = fx(atp + PI);                  // b < 0, a <= 0 (:257 / :248)
-        ptab[3 * SLR_PTAB_STRIDE + q] = fx(atn + PI);                  // b < 0, a > 0  (:257)
-        ptab[4 * SLR_PTAB_STRIDE + q] = fx(PI / 2);                    // b == 0, a < 0 (:252)
-        ptab[5 * SLR_PTAB_STRIDE + q] = fx(3 * PI / 2);                // b == 0, a > 0 (:250)
+        ptab[SLR_PTAB_C_POS + q] = fx(atp + 2 * PI);                   // b > 0, a > 0  (:259)
+        ptab[SLR_PTAB_C_POS - (q + 1)] = fx(atn);                      // b > 0, a <= 0 (:261 / :246)
+        ptab[SLR_PTAB_C_NEG + q] = fx(atn + PI);                       // b < 0, a > 0  (:257)
+        ptab[SLR_PTAB_C_NEG - (q + 1)] = fx(atp + PI);                 // b < 0, a <= 0 (:257 / :248)
+        ptab[SLR_PTAB_C_ZERO + q] = fx(3 * PI / 2);                    // b == 0, a > 0 (:250): idx = a - 1
+        ptab[SLR_PTAB_C_ZERO - (q + 1)] = fx(PI / 2);                  // b == 0, a < 0 (:252): idx = a - 1 <= -2
     }
-    ptab[4 * SLR_PTAB_STRIDE + 0] = SLR_PTAB_DEGENERATE;               // a == 0 and b == 0 (:254)
+    ptab[SLR_PTAB_C_ZERO - 1] = SLR_PTAB_DEGENERATE;                   // a == 0 and b == 0 (:254)
     if (!exact) {
         slr_set_error("strict tables: a wrapped phase is not a multiple of 2^-24 (host libm atanf out of spec?)");
         return SLR_ERR_INVALID;
     }
     for (int b = -255; b <= 255; b++) {
         const uint32_t ub = (uint32_t)abs(b);
-        const uint32_t M = ub ? 65536u / ub + 1u : 65536u;  // b == 0: q = |a| selects within rows 4/5
-        const uint32_t row = (b > 0) ? 0u : (b < 0) ? 2u : 4u;
-        btab[b + 256] = M | ((row * (uint32_t)SLR_PTAB_STRIDE) << 17);
+        const uint32_t M = ub ? 65536u / ub + 1u : 65536u;
+        const uint32_t centre = (b > 0) ? SLR_PTAB_C_POS : (b < 0) ? SLR_PTAB_C_NEG : SLR_PTAB_C_ZERO;
+        btab[b + 256] = M | ((centre * 4u) << 17);
     }
+    // every (a, b) pair through the device's own lookup against the branch form of :246-261 (C++ int division)
+    for (int b = -255; b <= 255; b++)
+        for (int a = -255; a <= 255; a++) {
+            int32_t want;
+            if (a == 0 && b == 0) want = SLR_PTAB_DEGENERATE;
+            else if (a == 0) want = fx(b > 0 ? 0.0f : PI);
+            else if (b == 0) want = fx(a > 0 ? 3 * PI / 2 : PI / 2);
+            else {
+                const float at = atanf((float)(a / b));
+                want = fx(b < 0 ? at + PI : a > 0 ? at + 2 * PI : at);
+            }
+            if (slr::wrapped_strict_fx(a, b, ptab, btab) != want) {
+                slr_set_error("strict tables: lookup disagrees with the branch form at a = %d, b = %d", a, b);
+                return SLR_ERR_INVALID;
+            }
+        }
     btab[0] = 0;
     if (!e->d_ptab) SLR_CHECK_CUDA(cudaMalloc(&e->d_ptab, sizeof(ptab)));
     if (!e->d_btab) SLR_CHECK_CUDA(cudaMalloc(&e->d_btab, sizeof(btab)));

@@ -116,7 +116,7 @@ __device__ __forceinline__ void decode_px(const uint8_t *__restrict__ rows, int 
     };
     const uint32_t wv = plane(0), bv = plane(1);
 #pragma unroll
-    for (int i = 0; i < PX; i++) ok[i] = (int)slr::byte_of(wv, i) - (int)slr::byte_of(bv, i) > p.black_thr;  // computeShadows
+    for (int i = 0; i < PX; i++) ok[i] = slr::byte_diff<1>(wv, bv, i) > p.black_thr;  // computeShadows
     if (MODE == SLR_MODE_STRICT) {
         int P[3][PX];
 #pragma unroll
@@ -124,8 +124,7 @@ __device__ __forceinline__ void decode_px(const uint8_t *__restrict__ rows, int 
             const uint32_t g1 = plane(2 + 4 * f), g2 = plane(3 + 4 * f), g3 = plane(4 + 4 * f), g4 = plane(5 + 4 * f);
 #pragma unroll
             for (int i = 0; i < PX; i++)
-                P[f][i] = slr::wrapped_strict_fx((int)slr::byte_of(g4, i) - (int)slr::byte_of(g2, i),
-                                                 (int)slr::byte_of(g1, i) - (int)slr::byte_of(g3, i), s_ptab, s_btab);
+                P[f][i] = slr::wrapped_strict_fx_px(g1, g2, g3, g4, i, s_ptab, s_btab);
         }
 #pragma unroll
         for (int i = 0; i < PX; i++) ph[i] = slr::heterodyne_strict_fx(P[0][i], P[1][i], P[2][i], ok[i]);
@@ -137,8 +136,7 @@ __device__ __forceinline__ void decode_px(const uint8_t *__restrict__ rows, int 
             const uint32_t g1 = plane(2 + 4 * f), g2 = plane(3 + 4 * f), g3 = plane(4 + 4 * f), g4 = plane(5 + 4 * f);
 #pragma unroll
             for (int i = 0; i < PX; i++) {
-                const int a = (int)slr::byte_of(g4, i) - (int)slr::byte_of(g2, i);
-                const int b = (int)slr::byte_of(g1, i) - (int)slr::byte_of(g3, i);
+                const int a = slr::byte_diff<1>(g4, g2, i), b = slr::byte_diff<1>(g1, g3, i);
                 ok[i] = ok[i] && ((a | b) != 0);
                 l[f][i] = slr::atan2_pos((float)a, (float)b);
             }
@@ -218,13 +216,39 @@ __device__ __forceinline__ void load_phases(const unsigned char *stage, int W, i
     }
 }
 
-// Shared-memory tables of one row.  LinkT = int (k_fused_mf) or int16_t (k_fused_flow: three row contexts per SM).
+// Shared-memory tables of one row.  LinkT = int (k_fused_mf) or int16_t (k_fused_flow: four row contexts per SM).
+// A chain link (bucket head or nxt entry) names a node as L = 4 * entry + 2 * side (side 0 = the value's lower bucket,
+// 1 = its upper one), -1 ends a chain: the entry's byte offset is 2 * (L & ~3) and the node's int16 link sits at byte L
+// (int links: 2 * L), so a chain step costs one mask-and-shift and one add instead of separate index arithmetic.
 template <typename LinkT>
 struct RowTablesT {
     uint2 *ent;   // [T]  {x = distinct right phase (float bits), y = smallest right column carrying it}
-    int *head;    // [HB] bucket heads (-1 = empty); a bucket index is taken modulo HB (a power of two)
-    LinkT *nxt;   // [2T] node n = entry + T*(0|1); -1 ends a chain
+    int *head;    // [HB] bucket heads (link, -1 = empty); a bucket index is taken modulo HB (a power of two)
+    LinkT *nxt;   // [2T] link of node (entry, side) at index 2 * entry + side
     int T, logT, HB;
+    __device__ __forceinline__ const uint2 *entry_of(int L) const
+    {
+        int m;   // (opaque to the front end, which would otherwise rewrite 2 * (L & ~3) as ((L + L) & ~7): three instructions)
+        asm("and.b32 %0, %1, 0xfffffffc;" : "=r"(m) : "r"(L));
+        return reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(ent) + 2 * m);
+    }
+    __device__ __forceinline__ int next_of(int L) const
+    {
+        return (int)*reinterpret_cast<const LinkT *>(reinterpret_cast<const char *>(nxt) + L * (int)(sizeof(LinkT) / 2));
+    }
+    // One step of a chain walk that may have ended already: where L names a node (L >= 0), key = the node's phase bits
+    // and L = the node's link; an ended chain keeps both registers.  Predicated loads in PTX: the C++ form
+    // (a ? load : default) materialises the two defaults on every step.
+    __device__ __forceinline__ void chain_step(const uint2 *e, int &L, uint32_t &key) const
+    {
+        const uint32_t ea = slr::smem_u32(e), la = slr::smem_u32(nxt) + (uint32_t)(L * (int)(sizeof(LinkT) / 2));
+        if (sizeof(LinkT) == 2)
+            asm volatile("{\n.reg .pred p;\nsetp.ge.s32 p, %1, 0;\n@p ld.shared.u32 %0, [%2];\n@p ld.shared.s16 %1, [%3];\n}"
+                         : "+r"(key), "+r"(L) : "r"(ea), "r"(la));
+        else
+            asm volatile("{\n.reg .pred p;\nsetp.ge.s32 p, %1, 0;\n@p ld.shared.u32 %0, [%2];\n@p ld.shared.s32 %1, [%3];\n}"
+                         : "+r"(key), "+r"(L) : "r"(ea), "r"(la));
+    }
 };
 using RowTables = RowTablesT<int>;
 
@@ -288,8 +312,8 @@ __device__ __forceinline__ void insert_right(const RowTablesT<LinkT> &t, const f
         if (claimed[q]) {
             const float v = __uint_as_float(key[q]);
             const int lo = window_bucket<CLAMP>(__fsub_rn(v, 0.11f)), hi = window_bucket<CLAMP>(__fadd_rn(v, 0.11f));
-            t.nxt[h[q]] = (LinkT)atomicExch(&t.head[lo & (HB - 1)], (int)h[q]);
-            if (hi != lo) t.nxt[h[q] + T] = (LinkT)atomicExch(&t.head[hi & (HB - 1)], (int)h[q] + T);
+            t.nxt[2 * h[q]] = (LinkT)atomicExch(&t.head[lo & (HB - 1)], (int)(4 * h[q]));
+            if (hi != lo) t.nxt[2 * h[q] + 1] = (LinkT)atomicExch(&t.head[hi & (HB - 1)], (int)(4 * h[q] + 2));
         }
     }
 }
@@ -301,8 +325,8 @@ __device__ __forceinline__ int first_match(const RowTablesT<LinkT> &t, float v)
     int best = INT_MAX;
     int n = t.head[window_bucket<CLAMP>(v) & (t.HB - 1)];
     while (n >= 0) {
-        const uint2 e = t.ent[n & (t.T - 1)];
-        n = t.nxt[n];
+        const uint2 e = *t.entry_of(n);
+        n = t.next_of(n);
         if (slr::phase_match(v, __uint_as_float(e.x))) best = min(best, (int)e.y);
     }
     return best;
@@ -317,15 +341,15 @@ __device__ __forceinline__ void first_match_x2(const RowTablesT<LinkT> &t, float
     best0 = best1 = INT_MAX;
     int n0 = (v0 == v0) ? t.head[window_bucket<CLAMP>(v0) & (t.HB - 1)] : -1;
     int n1 = (v1 == v1) ? t.head[window_bucket<CLAMP>(v1) & (t.HB - 1)] : -1;
+    uint32_t k0 = 0u, k1 = 0u;
     while ((n0 & n1) >= 0) {   // at least one chain has a node left
-        const int e0 = max(n0, 0) & (t.T - 1), e1 = max(n1, 0) & (t.T - 1);
+        // (an ended chain's link is -1: every access through it is predicated off)
+        const uint2 *e0 = t.entry_of(n0), *e1 = t.entry_of(n1);
         const bool a0 = n0 >= 0, a1 = n1 >= 0;
-        const uint32_t k0 = a0 ? t.ent[e0].x : 0u, k1 = a1 ? t.ent[e1].x : 0u;
-        const int m0 = a0 ? (int)t.nxt[n0] : -1, m1 = a1 ? (int)t.nxt[n1] : -1;
-        if (a0 && slr::phase_match(v0, __uint_as_float(k0))) best0 = min(best0, (int)t.ent[e0].y);
-        if (a1 && slr::phase_match(v1, __uint_as_float(k1))) best1 = min(best1, (int)t.ent[e1].y);
-        n0 = m0;
-        n1 = m1;
+        t.chain_step(e0, n0, k0);
+        t.chain_step(e1, n1, k1);
+        if (a0 && slr::phase_match(v0, __uint_as_float(k0))) best0 = min(best0, (int)e0->y);
+        if (a1 && slr::phase_match(v1, __uint_as_float(k1))) best1 = min(best1, (int)e1->y);
     }
 }
 

@@ -289,16 +289,16 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
                         issue_row(r + FLOW_STAGES);
                     }
                 }
-                // the right lane hands its upper two phases to the left lane: every lane decodes 4 pixels and files 2
+                // the right lane hands its upper two phases to the left lane: every lane decodes 4 pixels and files 2.
+                // A pixel without a phase travels as NaN (a decoded phase never is one; a caller-supplied NaN on the
+                // right is no phase either, load_phases), so the masks need no shuffle of their own.
+#pragma unroll
+                for (int q = 0; q < 4; q++) ph[q] = ok[q] ? ph[q] : slr::qnan();
                 const float n2 = __shfl_xor_sync(0xffffffffu, ph[2], 1), n3 = __shfl_xor_sync(0xffffffffu, ph[3], 1);
-                const unsigned okb = __shfl_xor_sync(0xffffffffu, (ok[2] ? 1u : 0u) | (ok[3] ? 2u : 0u), 1);
                 float ip[2] = {right ? ph[0] : n2, right ? ph[1] : n3};
-                bool io[2] = {live && (right ? ok[0] : (okb & 1u) != 0), live && (right ? ok[1] : (okb & 2u) != 0)};
+                bool io[2] = {live && ip[0] == ip[0], live && ip[1] == ip[1]};
                 insert_right<2, CLAMP>(tab, ip, io, right ? x0 : x0 + 2);
-                if (live && !right)
-                    reinterpret_cast<float4 *>(s_pl)[x0 >> 2] =
-                        make_float4(ok[0] ? ph[0] : slr::qnan(), ok[1] ? ph[1] : slr::qnan(), ok[2] ? ph[2] : slr::qnan(),
-                                    ok[3] ? ph[3] : slr::qnan());
+                if (live && !right) reinterpret_cast<float4 *>(s_pl)[x0 >> 2] = make_float4(ph[0], ph[1], ph[2], ph[3]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_dec[c]);
@@ -420,7 +420,7 @@ slr_status slr_launch_fused_flow(slr_engine *e, int mode, const FusedParams &p_i
     const bool raw = p.map1 != nullptr;   // the stack holds raw camera images: rectify jobs fill the stage buffer
     const int n_d = (W / 2 + 31) / 32, n_q = (W + 32 * FLOW_QPX - 1) / (32 * FLOW_QPX);
     const int n_r = raw ? 2 * ((W + 127) / 128) : 0;
-    if (smem > 227 * 1024 || 2 * p.T > 32768 || (stage_bytes % 16) != 0) return SLR_OK;
+    if (smem > 227 * 1024 || 4 * p.T > 32768 || (stage_bytes % 16) != 0) return SLR_OK;   // (16-bit links hold 4 * entry + 2)
     if (raw && (mode == MODE_PHASE_INPUT || p.calib.row0 != 0)) return SLR_OK;
     // rows per CTA must keep the job counter inside int32, pixel offsets inside uint32
     const long long rows = (long long)p.batch * p.H;

@@ -187,37 +187,68 @@ __device__ __forceinline__ bool phase_strict(const int (&G)[12], const float *__
 // byte i of a 32-bit word, zero extended: one PRMT
 __device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return __byte_perm(w, 0, 0x4440 + i); }
 
+// SC * (byte i of x - byte i of y) + c for two words of four pixels, SC in -128..127: two integer dot products with a
+// one-hot weight word (IDP.4A, unsigned bytes times signed weights, on the FMA pipe) instead of two byte extractions and
+// a subtraction on the ALU pipe, which is the busiest pipe of the strict decode.  i is a compile-time constant
+// wherever this is called (unrolled pixel loops), so the weight words are immediates.
+template <int SC>
+__device__ __forceinline__ int byte_diff(uint32_t x, uint32_t y, int i, int c = 0)
+{
+    const int wp = (int)((uint32_t)(SC & 0xff) << (8 * i)), wn = (int)((uint32_t)(-SC & 0xff) << (8 * i));
+    int r;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(y), "r"(wn), "r"(c));
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(wp), "r"(r));
+    return r;
+}
+
 // Every wrapped phase the reference can produce (Duke/mfreconstruct.cpp:246-261) is one of a few hundred floats in
 // [-1.6, 7.9], each zero or >= 0.78 in magnitude, i.e. an integer multiple of 2^-24.  The tables hold them as
 // int32 in units of 2^-24 ("fixed point", exact), so that the double-precision steps of :265-266 become exact
 // integer arithmetic followed by ONE rounding (I2F), which is what narrowing the exact double to float does.
 //
 //   btab[b + 256], b = G1-G3 in [-255, 255]:  bits 0..16  M = floor(65536/|b|) + 1   (b == 0: 65536)
-//                                             bits 17..   first ptab entry of the first row of this sign of b
-//   q = (|a| * M) >> 16 == floor(|a| / |b|) for 0 <= |a|, |b| <= 255 (b == 0: q = |a|): the excess |a|/65536 < 1/256
-//       <= 1/|b| can never reach the next integer because a non-integer quotient has a fractional part <= 1 - 1/|b|.
-//   ptab rows (256 entries, index q; C++ int division truncates toward zero, so the signed quotient is +-q):
-//     0: b > 0, a <= 0   atan(float(-q))            (:261, and :246 via q = 0)
-//     1: b > 0, a >  0   atan(float( q)) + 2*PI     (:259)
-//     2: b < 0, a <= 0   atan(float( q)) + PI       (:257, and :248 via q = 0)
-//     3: b < 0, a >  0   atan(float(-q)) + PI       (:257)
-//     4: b == 0, a <= 0  PI/2 (:252); entry 0 (a == 0: the degenerate branch :254) = SLR_PTAB_DEGENERATE
-//     5: b == 0, a >  0  3*PI/2 (:250)
-// Rows start SLR_PTAB_STRIDE = 256 + 8 words apart: the quotient is 0..7 for nine pixels in ten, and with the skew the
-// entries q = 0..7 of rows 0..3 (the four sign cases a warp mixes freely) occupy 32 distinct shared-memory banks instead
-// of four words each in banks 0..7.
-#define SLR_PTAB_ROWS 6
-#define SLR_PTAB_STRIDE 264
-#define SLR_PTAB_SIZE (SLR_PTAB_ROWS * SLR_PTAB_STRIDE)
+//                                             bits 17..   byte offset of the centre of b's group in ptab
+//   idx = (a * M - 1) >> 16 (arithmetic shift, a = G4-G2 signed) tells the sign of a AND the quotient apart:
+//       a >  0:  idx =  q        a <= 0:  idx = -(q + 1)        with q = floor(|a| / |b|) (b == 0: see below)
+//     |a| * M / 65536 exceeds |a| / |b| by less than |a| / 65536 < 1/256 <= 1/|b|, and a non-integer quotient has a
+//     fractional part <= 1 - 1/|b|: the scaled product never reaches q + 1, and for a != 0 it is never an integer
+//     (it is strictly above |a| / |b| >= q).  So flooring (a*M - 1) / 65536 gives q for a > 0, -(q + 1) for a < 0 (the
+//     negated ceiling) and -1 for a == 0, which shares its entry with a < 0, q == 0: both are atan(+-0) (+ PI).
+//     C++ int division truncates toward zero, so the reference's quotient is sign(a)*sign(b)*q.
+//   ptab groups of 512 entries around a centre (entry = centre + idx):
+//     b > 0:  idx >= 0  atan(float( q)) + 2*PI  (:259)         idx < 0  atan(float(-q))       (:261, :246 via a == 0)
+//     b < 0:  idx >= 0  atan(float(-q)) + PI    (:257)         idx < 0  atan(float( q)) + PI  (:257, :248 via a == 0)
+//     b == 0 (M = 65536, idx = a - 1):  idx >= 0  3*PI/2 (:250)     idx == -1  SLR_PTAB_DEGENERATE (:254)
+//                                       idx <= -2  PI/2 (:252)
+// The centres of the first two groups sit 16 banks apart: the quotient is 0..7 for nine pixels in ten, and those
+// entries of the four sign cases a warp mixes freely (idx -8..7 of both groups) occupy 32 distinct shared-memory banks.
+// slr_build_strict_tables (k_fused.cu) checks every (a, b) pair against the branch form before an engine starts.
+#define SLR_PTAB_C_POS 256                 // centre of the b > 0 group: entries 0..511
+#define SLR_PTAB_C_NEG (512 + 16 + 256)    // centre of the b < 0 group: entries 528..1039 (bank 16 where C_POS is bank 0)
+#define SLR_PTAB_C_ZERO (1040 + 256)       // centre of the b == 0 group: entries 1040..1551
+#define SLR_PTAB_SIZE 1552
 #define SLR_BTAB_SIZE 512
 #define SLR_PTAB_DEGENERATE INT_MIN
 
-__device__ __forceinline__ int wrapped_strict_fx(int a, int b, const int *__restrict__ ptab,
-                                                 const uint32_t *__restrict__ btab)
+// t = btab[b + 256]
+__host__ __device__ __forceinline__ int strict_lookup(int a, uint32_t t, const int *__restrict__ ptab)
 {
-    const uint32_t t = btab[b + 256];
-    const uint32_t q = ((uint32_t)abs(a) * (t & 0x1FFFFu)) >> 16;
-    return ptab[(t >> 17) + q + ((a > 0) ? (unsigned)SLR_PTAB_STRIDE : 0u)];
+    const int sp = a * (int)(t & 0x1FFFFu) - 1;
+    return *reinterpret_cast<const int *>(reinterpret_cast<const char *>(ptab) + (t >> 17) + ((sp >> 16) << 2));
+}
+__host__ __device__ __forceinline__ int wrapped_strict_fx(int a, int b, const int *__restrict__ ptab,
+                                                          const uint32_t *__restrict__ btab)
+{
+    return strict_lookup(a, btab[b + 256], ptab);
+}
+// The same for pixel i of the four plane words G1..G4 of one frequency (a = G4 - G2, b = G1 - G3, :239-242), tables
+// in shared memory: the address of b's btab entry comes straight out of the dot products.
+__device__ __forceinline__ int wrapped_strict_fx_px(uint32_t g1, uint32_t g2, uint32_t g3, uint32_t g4, int i,
+                                                    const int *__restrict__ s_ptab, const uint32_t *__restrict__ s_btab)
+{
+    uint32_t t;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(byte_diff<4>(g1, g3, i, (int)smem_u32(s_btab + 256))));
+    return strict_lookup(byte_diff<1>(g4, g2, i), t, s_ptab);
 }
 
 // Heterodyne of :265-268 on fixed-point wrapped phases.  I0 - I1 (+ 2*PI) is exact in int32 (|I| < 2^27), and
@@ -236,8 +267,10 @@ __device__ __forceinline__ float heterodyne_strict_fx(int I0, int I1, int I2, bo
     const int C_I = (int)C_S;                           // 2*PI in units of 2^-24 (a multiple of 8)
     ok = ok && (min(I0, min(I1, I2)) != SLR_PTAB_DEGENERATE);
     // (unsigned arithmetic: a degenerate entry would overflow int; its pixel is dropped anyway)
-    const int d01 = (int)((unsigned)I0 - (unsigned)I1 + ((I0 > I1) ? 0u : (unsigned)C_I));
-    const int d12 = (int)((unsigned)I1 - (unsigned)I2 + ((I1 > I2) ? 0u : (unsigned)C_I));
+    // (no overflow for table values, so I0 > I1 is the sign of the difference: one compare-and-add on the difference)
+    int d01 = (int)((unsigned)I0 - (unsigned)I1), d12 = (int)((unsigned)I1 - (unsigned)I2);
+    if (d01 <= 0) d01 = (int)((unsigned)d01 + (unsigned)C_I);
+    if (d12 <= 0) d12 = (int)((unsigned)d12 + (unsigned)C_I);
     const float P12 = __int2float_rn(d01);              // = P12 * 2^24
     const float P23 = __int2float_rn(d12);
     const float d = __fsub_rn(P12, P23);
@@ -344,10 +377,10 @@ __device__ __forceinline__ void div3_narrow(double a0, double a1, double a2, dou
         const double rem = fma(-q, w, a);
         q = fma(rem, r, q);
         f = __double2float_rn(q);
-        const unsigned lo = (unsigned)__double2loint(q) & 0x1FFFFFFFu;
-        const unsigned ef = (__float_as_uint(f) >> 23) & 0xffu;
-        slow |= (lo - 0x0FFFFFF8u) < 17u;                  // float rounding boundary within 8 double ulps
-        slow |= (ef - 1u) > 253u;                          // zero, subnormal, inf or nan result
+        // float rounding boundary within 8 double ulps: the 29 dropped bits in 0x0FFFFFF8 .. 0x10000008 — tested as
+        // "bits 5..28 of (dropped - 0x0FFFFFF8) are clear", i.e. .. 0x10000017: a superset, one add and one test
+        slow |= (((unsigned)__double2loint(q) - 0x0FFFFFF8u) & 0x1FFFFFE0u) == 0u;
+        slow |= !(fabsf(f) >= 1.17549435e-38f && fabsf(f) <= 3.40282347e+38f);   // zero, subnormal, inf or nan result
     };
     one(a0, f0);
     one(a1, f1);
