@@ -236,18 +236,29 @@ struct RowTablesT {
     {
         return (int)*reinterpret_cast<const LinkT *>(reinterpret_cast<const char *>(nxt) + L * (int)(sizeof(LinkT) / 2));
     }
-    // One step of a chain walk that may have ended already: where L names a node (L >= 0), key = the node's phase bits
-    // and L = the node's link; an ended chain keeps both registers.  Predicated loads in PTX: the C++ form
-    // (a ? load : default) materialises the two defaults on every step.
-    __device__ __forceinline__ void chain_step(const uint2 *e, int &L, uint32_t &key) const
+    // One step of the walk for left phase v along a chain that may have ended already: where L names a node (L >= 0),
+    // best = min(best, the node's column) if the node's phase matches v (slr::phase_match: fabsf(v - pR) < 0.1f), and
+    // L = the node's link; an ended chain keeps its registers.  In PTX because the C++ form (a ? load : default)
+    // materialises a default for every predicated load on every step.  The entry {phase bits, smallest column} is one
+    // 64-bit load: two steps in five match and need the column anyway, and a second load of the same entry costs an
+    // instruction and as many shared-memory wavefronts as the first.
+    __device__ __forceinline__ void chain_step(float v, int &L, int &best, uint32_t &key, int &col) const
     {
-        const uint32_t ea = slr::smem_u32(e), la = slr::smem_u32(nxt) + (uint32_t)(L * (int)(sizeof(LinkT) / 2));
+        const uint32_t ea = slr::smem_u32(entry_of(L)), la = slr::smem_u32(nxt) + (uint32_t)(L * (int)(sizeof(LinkT) / 2));
+#define SLR_CHAIN_STEP(LD_LINK)                                                                               \
+    asm volatile("{\n.reg .pred p, q;\n.reg .f32 d;\n"                                                       \
+                 "setp.ge.s32 p, %0, 0;\n"                                                                     \
+                 "@p ld.shared.v2.u32 {%2, %3}, [%5];\n"                                                       \
+                 "@p " LD_LINK " %0, [%6];\n"                                                                  \
+                 "sub.rn.f32 d, %4, %2;\nabs.f32 d, d;\nsetp.lt.and.f32 q, d, 0f3DCCCCCD, p;\n"                \
+                 "@q min.s32 %1, %1, %3;\n}"                                                                   \
+                 : "+r"(L), "+r"(best), "+r"(key), "+r"(col)                                                   \
+                 : "f"(v), "r"(ea), "r"(la))
         if (sizeof(LinkT) == 2)
-            asm volatile("{\n.reg .pred p;\nsetp.ge.s32 p, %1, 0;\n@p ld.shared.u32 %0, [%2];\n@p ld.shared.s16 %1, [%3];\n}"
-                         : "+r"(key), "+r"(L) : "r"(ea), "r"(la));
+            SLR_CHAIN_STEP("ld.shared.s16");
         else
-            asm volatile("{\n.reg .pred p;\nsetp.ge.s32 p, %1, 0;\n@p ld.shared.u32 %0, [%2];\n@p ld.shared.s32 %1, [%3];\n}"
-                         : "+r"(key), "+r"(L) : "r"(ea), "r"(la));
+            SLR_CHAIN_STEP("ld.shared.s32");
+#undef SLR_CHAIN_STEP
     }
 };
 using RowTables = RowTablesT<int>;
@@ -334,22 +345,17 @@ __device__ __forceinline__ int first_match(const RowTablesT<LinkT> &t, float v)
 
 // The same for two left pixels at once (NaN = no pixel): both chains advance in one loop, so a warp iterates
 // max(len0, len1) over its lanes instead of max(len0) + max(len1), and the two walks' shared-memory round trips overlap.
-// The smallest-column word of an entry is loaded only where the value matches.
 template <bool CLAMP, typename LinkT>
 __device__ __forceinline__ void first_match_x2(const RowTablesT<LinkT> &t, float v0, float v1, int &best0, int &best1)
 {
     best0 = best1 = INT_MAX;
     int n0 = (v0 == v0) ? t.head[window_bucket<CLAMP>(v0) & (t.HB - 1)] : -1;
     int n1 = (v1 == v1) ? t.head[window_bucket<CLAMP>(v1) & (t.HB - 1)] : -1;
-    uint32_t k0 = 0u, k1 = 0u;
-    while ((n0 & n1) >= 0) {   // at least one chain has a node left
-        // (an ended chain's link is -1: every access through it is predicated off)
-        const uint2 *e0 = t.entry_of(n0), *e1 = t.entry_of(n1);
-        const bool a0 = n0 >= 0, a1 = n1 >= 0;
-        t.chain_step(e0, n0, k0);
-        t.chain_step(e1, n1, k1);
-        if (a0 && slr::phase_match(v0, __uint_as_float(k0))) best0 = min(best0, (int)e0->y);
-        if (a1 && slr::phase_match(v1, __uint_as_float(k1))) best1 = min(best1, (int)e1->y);
+    uint32_t k0 = 0u, k1 = 0u;   // (scratch registers of the steps)
+    int c0 = INT_MAX, c1 = INT_MAX;
+    while ((n0 & n1) >= 0) {   // at least one chain has a node left (an ended chain's link is -1)
+        t.chain_step(v0, n0, best0, k0, c0);
+        t.chain_step(v1, n1, best1, k1, c1);
     }
 }
 

@@ -323,8 +323,9 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
                 j[q] = (qidx * FLOW_QPX + q) * 32 + lane;
                 const bool inside = j[q] < W;
                 // undistortPoints maps of the left pixel (L2-resident, coalesced): in flight during the table walk
-                ulx[q] = inside ? __ldg(p.lx + ri.map_px + j[q]) : 0.0f;
-                uly[q] = inside ? __ldg(p.ly + ri.map_px + j[q]) : 0.0f;
+                // (one 32-bit pixel index per load, widened once: pointer + unsigned + int is two 64-bit additions)
+                ulx[q] = inside ? __ldg(p.lx + (ri.map_px + (unsigned)j[q])) : 0.0f;
+                uly[q] = inside ? __ldg(p.ly + (ri.map_px + (unsigned)j[q])) : 0.0f;
                 v[q] = inside ? s_pl[j[q]] : slr::qnan();
             }
             static_assert(FLOW_QPX == 2, "the query job walks two chains per lane");
@@ -336,7 +337,7 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
                 const bool hit = best[q] != INT_MAX;
                 d[q] = 1.0f;
                 if (hit)
-                    d[q] = __fsub_rn(ulx[q], __ldg(p.rx + ri.map_px + best[q]));
+                    d[q] = __fsub_rn(ulx[q], __ldg(p.rx + (ri.map_px + (unsigned)best[q])));
                 else
                     ulx[q] = 0.0f, uly[q] = 0.0f;
             }

@@ -380,11 +380,14 @@ __device__ __forceinline__ void div3_narrow(double a0, double a1, double a2, dou
         // float rounding boundary within 8 double ulps: the 29 dropped bits in 0x0FFFFFF8 .. 0x10000008 — tested as
         // "bits 5..28 of (dropped - 0x0FFFFFF8) are clear", i.e. .. 0x10000017: a superset, one add and one test
         slow |= (((unsigned)__double2loint(q) - 0x0FFFFFF8u) & 0x1FFFFFE0u) == 0u;
-        slow |= !(fabsf(f) >= 1.17549435e-38f && fabsf(f) <= 3.40282347e+38f);   // zero, subnormal, inf or nan result
     };
     one(a0, f0);
     one(a1, f1);
     one(a2, f2);
+    // a zero, subnormal or infinite result: smallest and largest magnitude of the three against the normal range (a NaN
+    // quotient needs a NaN numerator here, w being finite and non-zero, and is a NaN on either path)
+    slow |= !(fminf(fminf(fabsf(f0), fabsf(f1)), fabsf(f2)) >= 1.17549435e-38f &&
+              fmaxf(fmaxf(fabsf(f0), fabsf(f1)), fabsf(f2)) <= 3.40282347e+38f);
     if (slow) {
         f0 = __double2float_rn(__ddiv_rn(a0, w));
         f1 = __double2float_rn(__ddiv_rn(a1, w));
