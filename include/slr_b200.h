@@ -95,6 +95,11 @@ SLR_API slr_status slr_set_calib(slr_engine *e, const slr_camera cams[2], const 
                                  const float *rigid3x4);
 SLR_API const char *slr_last_error(void);
 SLR_API const char *slr_version(void);
+/* Host-only self-check of the strict-mode lookup tables the MF kernels decode with (they replace the branches of
+ * Duke/mfreconstruct.cpp:246-261: C++ int division inside atan, PI = 3.1416f).  Builds the tables as an engine does and
+ * compares the lookup with the branch form for every a = G4-G2, b = G1-G3 in [-255, 255]; h_fx (NULL, or 511 x 511
+ * int32) receives the wrapped phases [b + 255][a + 255] in units of 2^-24 (INT32_MIN: the pixel is dropped, :254). */
+SLR_API slr_status slr_strict_tables_check(int32_t *h_fx);
 
 /* ---- pattern synthesis (host; rows a1, a2 of SURVEY.md §8) ------------------------------------- */
 /* GrayCodes::calNumOfImgs, Duke/graycodes.cpp:22-30 */

@@ -64,7 +64,7 @@ EXPORTS = [
     "slr_kernel_launches", "slr_mesh_index", "slr_mesh_index_host", "slr_allgather", "slr_nccl_unique_id",
     "slr_nccl_comm_create", "slr_nccl_comm_destroy", "slr_set_rectify_maps", "slr_rectify_stack", "slr_set_host_input_raw", "slr_run_gray_host",
     "slr_run_mf_raw", "slr_ingest_begin", "slr_ingest_image", "slr_run_mf_ingested", "slr_run_ge_ingested", "slr_ingest_abort",
-    "slr_horn_method", "slr_register_scan", "slr_merge_scans", "slr_png_unfilter",
+    "slr_horn_method", "slr_register_scan", "slr_merge_scans", "slr_png_unfilter", "slr_strict_tables_check",
 ]
 
 
@@ -85,6 +85,7 @@ def capi():
     lib.slr_set_stream.argtypes = [vp, vp]
     lib.slr_synchronize.argtypes = [vp]
     lib.slr_set_calib.argtypes = [vp, C.POINTER(CCamera), C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    lib.slr_strict_tables_check.argtypes = [vp]
     lib.slr_gray_num_bits.argtypes = [i32]
     lib.slr_gray_num_imgs.argtypes = [i32, i32, i32]
     lib.slr_generate_gray_patterns.argtypes = [vp, i32, i32, i32]
@@ -154,6 +155,15 @@ def generate_gray_patterns(W: int, H: int, use_epi: bool) -> np.ndarray:
     n = lib.slr_gray_num_imgs(W, H, int(use_epi))
     out = np.empty((n, H, W), np.uint8)
     _check(lib.slr_generate_gray_patterns(out.ctypes.data, W, H, int(use_epi)), "slr_generate_gray_patterns")
+    return out
+
+
+def strict_tables() -> np.ndarray:
+    """The MF kernels' strict-mode lookup (slr_device.cuh: wrapped_strict_fx) for every a = G4-G2, b = G1-G3 in
+    [-255, 255] -> int32 [511 (b + 255), 511 (a + 255)] in units of 2^-24, INT32_MIN where the pixel is dropped
+    (Duke/mfreconstruct.cpp:246-261).  Host-only: raises if the library's own check against the branch form fails."""
+    out = np.empty((511, 511), np.int32)
+    _check(capi().slr_strict_tables_check(out.ctypes.data), "slr_strict_tables_check")
     return out
 
 

@@ -274,11 +274,9 @@ k_fused_mf(const FusedParams p)
 
 }  // namespace
 
-// strict-mode tables (layout: slr_device.cuh), built once per engine on the host with the host libm
-slr_status slr_build_strict_tables(slr_engine *e)
+// strict-mode tables (layout: slr_device.cuh), built on the host with the host libm and checked for every (a, b)
+static slr_status strict_tables_host(int32_t *ptab, uint32_t *btab)
 {
-    static int32_t ptab[SLR_PTAB_SIZE];
-    static uint32_t btab[SLR_BTAB_SIZE];
     const float PI = SLR_PI_DEC;
     bool exact = true;
     auto fx = [&](float v) -> int32_t {  // v in units of 2^-24; exact for every value the reference can produce
@@ -325,10 +323,33 @@ slr_status slr_build_strict_tables(slr_engine *e)
             }
         }
     btab[0] = 0;
+    return SLR_OK;
+}
+
+// once per engine
+slr_status slr_build_strict_tables(slr_engine *e)
+{
+    static int32_t ptab[SLR_PTAB_SIZE];
+    static uint32_t btab[SLR_BTAB_SIZE];
+    const slr_status st = strict_tables_host(ptab, btab);
+    if (st != SLR_OK) return st;
     if (!e->d_ptab) SLR_CHECK_CUDA(cudaMalloc(&e->d_ptab, sizeof(ptab)));
     if (!e->d_btab) SLR_CHECK_CUDA(cudaMalloc(&e->d_btab, sizeof(btab)));
     SLR_CHECK_CUDA(cudaMemcpy(e->d_ptab, ptab, sizeof(ptab), cudaMemcpyHostToDevice));
     SLR_CHECK_CUDA(cudaMemcpy(e->d_btab, btab, sizeof(btab), cudaMemcpyHostToDevice));
+    return SLR_OK;
+}
+
+// Host-only view of the same tables for tests: h_fx[(b + 255) * 511 + (a + 255)] = the kernels' lookup for a = G4 - G2,
+// b = G1 - G3 (needs no GPU and no engine).
+extern "C" slr_status slr_strict_tables_check(int32_t *h_fx)
+{
+    static int32_t ptab[SLR_PTAB_SIZE];
+    static uint32_t btab[SLR_BTAB_SIZE];
+    const slr_status st = strict_tables_host(ptab, btab);
+    if (st != SLR_OK || !h_fx) return st;
+    for (int b = -255; b <= 255; b++)
+        for (int a = -255; a <= 255; a++) h_fx[(b + 255) * 511 + (a + 255)] = slr::wrapped_strict_fx(a, b, ptab, btab);
     return SLR_OK;
 }
 

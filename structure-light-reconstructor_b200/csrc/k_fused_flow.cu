@@ -70,22 +70,34 @@ __device__ long long g_flow_trace[TRACE_JOBS * 4];   // {type | row << 8 | warp 
 #define FLOW_TRACE_END(type, row) do { } while (0)
 #endif
 
-// counter += 1, returns the old value: elects the job that finishes a row's stage reads / queries last.  The ORDERING
-// between the jobs' shared-memory accesses and what the elected job does next (bulk copies into the stage, the table
-// clear) comes from an mbarrier every job arrives on (release) and the elected job waits on (acquire) — an acq_rel atomic
-// costs a MEMBAR.ALL.CTA that also waits for the job's global stores.  (atom.inc, not atom.add: ptxas wraps an add of a
-// warp-uniform operand into its warp-aggregation sequence — vote, popc, lane masks — which costs more than the atomic
-// when a single lane executes it.)
-__device__ __forceinline__ int count_job(int *p)
+// The single-lane steps of a job: lane 0 arrives (release) on an mbarrier that counts jobs and / or bumps a counter for
+// its warp.  counter += 1 returns the old value and elects the job that finishes a row's stage reads / queries last;
+// the ORDERING between the jobs' shared-memory accesses and what the elected job does next (bulk copies into the stage,
+// the table clear) comes from the mbarrier every job arrives on (release) and the elected job waits on (acquire) — an
+// acq_rel atomic costs a MEMBAR.ALL.CTA that also waits for the job's global stores.  (atom.inc, not atom.add: ptxas
+// wraps an add of a warp-uniform operand into its warp-aggregation sequence — vote, popc, lane masks — which costs more
+// than the atomic when a single lane executes it.)  Written as predicated PTX rather than `if (lane == 0)`: no default
+// value to materialise for the other lanes and one convergence region where a job does both.  Results are defined on
+// lane 0 only.
+__device__ __forceinline__ void mbar_arrive_lane0(int lane, uint64_t *bar)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.eq.s32 p, %1, 0;\n@p mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n}"
+                 ::"r"(slr::smem_u32(bar)), "r"(lane) : "memory");
+}
+__device__ __forceinline__ int count_lane0(int lane, int *ctr)
 {
     unsigned old;
-    asm volatile("atom.relaxed.cta.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(old) : "r"(slr::smem_u32(p)) : "memory");
+    asm volatile("{\n.reg .pred p;\nsetp.eq.s32 p, %2, 0;\n@p atom.relaxed.cta.shared.inc.u32 %0, [%1], 0x7fffffff;\n}"
+                 : "=r"(old) : "r"(slr::smem_u32(ctr)), "r"(lane) : "memory");
     return (int)old;
 }
-// one arrival (release) on an mbarrier that counts jobs
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+__device__ __forceinline__ int arrive_count_lane0(int lane, uint64_t *bar, int *ctr)   // both, in this order
 {
-    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(slr::smem_u32(bar)) : "memory");
+    unsigned old;
+    asm volatile("{\n.reg .pred p;\nsetp.eq.s32 p, %3, 0;\n@p mbarrier.arrive.release.cta.shared::cta.b64 _, [%1];\n"
+                 "@p atom.relaxed.cta.shared.inc.u32 %0, [%2], 0x7fffffff;\n}"
+                 : "=r"(old) : "r"(slr::smem_u32(bar)), "r"(slr::smem_u32(ctr)), "r"(lane) : "memory");
+    return (int)old;
 }
 
 // shared-memory bytes of one row context: ent[T] (8 B) + head[T] (4 B) + nxt[2T] (2 B) + left phases [W] (4 B)
@@ -217,10 +229,8 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
     // of a step from draw to completion (8 warps share a scheduler), so a row's queries are drawn two steps after
     // its decode jobs and practically never wait.
     for (;;) {
-        int g = 0;
         // (atom.inc in plain PTX: atomicAdd / atom.add under `lane == 0` becomes a 14-instruction warp-aggregation sequence)
-        if (lane == 0) asm volatile("atom.relaxed.cta.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(g) : "r"(slr::smem_u32(job_ctr)) : "memory");
-        g = __shfl_sync(0xffffffffu, g, 0);
+        const int g = __shfl_sync(0xffffffffu, count_lane0(lane, job_ctr), 0);
         if (g >= total_jobs) break;
         FLOW_TRACE_DRAW();
         const int t = (int)__umulhi((unsigned)g, js_magic);   // g / JS (exact for g * JS < 2^32, checked by the launcher)
@@ -250,7 +260,7 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
                                                 p.map2 + (size_t)cam * P, W, p.H, N, i, x, x < W, dst, (size_t)W, lane);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_stage[r % FLOW_STAGES]);
+            mbar_arrive_lane0(lane, &bar_stage[r % FLOW_STAGES]);
             FLOW_TRACE_END(3, r);
             continue;
         }
@@ -279,12 +289,11 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
                 // the last reader streams row r + 2 into the buffer: a third of a decode job earlier than its completion,
                 // which is the slack the bulk copies need to land before row r + 2 is drawn.
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_free[r % FLOW_STAGES]);
-                if (!RAW) {
-                    int last_reader = 0;
-                    if (lane == 0) last_reader = count_job(&done_l[c]) + 1 == (u + 1) * n_d;
-                    last_reader = __shfl_sync(0xffffffffu, last_reader, 0);
-                    if (last_reader && r + FLOW_STAGES < R) {
+                if (RAW) {
+                    mbar_arrive_lane0(lane, &bar_free[r % FLOW_STAGES]);
+                } else {
+                    const int readers = __shfl_sync(0xffffffffu, arrive_count_lane0(lane, &bar_free[r % FLOW_STAGES], &done_l[c]), 0);
+                    if (readers + 1 == (u + 1) * n_d && r + FLOW_STAGES < R) {
                         slr::mbar_wait(&bar_free[r % FLOW_STAGES], (uint32_t)((r / FLOW_STAGES) & 1));   // acquire: every reader's loads
                         issue_row(r + FLOW_STAGES);
                     }
@@ -301,7 +310,7 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
                 if (live && !right) reinterpret_cast<float4 *>(s_pl)[x0 >> 2] = make_float4(ph[0], ph[1], ph[2], ph[3]);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_dec[c]);
+            mbar_arrive_lane0(lane, &bar_dec[c]);
             FLOW_TRACE_END(0, r);
         } else {
             // ================= query + emit job (FLOW_QPX * 32 left pixels) of row r = t - 1 - FLOW_LAG =================
@@ -383,17 +392,12 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
                 if (j[q] < W && p.match_k) p.match_k[o] = hit ? best[q] : -1;
             }
             __syncwarp();
-            int last = 0;
-            if (lane == 0) {
-                mbar_arrive(&bar_qry[c]);
-                last = count_job(&done_q[c]) + 1 == (u + 1) * n_q;
-            }
-            last = __shfl_sync(0xffffffffu, last, 0);
+            const bool last = __shfl_sync(0xffffffffu, arrive_count_lane0(lane, &bar_qry[c], &done_q[c]), 0) + 1 == (u + 1) * n_q;
             if (last) {  // nobody reads this row's tables any more: clear them for row r + FLOW_CTX
                 slr::mbar_wait(&bar_qry[c], (uint32_t)(u & 1));   // acquire: every query job's table reads
                 clear_tables(c, lane, 32);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_clr[c]);
+                mbar_arrive_lane0(lane, &bar_clr[c]);
             }
             FLOW_TRACE_END(last ? 2 : 1, r);
         }

@@ -49,6 +49,26 @@ def test_gray_num_bits_matches_oracle(oracle):
         assert slr_b200.gray_num_bits(n) == oracle.gray_num_bits(n)
 
 
+def test_strict_lookup_tables_equal_the_oracle_for_every_difference_pair(oracle):
+    """The kernels decode strict mode through two tables (reciprocal multiplier per b, wrapped phase per sign and quotient)
+    instead of the branches of Duke/mfreconstruct.cpp:246-261: every (G4-G2, G1-G3) pair against the C oracle and the
+    numpy restatement, in the kernels' 2^-24 fixed point."""
+    import ref_np
+    fx = slr_b200.strict_tables()
+    b, a = np.meshgrid(np.arange(-255, 256), np.arange(-255, 256), indexing="ij")
+    P, ok = ref_np.wrapped_phase(a, b)
+    want = np.where(ok, np.round(P.astype(np.float64) * 2.0 ** 24), -2.0 ** 31).astype(np.int64)
+    assert (P.astype(np.float64) * 2.0 ** 24 == np.round(P.astype(np.float64) * 2.0 ** 24)).all()   # exact in fixed point
+    assert (fx == want).all(), np.argwhere(fx != want)[:5]
+    for bb in (-255, -128, -3, -1, 0, 1, 2, 7, 254, 255):          # the C oracle on a band of b values
+        for aa in range(-255, 256):
+            ok_o, p_o = oracle.wrapped_phase_strict(aa, bb)
+            got = int(fx[bb + 255, aa + 255])
+            assert (got == -2 ** 31) == (not ok_o), (aa, bb)
+            if ok_o:
+                assert got == int(round(float(np.float32(p_o)) * 2.0 ** 24)), (aa, bb)
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():
