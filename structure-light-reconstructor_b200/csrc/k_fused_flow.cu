@@ -327,28 +327,28 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
             const FlowTables tab = tables_of(c, s_pl);
             int j[FLOW_QPX], best[FLOW_QPX];
             float ulx[FLOW_QPX], uly[FLOW_QPX], v[FLOW_QPX];
+            bool inside[FLOW_QPX];
+            constexpr bool FULL = WCT > 0 && WCT % (32 * FLOW_QPX) == 0;   // every query job lies inside the row
 #pragma unroll
             for (int q = 0; q < FLOW_QPX; q++) {
                 j[q] = (qidx * FLOW_QPX + q) * 32 + lane;
-                const bool inside = j[q] < W;
+                inside[q] = FULL || j[q] < W;
                 // undistortPoints maps of the left pixel (L2-resident, coalesced): in flight during the table walk
                 // (one 32-bit pixel index per load, widened once: pointer + unsigned + int is two 64-bit additions)
-                ulx[q] = inside ? __ldg(p.lx + (ri.map_px + (unsigned)j[q])) : 0.0f;
-                uly[q] = inside ? __ldg(p.ly + (ri.map_px + (unsigned)j[q])) : 0.0f;
-                v[q] = inside ? s_pl[j[q]] : slr::qnan();
+                ulx[q] = inside[q] ? __ldg(p.lx + (ri.map_px + (unsigned)j[q])) : 0.0f;
+                uly[q] = inside[q] ? __ldg(p.ly + (ri.map_px + (unsigned)j[q])) : 0.0f;
+                v[q] = inside[q] ? s_pl[j[q]] : slr::qnan();
             }
             static_assert(FLOW_QPX == 2, "the query job walks two chains per lane");
             first_match_x2<CLAMP>(tab, v[0], v[1], best[0], best[1]);
             float d[FLOW_QPX], X[FLOW_QPX], Y[FLOW_QPX], Z[FLOW_QPX];
 #pragma unroll
             for (int q = 0; q < FLOW_QPX; q++) {
-                // every pixel is reprojected unconditionally; misses get harmless inputs (disparity 1) and become NaN
+                // every pixel is reprojected unconditionally; a miss keeps its own (finite) undistorted position, gets
+                // the harmless disparity 1 and becomes NaN afterwards
                 const bool hit = best[q] != INT_MAX;
                 d[q] = 1.0f;
-                if (hit)
-                    d[q] = __fsub_rn(ulx[q], __ldg(p.rx + (ri.map_px + (unsigned)best[q])));
-                else
-                    ulx[q] = 0.0f, uly[q] = 0.0f;
+                if (hit) d[q] = __fsub_rn(ulx[q], __ldg(p.rx + (ri.map_px + (unsigned)best[q])));
             }
 #pragma unroll
             for (int q = 0; q < FLOW_QPX; q++)
@@ -360,7 +360,7 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
                 const float ox = hit ? X[q] : slr::qnan(), oy = hit ? Y[q] : slr::qnan(), oz = hit ? Z[q] : slr::qnan();
                 const unsigned o = ri.out_px + (unsigned)j[q];   // pixel offsets fit 32 bits (checked by the launcher)
                 if (p.n_t == 1) {
-                    if (j[q] < W) {
+                    if (inside[q]) {
                         float *dst = p.xyz + (size_t)o * 3;
                         dst[0] = ox;
                         dst[1] = oy;
@@ -386,10 +386,10 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
 #pragma unroll 1
                     for (int tg = 0; tg < p.n_t; tg++) {
                         if (4 * lane + 3 < n_f) *reinterpret_cast<float4 *>(p.xyz_t[tg] + f0 + 4 * lane) = v4;
-                        if (j[q] < W) p.valid_t[tg][o] = hit ? 1 : 0;
+                        if (inside[q]) p.valid_t[tg][o] = hit ? 1 : 0;
                     }
                 }
-                if (j[q] < W && p.match_k) p.match_k[o] = hit ? best[q] : -1;
+                if (inside[q] && p.match_k) p.match_k[o] = hit ? best[q] : -1;
             }
             __syncwarp();
             const bool last = __shfl_sync(0xffffffffu, arrive_count_lane0(lane, &bar_qry[c], &done_q[c]), 0) + 1 == (u + 1) * n_q;
