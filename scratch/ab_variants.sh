@@ -1,14 +1,17 @@
 #!/bin/bash
-# A/B of candidate builds (scratch/variants/libslr_<v>.so) on one box: parity first, then the bench's kernel-only leg.
-# usage (on the GPU box): scratch/ab_variants.sh v2 v1 v0
+# A/B of candidate builds (scratch/variants/libslr_<v>.so) on one box: the bench's kernel-only legs (main, noisy, corrected,
+# raw); a variant named with a trailing '+' runs the parity files first.
+# usage (on the GPU box): scratch/ab_variants.sh v6 v4b v5b+ v6
 mkdir -p gpurun_out
-for V in "$@"; do
+n=0
+for A in "$@"; do
+    V=${A%+}; n=$((n + 1))
     export SLR_B200_LIB=$PWD/scratch/variants/libslr_$V.so
-    if [ "$V" != v0 ]; then
+    if [ "$A" != "$V" ]; then
         (timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_routes.py -m gpu -x -q 2>&1 | tail -4) > gpurun_out/ab_${V}_pytest.log
         echo "== $V parity: $(tail -1 gpurun_out/ab_${V}_pytest.log)"
     fi
-    python bench.py --no-cpu --no-e2e --steps 30 > gpurun_out/ab_$V.json 2> gpurun_out/ab_$V.err
+    python bench.py --no-cpu --no-e2e --steps 20 > gpurun_out/ab_${V}_$n.json 2> gpurun_out/ab_${V}_$n.err
     python -c "
-import json; d=json.load(open('gpurun_out/ab_$V.json')); print('$V', round(d['value']), round(d['roofline']['frac'],4), round(d['ms_per_step'],4), [round(v['roofline_frac'],4) for v in d['config']['variants']], {k: round(v['ms_per_step'],3) for k,v in d['config']['raw_input'].items() if isinstance(v, dict)})"
+import json; d=json.load(open('gpurun_out/ab_${V}_$n.json')); print('$V', round(d['value']), round(d['roofline']['frac'],4), round(d['ms_per_step'],4), [round(v['ms_per_step'],4) for v in d['config']['variants']], {k: round(v['ms_per_step'],3) for k,v in d['config']['raw_input'].items() if isinstance(v, dict)})"
 done

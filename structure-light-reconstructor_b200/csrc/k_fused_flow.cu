@@ -77,8 +77,19 @@ __device__ long long g_flow_trace[TRACE_JOBS * 4];   // {type | row << 8 | warp 
 // acq_rel atomic costs a MEMBAR.ALL.CTA that also waits for the job's global stores.  (atom.inc, not atom.add: ptxas
 // wraps an add of a warp-uniform operand into its warp-aggregation sequence — vote, popc, lane masks — which costs more
 // than the atomic when a single lane executes it.)  Written as predicated PTX rather than `if (lane == 0)`: no default
-// value to materialise for the other lanes and one convergence region where a job does both.  Results are defined on
-// lane 0 only.
+// value to materialise for the other lanes and one convergence region where a job does both (1.7 % on rectified input).
+// Results are defined on lane 0 only.  The RAW instantiations keep the branch form below: with their rectify jobs they
+// sit at the 64-register limit, and the predicated form costs them two more spilled registers (4.31 vs 4.16 ms).
+__device__ __forceinline__ int count_job(int *p)
+{
+    unsigned old;
+    asm volatile("atom.relaxed.cta.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(old) : "r"(slr::smem_u32(p)) : "memory");
+    return (int)old;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(slr::smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_lane0(int lane, uint64_t *bar)
 {
     asm volatile("{\n.reg .pred p;\nsetp.eq.s32 p, %1, 0;\n@p mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n}"
@@ -230,7 +241,13 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
     // its decode jobs and practically never wait.
     for (;;) {
         // (atom.inc in plain PTX: atomicAdd / atom.add under `lane == 0` becomes a 14-instruction warp-aggregation sequence)
-        const int g = __shfl_sync(0xffffffffu, count_lane0(lane, job_ctr), 0);
+        int g = 0;
+        if (RAW) {
+            if (lane == 0) g = count_job(job_ctr);
+        } else {
+            g = count_lane0(lane, job_ctr);
+        }
+        g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= total_jobs) break;
         FLOW_TRACE_DRAW();
         const int t = (int)__umulhi((unsigned)g, js_magic);   // g / JS (exact for g * JS < 2^32, checked by the launcher)
@@ -260,7 +277,7 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
                                                 p.map2 + (size_t)cam * P, W, p.H, N, i, x, x < W, dst, (size_t)W, lane);
             }
             __syncwarp();
-            mbar_arrive_lane0(lane, &bar_stage[r % FLOW_STAGES]);
+            if (lane == 0) mbar_arrive(&bar_stage[r % FLOW_STAGES]);
             FLOW_TRACE_END(3, r);
             continue;
         }
@@ -290,7 +307,7 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
                 // which is the slack the bulk copies need to land before row r + 2 is drawn.
                 __syncwarp();
                 if (RAW) {
-                    mbar_arrive_lane0(lane, &bar_free[r % FLOW_STAGES]);
+                    if (lane == 0) mbar_arrive(&bar_free[r % FLOW_STAGES]);
                 } else {
                     const int readers = __shfl_sync(0xffffffffu, arrive_count_lane0(lane, &bar_free[r % FLOW_STAGES], &done_l[c]), 0);
                     if (readers + 1 == (u + 1) * n_d && r + FLOW_STAGES < R) {
@@ -310,7 +327,11 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
                 if (live && !right) reinterpret_cast<float4 *>(s_pl)[x0 >> 2] = make_float4(ph[0], ph[1], ph[2], ph[3]);
             }
             __syncwarp();
-            mbar_arrive_lane0(lane, &bar_dec[c]);
+            if (RAW) {
+                if (lane == 0) mbar_arrive(&bar_dec[c]);
+            } else {
+                mbar_arrive_lane0(lane, &bar_dec[c]);
+            }
             FLOW_TRACE_END(0, r);
         } else {
             // ================= query + emit job (FLOW_QPX * 32 left pixels) of row r = t - 1 - FLOW_LAG =================
@@ -327,28 +348,28 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
             const FlowTables tab = tables_of(c, s_pl);
             int j[FLOW_QPX], best[FLOW_QPX];
             float ulx[FLOW_QPX], uly[FLOW_QPX], v[FLOW_QPX];
-            bool inside[FLOW_QPX];
-            constexpr bool FULL = WCT > 0 && WCT % (32 * FLOW_QPX) == 0;   // every query job lies inside the row
 #pragma unroll
             for (int q = 0; q < FLOW_QPX; q++) {
                 j[q] = (qidx * FLOW_QPX + q) * 32 + lane;
-                inside[q] = FULL || j[q] < W;
+                const bool inside = j[q] < W;
                 // undistortPoints maps of the left pixel (L2-resident, coalesced): in flight during the table walk
                 // (one 32-bit pixel index per load, widened once: pointer + unsigned + int is two 64-bit additions)
-                ulx[q] = inside[q] ? __ldg(p.lx + (ri.map_px + (unsigned)j[q])) : 0.0f;
-                uly[q] = inside[q] ? __ldg(p.ly + (ri.map_px + (unsigned)j[q])) : 0.0f;
-                v[q] = inside[q] ? s_pl[j[q]] : slr::qnan();
+                ulx[q] = inside ? __ldg(p.lx + (ri.map_px + (unsigned)j[q])) : 0.0f;
+                uly[q] = inside ? __ldg(p.ly + (ri.map_px + (unsigned)j[q])) : 0.0f;
+                v[q] = inside ? s_pl[j[q]] : slr::qnan();
             }
             static_assert(FLOW_QPX == 2, "the query job walks two chains per lane");
             first_match_x2<CLAMP>(tab, v[0], v[1], best[0], best[1]);
             float d[FLOW_QPX], X[FLOW_QPX], Y[FLOW_QPX], Z[FLOW_QPX];
 #pragma unroll
             for (int q = 0; q < FLOW_QPX; q++) {
-                // every pixel is reprojected unconditionally; a miss keeps its own (finite) undistorted position, gets
-                // the harmless disparity 1 and becomes NaN afterwards
+                // every pixel is reprojected unconditionally; misses get harmless inputs (disparity 1) and become NaN
                 const bool hit = best[q] != INT_MAX;
                 d[q] = 1.0f;
-                if (hit) d[q] = __fsub_rn(ulx[q], __ldg(p.rx + (ri.map_px + (unsigned)best[q])));
+                if (hit)
+                    d[q] = __fsub_rn(ulx[q], __ldg(p.rx + (ri.map_px + (unsigned)best[q])));
+                else
+                    ulx[q] = 0.0f, uly[q] = 0.0f;
             }
 #pragma unroll
             for (int q = 0; q < FLOW_QPX; q++)
@@ -360,7 +381,7 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
                 const float ox = hit ? X[q] : slr::qnan(), oy = hit ? Y[q] : slr::qnan(), oz = hit ? Z[q] : slr::qnan();
                 const unsigned o = ri.out_px + (unsigned)j[q];   // pixel offsets fit 32 bits (checked by the launcher)
                 if (p.n_t == 1) {
-                    if (inside[q]) {
+                    if (j[q] < W) {
                         float *dst = p.xyz + (size_t)o * 3;
                         dst[0] = ox;
                         dst[1] = oy;
@@ -386,18 +407,31 @@ k_fused_flow(const FusedParams p, const int n_r_rt, const int n_d_rt, const int 
 #pragma unroll 1
                     for (int tg = 0; tg < p.n_t; tg++) {
                         if (4 * lane + 3 < n_f) *reinterpret_cast<float4 *>(p.xyz_t[tg] + f0 + 4 * lane) = v4;
-                        if (inside[q]) p.valid_t[tg][o] = hit ? 1 : 0;
+                        if (j[q] < W) p.valid_t[tg][o] = hit ? 1 : 0;
                     }
                 }
-                if (inside[q] && p.match_k) p.match_k[o] = hit ? best[q] : -1;
+                if (j[q] < W && p.match_k) p.match_k[o] = hit ? best[q] : -1;
             }
             __syncwarp();
-            const bool last = __shfl_sync(0xffffffffu, arrive_count_lane0(lane, &bar_qry[c], &done_q[c]), 0) + 1 == (u + 1) * n_q;
+            int last = 0;
+            if (RAW) {
+                if (lane == 0) {
+                    mbar_arrive(&bar_qry[c]);
+                    last = count_job(&done_q[c]) + 1 == (u + 1) * n_q;
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+            } else {
+                last = __shfl_sync(0xffffffffu, arrive_count_lane0(lane, &bar_qry[c], &done_q[c]), 0) + 1 == (u + 1) * n_q;
+            }
             if (last) {  // nobody reads this row's tables any more: clear them for row r + FLOW_CTX
                 slr::mbar_wait(&bar_qry[c], (uint32_t)(u & 1));   // acquire: every query job's table reads
                 clear_tables(c, lane, 32);
                 __syncwarp();
-                mbar_arrive_lane0(lane, &bar_clr[c]);
+                if (RAW) {
+                    if (lane == 0) mbar_arrive(&bar_clr[c]);
+                } else {
+                    mbar_arrive_lane0(lane, &bar_clr[c]);
+                }
             }
             FLOW_TRACE_END(last ? 2 : 1, r);
         }
